@@ -1,0 +1,334 @@
+/*
+ * pmgt_b200.h -- C ABI of libpmgt_b200.so: the B200 (sm_100a) implementation of
+ * the PMGT pre-training hot path (uoo723/PMGT).
+ *
+ * The reference is pure Python and has no FFI of its own; the boundary a
+ * maintainer binds is therefore this header, loaded with ctypes from the
+ * host-side mirror of the reference's Python API (pmgt_b200/*.py).  Every entry
+ * point cites the reference code it replaces (paths relative to the reference
+ * repository root).
+ *
+ * Conventions
+ *  - plain C: raw pointers, explicit sizes, no torch types;
+ *  - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *  - the caller owns every buffer; the library allocates nothing persistent
+ *    except the opaque pmgt_graph handle (and small per-device scratch);
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *    no entry point synchronises the device unless stated;
+ *  - return value: 0 on success, negative pmgt_status on failure, and
+ *    pmgt_last_error() then describes the failure (thread-local);
+ *  - bf16 buffers are `uint16_t` bit patterns (torch.bfloat16 storage);
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    fails with PMGT_ERR_CUDA.
+ */
+#ifndef PMGT_B200_H_
+#define PMGT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pmgt_status {
+  PMGT_OK = 0,
+  PMGT_ERR_INVALID = -1, /* bad argument (shape / alignment / range)            */
+  PMGT_ERR_CUDA = -2,    /* CUDA runtime / driver error or no device            */
+  PMGT_ERR_UNSUPPORTED = -3
+} pmgt_status;
+
+/* ABI version of this header; bumped on any signature change. */
+#define PMGT_B200_ABI_VERSION 1
+int pmgt_abi_version(void);
+const char* pmgt_last_error(void);
+
+/* ------------------------------------------------------------------------ */
+/* Item graph (CSR)                                                          */
+/* ------------------------------------------------------------------------ */
+/*
+ * Replaces the weighted nx.Graph the reference keeps on the host
+ * (pmgt/pmgt/trainer.py:34-41, used at pmgt/pmgt/datasets.py:27-32,167-180).
+ * Node-id space is the reference's: 0 = <pad>, 1 = <mask>, real nodes
+ * 2..num_nodes+1 (datasets.py:96-102).  indptr has num_nodes+3 entries and is
+ * indexed by node id (rows 0 and 1 are empty).  indices keeps the adjacency
+ * INSERTION order of the nx.Graph so that inverse-CDF positions mean the same
+ * neighbours as in the reference.  cdf[e] is the running softmax CDF of the
+ * edge weights of the row e belongs to (datasets.py:27-29 + numpy's legacy
+ * RandomState.choice: p.cumsum(), normalised, last entry forced to 1).
+ * The arrays are COPIED to the device; the host buffers may be freed.
+ */
+typedef struct pmgt_graph pmgt_graph;
+
+int pmgt_graph_create(pmgt_graph** out, int device, int64_t num_nodes, int64_t num_edges_directed,
+                      const int64_t* indptr_host, const int32_t* indices_host,
+                      const float* cdf_host);
+int pmgt_graph_destroy(pmgt_graph* g);
+int64_t pmgt_graph_num_nodes(const pmgt_graph* g);
+int64_t pmgt_graph_num_edges(const pmgt_graph* g);
+/* device pointers of the resident CSR (for tests / roofline byte accounting) */
+const int64_t* pmgt_graph_indptr(const pmgt_graph* g);
+const int32_t* pmgt_graph_indices(const pmgt_graph* g);
+const float* pmgt_graph_cdf(const pmgt_graph* g);
+
+/* ------------------------------------------------------------------------ */
+/* K1  MCNSampling: context sampler + pair selection (Philox4x32-10)          */
+/* ------------------------------------------------------------------------ */
+/*
+ * pmgt_sample_contexts replaces _sample_context_neigh + _get_attention_mask +
+ * get_input_tensor (pmgt/pmgt/datasets.py:14-79) for a whole batch of roots.
+ *
+ *   roots[n]     node id of the n-th context's target node
+ *   ctx_keys[n]  64-bit RNG sub-stream id of that context (counter words 2,3)
+ *   hops_host    hop sampling sizes (depth entries, host memory), e.g. {16,8,4}
+ *   out_ids      [n_ctx][max_ctx+1] int64: root, then the top-`max_ctx`
+ *                neighbours by score (frequency x hop weight, ties broken by
+ *                first appearance), right-padded with 0
+ *   out_mask     [n_ctx][max_ctx+1] float32: 1 for root + real neighbours
+ *   out_visited_deg (optional, may be NULL) [n_ctx] int64: sum of the degrees
+ *                of every row the context visited (roofline byte accounting)
+ *
+ * Draw d of a context uses Philox counter (d/4, PMGT_STREAM_CTX, key_lo, key_hi)
+ * word d%4 under key (seed_lo, seed_hi); u = (word >> 8) * 2^-24; the neighbour
+ * is row[upper_bound(cdf_row, u)].  d enumerates hop 1 first, then hop 2 in
+ * parent order, ...  oracle/philox_sampler.c replays exactly this on the CPU.
+ */
+#define PMGT_STREAM_CTX 0u
+#define PMGT_STREAM_POS 1u
+#define PMGT_STREAM_NEG 2u
+#define PMGT_MAX_NEG_ATTEMPTS 64
+
+int pmgt_sample_contexts(const pmgt_graph* g, const int64_t* roots, const int64_t* ctx_keys,
+                         int64_t n_ctx, const int32_t* hops_host, int depth, int max_ctx,
+                         uint64_t seed, int64_t* out_ids, float* out_mask,
+                         int64_t* out_visited_deg, void* stream);
+
+/*
+ * pmgt_sample_pairs replaces PMGTDataset._sample_neigh / _sample_neg /
+ * _get_label_tensor (pmgt/pmgt/datasets.py:125-146,159,167-183).
+ * For target b: n_pos = min(max_pos, deg) distinct neighbours (partial
+ * Fisher-Yates on stream PMGT_STREAM_POS), then n_neg = max(min_neg,
+ * max_total - n_pos) uniform node ids in [2, N+2) rejected while adjacent to
+ * the target (stream PMGT_STREAM_NEG, at most PMGT_MAX_NEG_ATTEMPTS attempts
+ * per negative).  Rows are written at a fixed stride `pair_stride`
+ * (>= max_pos + max(min_neg, max_total)); unused slots are 0.
+ *   out_pairs [n_tgt][pair_stride] int64, out_labels [n_tgt][pair_stride] f32,
+ *   out_num_pairs [n_tgt] int64.
+ */
+int pmgt_sample_pairs(const pmgt_graph* g, const int64_t* targets, const int64_t* tgt_keys,
+                      int64_t n_tgt, int max_pos, int min_neg, int max_total, int pair_stride,
+                      uint64_t seed, int64_t* out_pairs, float* out_labels,
+                      int64_t* out_num_pairs, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* GEMM on tcgen05 tensor cores (building block of K2 / K3 / K5)              */
+/* ------------------------------------------------------------------------ */
+/*
+ * D[M,N] (+)= op(A)[M,K] * op(B)[K,N], bf16 operands, fp32 accumulation in
+ * TMEM, TMA- or cp.async-gather-staged operands.  Replaces the cuBLAS GEMMs
+ * behind nn.Linear in PMGTEmbeddings / PMGTSelfAttention / BertSelfOutput /
+ * BertIntermediate / BertOutput / PMGTNodeConstructLoss
+ * (pmgt/pmgt/modeling_pmgt.py:195-198,429-433,371,322-325,566-569) and their
+ * autograd backward GEMMs.
+ *
+ * Operand storage ("major"):
+ *   a_mn = 0: A stored row-major [M][K] (lda = row pitch in elements)
+ *   a_mn = 1: A stored row-major [K][M]  (i.e. A^T is what is in memory)
+ *   b_mn = 0: B stored row-major [N][K]  (nn.Linear weight layout)
+ *   b_mn = 1: B stored row-major [K][N]
+ * Gather: if a_rows != NULL the stored rows of A (a_mn=0: the M rows; a_mn=1:
+ * the K rows) are fetched through the index vector, row r of the operand is
+ * a + a_rows[r]*lda.  Same for b_rows.  Indices are int64; index < 0 or row
+ * beyond the logical extent reads as zeros.
+ *
+ * Epilogue (flags in `epi`): v = acc * alpha; +bias[n]; GELU(erf) with the
+ * pre-activation stored to `aux`; or multiply by gelu'(aux[m][n]); + addend;
+ * store as bf16 (out_bf16), fp32 (out_f32) or atomically accumulate into fp32
+ * (PMGT_EPI_ATOMIC, used with split_k > 1 for weight gradients).
+ */
+#define PMGT_EPI_BIAS 1u
+#define PMGT_EPI_GELU 2u      /* out = gelu(v); aux_out (bf16) = v            */
+#define PMGT_EPI_GELU_BWD 4u  /* out = v * gelu'(aux_in[m][n])                */
+#define PMGT_EPI_ADDEND 8u    /* out += addend[m][n] (bf16)                   */
+#define PMGT_EPI_OUT_F32 16u  /* store fp32 instead of bf16                   */
+#define PMGT_EPI_ATOMIC 32u   /* fp32 atomicAdd into out (implies OUT_F32)    */
+
+typedef struct pmgt_gemm_args {
+  int64_t M, N, K;
+  const uint16_t* a; int64_t lda; int a_mn; const int64_t* a_rows; int64_t a_src_rows;
+  const uint16_t* b; int64_t ldb; int b_mn; const int64_t* b_rows; int64_t b_src_rows;
+  void* out; int64_t ldo;
+  const float* bias;            /* [N] fp32                                   */
+  const uint16_t* addend; int64_t ld_addend;
+  uint16_t* aux; int64_t ld_aux; /* GELU: written; GELU_BWD: read             */
+  float alpha;
+  uint32_t epi;
+  int split_k;                  /* >= 1                                        */
+} pmgt_gemm_args;
+
+int pmgt_gemm_bf16(const pmgt_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* K2  multimodal feature path                                               */
+/* ------------------------------------------------------------------------ */
+/*
+ * The gather + per-modality projection GEMMs go through pmgt_gemm_bf16 with
+ * a_rows = node ids (replaces get_input_feat_embeds, pmgt/pmgt/utils.py:43-50,
+ * and feat_linear, modeling_pmgt.py:195-198).  pmgt_embed_fuse_fwd/bwd are the
+ * rest of PMGTEmbeddings.forward (modeling_pmgt.py:199-208): modality
+ * attention softmax(Linear(tanh([e_v;e_t]))), weighted sum, + position + role
+ * embedding, LayerNorm, dropout.
+ *   ev, et      [T][H] bf16 projected features (T = rows * L tokens)
+ *   w_att [2][2H], b_att [2], pos [max_pos][H], role [2][H], ln_g/ln_b [H] fp32
+ *   x_out       [T][H] bf16
+ * Backward recomputes the forward from ev/et and produces dev/det (bf16) and
+ * fp32 gradients ACCUMULATED (atomicAdd) into d_w_att, d_b_att, d_pos, d_role,
+ * d_ln_g, d_ln_b, d_bias_v, d_bias_t (column sums of dev/det).
+ */
+typedef struct pmgt_embed_args {
+  int64_t rows; int L; int H;
+  const uint16_t* ev; const uint16_t* et;
+  const float* w_att; const float* b_att; const float* pos; const float* role;
+  const float* ln_g; const float* ln_b; float ln_eps;
+  float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
+  uint16_t* x_out;            /* fwd */
+  const uint16_t* dx;         /* bwd: [T][H] bf16 */
+  uint16_t* dev; uint16_t* det;
+  float* d_w_att; float* d_b_att; float* d_pos; float* d_role; float* d_ln_g; float* d_ln_b;
+  float* d_bias_v; float* d_bias_t;
+} pmgt_embed_args;
+
+int pmgt_embed_fuse_fwd(const pmgt_embed_args* a, void* stream);
+int pmgt_embed_fuse_bwd(const pmgt_embed_args* a, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* K3  encoder layer pieces                                                  */
+/* ------------------------------------------------------------------------ */
+/*
+ * Dual-softmax "diversity promoting" attention core of PMGTSelfAttention
+ * (modeling_pmgt.py:435-526), one (sequence, head) per warp:
+ *   S1 = 1 - C C^T / (|C||C|^T) + I + mask ; P1 = dropout(softmax(S1))
+ *   S2 = Q K^T / sqrt(dh) + mask           ; P2 = dropout(softmax(S2))
+ *   ctx = (beta P1 + (1-beta) P2) V
+ * qkvc is [T][4H] bf16 with column blocks [Q | K | V | C]; mask is the
+ * reference's 0/1 attention mask [rows][L] fp32 (the additive -10000 key mask
+ * of transformers 4.11.2 get_extended_attention_mask is applied inside).
+ * Backward recomputes P1/P2 and writes dqkvc [T][4H] bf16 and accumulates the
+ * bias gradient d_bias_qkvc [4H] (fp32 atomicAdd) when non-NULL.
+ */
+typedef struct pmgt_attn_args {
+  int64_t rows; int L; int H; int heads; float beta;
+  const uint16_t* qkvc; const float* mask;
+  float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
+  uint16_t* ctx;               /* fwd out [T][H] */
+  const uint16_t* dctx;        /* bwd in  [T][H] */
+  uint16_t* dqkvc;             /* bwd out [T][4H] */
+  float* d_bias_qkvc;          /* bwd out [4H], accumulated */
+} pmgt_attn_args;
+
+int pmgt_attn_core_fwd(const pmgt_attn_args* a, void* stream);
+int pmgt_attn_core_bwd(const pmgt_attn_args* a, void* stream);
+
+/*
+ * y = LayerNorm(dropout(o) + res) -- BertSelfOutput / BertOutput after their
+ * dense layer (transformers BertSelfOutput/BertOutput, called at
+ * modeling_pmgt.py:371,324).  o already contains the dense bias.
+ * Backward: given dy, recomputes z = dropout(o)+res and writes dz (bf16, the
+ * gradient wrt `res`; the gradient wrt `o` is dz with the dropout mask applied,
+ * written to d_o when dropout_p > 0, else d_o may alias dz) and accumulates
+ * d_g, d_b (LayerNorm) and d_bias (column sums of d_o) in fp32.
+ */
+typedef struct pmgt_resln_args {
+  int64_t T; int H;
+  const uint16_t* o; const uint16_t* res;
+  const float* ln_g; const float* ln_b; float ln_eps;
+  float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
+  uint16_t* y; float* y_f32;   /* fwd out; y_f32 optional */
+  const uint16_t* dy; const float* dy_f32; /* bwd in: dy (bf16) and/or dy_f32 are summed */
+  uint16_t* dz; uint16_t* d_o;
+  float* d_g; float* d_b; float* d_bias;
+} pmgt_resln_args;
+
+int pmgt_res_ln_fwd(const pmgt_resln_args* a, void* stream);
+int pmgt_res_ln_bwd(const pmgt_resln_args* a, void* stream);
+
+/* column sums: out[n] += sum_t x[t][n]  (bias gradients), x bf16 [T][N] */
+int pmgt_colsum_bf16(const uint16_t* x, int64_t T, int64_t N, int64_t ldx, float* out, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* K4  graph-structure reconstruction loss                                   */
+/* ------------------------------------------------------------------------ */
+/*
+ * PMGTGraphConstructLoss + the per-target loop of PMGT.forward
+ * (modeling_pmgt.py:537-546, models.py:104-127) for the whole batch at once.
+ *   tgt_h   [B][ld_t] fp32 : position-0 hidden state of each target row
+ *   pair_h  [SP][ld_p] fp32: position-0 hidden state of each pair row
+ *   pair_off[B+1] int64    : prefix sum of num_pairs
+ *   labels  [SP] fp32
+ * fwd: logits [SP] fp32, loss_out[0] = mean_b mean_p BCEWithLogits.
+ * bwd: d_tgt / d_pair (same layout as the inputs, overwritten) scaled by
+ *      *grad_out (device scalar).
+ */
+typedef struct pmgt_gsr_args {
+  int64_t B; int64_t SP; int H;
+  const float* tgt_h; int64_t ld_t; const float* pair_h; int64_t ld_p;
+  const int64_t* pair_off; const float* labels;
+  float* logits; float* loss_out;
+  const float* grad_out; float* d_tgt; float* d_pair;
+} pmgt_gsr_args;
+
+int pmgt_gsr_fwd(const pmgt_gsr_args* a, void* stream);
+int pmgt_gsr_bwd(const pmgt_gsr_args* a, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* K5  node-feature reconstruction loss                                      */
+/* ------------------------------------------------------------------------ */
+/*
+ * MSE part of PMGTNodeConstructLoss (modeling_pmgt.py:566-569) for ONE
+ * modality: proj [Mm][D] bf16 (= Linear(h_masked), produced by pmgt_gemm_bf16)
+ * against rows of the frozen feature table gathered by target_ids
+ * (models.py:150,159).  fwd accumulates  weight * mean((proj-tgt)^2)  into
+ * loss_out[0]; bwd writes dproj = *grad_out * weight * 2/(Mm*D) * (proj-tgt).
+ * Mm == 0 contributes NaN like nn.MSELoss over an empty tensor.
+ */
+typedef struct pmgt_nfr_args {
+  int64_t Mm; int64_t D;
+  const uint16_t* proj; int64_t ld_proj;
+  const uint16_t* table; int64_t ld_table; const int64_t* target_ids;
+  float weight;
+  float* loss_out;
+  const float* grad_out; uint16_t* dproj;
+} pmgt_nfr_args;
+
+int pmgt_nfr_mse_fwd(const pmgt_nfr_args* a, void* stream);
+int pmgt_nfr_mse_bwd(const pmgt_nfr_args* a, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* K6  optimizer + utility                                                   */
+/* ------------------------------------------------------------------------ */
+/*
+ * Dense branch of DenseSparseAdamW.step (pmgt/optimizers.py:256-270) over a
+ * flat fp32 parameter buffer: p *= 1 - lr*wd[i]; m = b1 m + (1-b1) g;
+ * v = b2 v + (1-b2) g^2; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps).
+ * `decay_mask` (uint8, per element) selects the weight-decay group
+ * (base_trainer.py:35-59: no decay for names containing "bias" or
+ * "LayerNorm.weight").  grad_scale multiplies g first (1/world_size after an
+ * allreduce-sum, gradient clipping coefficient, ...); if grad_scale_dev is
+ * non-NULL the device scalar is used instead.
+ */
+int pmgt_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t* decay_mask,
+                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int64_t step, float grad_scale, const float* grad_scale_dev, void* stream);
+
+/* fp32 -> bf16 cast of a flat buffer (weights shadow / feature tables) */
+int pmgt_cast_f32_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);
+/* sum of squares of a flat fp32 buffer accumulated into out[0] (clip_grad_norm_) */
+int pmgt_sumsq_f32(const float* x, int64_t n, float* out, void* stream);
+/* out[r][:] = src[idx[r]][:]   (bf16 rows, D elements, D % 8 == 0) */
+int pmgt_gather_rows_bf16(const uint16_t* src, int64_t ld_src, const int64_t* idx, int64_t n_rows,
+                          int64_t D, uint16_t* out, int64_t ld_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMGT_B200_H_ */

@@ -1,0 +1,37 @@
+// Library-wide plumbing of libpmgt_b200.so: thread-local error string, ABI
+// version, cached device properties.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace pmgt {
+
+static thread_local char g_err[512] = {0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+}  // namespace pmgt
+
+extern "C" {
+int pmgt_abi_version(void) { return PMGT_B200_ABI_VERSION; }
+const char* pmgt_last_error(void) { return pmgt::g_err; }
+}

@@ -1,0 +1,131 @@
+// Shared helpers for libpmgt_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pmgt_b200.h"
+
+namespace pmgt {
+
+void set_error(const char* fmt, ...);
+
+#define PMGT_CHECK_CUDA(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      pmgt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                      __LINE__);                                                           \
+      return PMGT_ERR_CUDA;                                                                \
+    }                                                                                      \
+  } while (0)
+
+#define PMGT_REQUIRE(cond, ...)                                                            \
+  do {                                                                                     \
+    if (!(cond)) {                                                                         \
+      pmgt::set_error(__VA_ARGS__);                                                        \
+      return PMGT_ERR_INVALID;                                                             \
+    }                                                                                      \
+  } while (0)
+
+#define PMGT_LAUNCH_CHECK()                                                                \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess) {                                                               \
+      pmgt::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
+                      __LINE__);                                                           \
+      return PMGT_ERR_CUDA;                                                                \
+    }                                                                                      \
+  } while (0)
+
+int num_sms();  // SM count of the current device (cached)
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  The same function is restated in
+// plain C in oracle/philox_sampler.c; the two must agree bit for bit.
+// ---------------------------------------------------------------------------
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                         uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n1 = lo1;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    uint32_t n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+__host__ __device__ __forceinline__ uint32_t philox_word(const Philox4& p, int i) {
+  return i == 0 ? p.x : (i == 1 ? p.y : (i == 2 ? p.z : p.w));
+}
+
+// dropout keep decision for element `idx` of dropout site `site`.
+// keep with probability 1-p; the caller scales kept values by 1/(1-p).
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint64_t idx, float p) {
+  Philox4 r = philox4x32_10((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), site, 0x5eedu,
+                            (uint32_t)seed, (uint32_t)(seed >> 32));
+  uint32_t wsel = philox_word(r, (int)(idx & 3));
+  float u = (float)(wsel >> 8) * (1.0f / 16777216.0f);
+  return u >= p;
+}
+
+// ---------------------------------------------------------------------------
+// small device utilities
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) {
+  return __uint_as_float(((uint32_t)b) << 16);
+}
+__device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t v, float& lo, float& hi) {
+  lo = __uint_as_float(v << 16);
+  hi = __uint_as_float(v & 0xffff0000u);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float kInvSqrt2Pi = 0.39894228040143267794f;
+  float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  return cdf + x * kInvSqrt2Pi * __expf(-0.5f * x * x);
+}
+
+}  // namespace pmgt

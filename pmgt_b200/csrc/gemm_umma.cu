@@ -1,0 +1,531 @@
+// tcgen05 (UMMA) GEMM for sm_100a: bf16 operands, fp32 accumulators in TMEM.
+//
+//   D[M,N] (+)= op(A)[M,K] * op(B)[K,N]
+//
+// CTA tile 128 x 128, K block 64, 128B-swizzled shared-memory slabs.  Operands
+// are staged either by TMA (cp.async.bulk.tensor.2d, hardware swizzle) or, when
+// rows are fetched through an index vector (the multimodal feature gather of
+// PMGT, pmgt/pmgt/utils.py:43-50), by 16-byte cp.async copies that write the
+// same swizzle pattern by hand, so the gathered [tokens, 2304] feature matrix
+// is never materialised in HBM.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// single-thread MMA issuer, warps 2..5 = cp.async gather producers (if any
+// operand is gathered) and then the epilogue (one accumulator row per thread,
+// tcgen05.ld 32x32b).
+//
+// Shared-memory slab layouts (one "slab" = rows of 128 bytes = 64 bf16):
+//   K-major operand  : 1 slab of 128 rows (row = M/N index, 64 K elements).
+//                      UMMA desc: SWIZZLE_128B, SBO = 1024 B; K advance = +32 B.
+//   MN-major operand : 2 slabs of 64 rows (row = K index, 64 M/N elements each).
+//                      UMMA desc: SWIZZLE_128B, LBO = 8192 B (next 64 M/N),
+//                      SBO = 1024 B (next 8 K rows); K advance = +2048 B.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pmgt {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 192;
+constexpr int kOperandStageBytes = 128 * BK * 2;  // 16 KiB for either layout
+constexpr int kTmemCols = 128;
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) __trap();  // a lost arrival becomes an error, not a hang
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar,
+                                            int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//  [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct GemmKernelArgs {
+  int M, N, K;
+  // gather sources (used when the corresponding operand is gathered)
+  const uint16_t* a_src; long long lda; const long long* a_rows; long long a_src_rows;
+  const uint16_t* b_src; long long ldb; const long long* b_rows; long long b_src_rows;
+  void* out; long long ldo;
+  const float* bias;
+  const uint16_t* addend; long long ld_addend;
+  uint16_t* aux; long long ld_aux;
+  float alpha;
+  uint32_t epi;
+  int kb_per_split;  // k-blocks per blockIdx.z
+};
+
+struct GemmSmem {
+  uint64_t full[4];
+  uint64_t empty[4];
+  uint64_t accum_full;
+  uint32_t tmem_base;
+};
+
+// Fill one 128B-swizzled slab with `nrows` gathered row segments of 64 bf16.
+//   slab row r <- src[row_index(r)] [col0 .. col0+64)
+template <int ROWS_PER_THREAD>
+__device__ __forceinline__ void gather_slab(uint32_t slab, int t, const uint16_t* __restrict__ src, long long ld,
+                                            const long long* rows /*ROWS_PER_THREAD resolved row ids, <0 = zero*/,
+                                            int col0, int col_limit) {
+  const int c = t & 7;
+  const int col = col0 + c * 8;
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+    const int r = (t >> 3) + 16 * i;
+    const long long row = rows[i];
+    const bool ok = row >= 0 && col < col_limit;
+    const void* g = ok ? (const void*)(src + row * ld + col) : (const void*)src;
+    cp_async_16(slab + r * 128 + ((c ^ (r & 7)) << 4), g, ok ? 16u : 0u);
+  }
+}
+
+template <bool A_MN, bool B_MN, bool GATHER_A, bool GATHER_B, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmKernelArgs p) {
+  static_assert(!(GATHER_A && A_MN), "gathered A must be K-major");
+  static_assert(!(GATHER_B && !B_MN), "gathered B must be MN-major");
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // 1024-byte alignment is required by SWIZZLE_128B
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + STAGES * kOperandStageBytes;
+  GemmSmem* sh = reinterpret_cast<GemmSmem*>(smem + 2 * STAGES * kOperandStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int num_kb_total = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  int kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > num_kb_total) kb_end = num_kb_total;
+  const int num_kb = kb_end - kb_begin;
+  if (num_kb <= 0) return;  // uniform for the whole CTA
+
+  constexpr bool kAnyGather = GATHER_A || GATHER_B;
+  constexpr uint32_t kTmaBytes = (GATHER_A ? 0u : (uint32_t)kOperandStageBytes) + (GATHER_B ? 0u : (uint32_t)kOperandStageBytes);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&sh->full[s], 1u + (kAnyGather ? 128u : 0u));
+      mbar_init(&sh->empty[s], 1u);
+    }
+    mbar_init(&sh->accum_full, 1u);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                 "r"((uint32_t)kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&sh->empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&sh->full[s], kTmaBytes);
+        const int k0 = (kb_begin + i) * BK;
+        if (!GATHER_A) {
+          const uint32_t dst = smem_u32(smem_a + s * kOperandStageBytes);
+          if (!A_MN) {
+            tma_load_2d(dst, &tmap_a, &sh->full[s], k0, m0);
+          } else {
+            tma_load_2d(dst, &tmap_a, &sh->full[s], m0, k0);
+            tma_load_2d(dst + 8192, &tmap_a, &sh->full[s], m0 + 64, k0);
+          }
+        }
+        if (!GATHER_B) {
+          const uint32_t dst = smem_u32(smem_b + s * kOperandStageBytes);
+          if (!B_MN) {
+            tma_load_2d(dst, &tmap_b, &sh->full[s], k0, n0);
+          } else {
+            tma_load_2d(dst, &tmap_b, &sh->full[s], n0, k0);
+            tma_load_2d(dst + 8192, &tmap_b, &sh->full[s], n0 + 64, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&sh->full[s], ph);
+        tcgen05_fence_after();
+        const uint32_t a_base = smem_u32(smem_a + s * kOperandStageBytes);
+        const uint32_t b_base = smem_u32(smem_b + s * kOperandStageBytes);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = A_MN ? umma_desc(a_base + k * 2048, 8192, 1024) : umma_desc(a_base + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? umma_desc(b_base + k * 2048, 8192, 1024) : umma_desc(b_base + k * 32, 16, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&sh->empty[s]);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(&sh->accum_full);
+    }
+  } else {
+    // ===================== gather producers, then epilogue =====================
+    const int t = threadIdx.x - 64;  // 0..127
+    if (kAnyGather) {
+      long long a_rows_reg[8];
+      if (GATHER_A) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + (t >> 3) + 16 * i;
+          long long row = -1;
+          if (m < p.M) {
+            row = p.a_rows[m];
+            if (row >= p.a_src_rows) row = -1;
+          }
+          a_rows_reg[i] = row;
+        }
+      }
+      constexpr int LAG = STAGES - 1;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&sh->empty[s], ph ^ 1u);
+        const int k0 = (kb_begin + i) * BK;
+        if (GATHER_A) {
+          gather_slab<8>(smem_u32(smem_a + s * kOperandStageBytes), t, p.a_src, p.lda, a_rows_reg, k0, p.K);
+        }
+        if (GATHER_B) {
+          long long b_rows_reg[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int kk = k0 + (t >> 3) + 16 * j;
+            long long row = -1;
+            if (kk < p.K) {
+              row = p.b_rows[kk];
+              if (row >= p.b_src_rows) row = -1;
+            }
+            b_rows_reg[j] = row;
+          }
+          const uint32_t bs = smem_u32(smem_b + s * kOperandStageBytes);
+          gather_slab<4>(bs, t, p.b_src, p.ldb, b_rows_reg, n0, p.N);
+          gather_slab<4>(bs + 8192, t, p.b_src, p.ldb, b_rows_reg, n0 + 64, p.N);
+        }
+        cp_async_commit();
+        if (i >= LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async_smem();
+          mbar_arrive(&sh->full[(i - LAG) % STAGES]);
+        }
+      }
+      // drain
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      for (int i = (num_kb > LAG ? num_kb - LAG : 0); i < num_kb; ++i) mbar_arrive(&sh->full[i % STAGES]);
+    }
+
+    // ---- epilogue: thread owns accumulator row (quarter*32 + lane) ----
+    mbar_wait(&sh->accum_full, 0u);
+    tcgen05_fence_after();
+    const int quarter = warp & 3;
+    const int m = m0 + quarter * 32 + lane;
+    const bool row_ok = m < p.M;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t epi = p.epi;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld_x32(taddr + (uint32_t)c0, r);
+      tmem_wait_ld();
+      if (!row_ok) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = n0 + c0 + g * 8;
+        if (n >= p.N) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
+        if (epi & PMGT_EPI_BIAS) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (epi & PMGT_EPI_GELU) {
+          uint4 pre;
+          pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
+          pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(p.aux + (long long)m * p.ld_aux + n) = pre;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (epi & PMGT_EPI_GELU_BWD) {
+          const uint4 pre = *reinterpret_cast<const uint4*>(p.aux + (long long)m * p.ld_aux + n);
+          float x[8];
+          unpack_bf16x2(pre.x, x[0], x[1]); unpack_bf16x2(pre.y, x[2], x[3]);
+          unpack_bf16x2(pre.z, x[4], x[5]); unpack_bf16x2(pre.w, x[6], x[7]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(x[j]);
+        }
+        if (epi & PMGT_EPI_ADDEND) {
+          const uint4 ad = *reinterpret_cast<const uint4*>(p.addend + (long long)m * p.ld_addend + n);
+          float x[8];
+          unpack_bf16x2(ad.x, x[0], x[1]); unpack_bf16x2(ad.y, x[2], x[3]);
+          unpack_bf16x2(ad.z, x[4], x[5]); unpack_bf16x2(ad.w, x[6], x[7]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += x[j];
+        }
+        if (epi & PMGT_EPI_ATOMIC) {
+          float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
+        } else if (epi & PMGT_EPI_OUT_F32) {
+          float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (long long)m * p.ldo + n) = o;
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2D bf16 tensor map over a row-major [rows][inner] matrix with row pitch ld (elements)
+static int make_tmap(CUtensorMap* map, const void* base, long long inner, long long rows, long long ld,
+                     int box_inner, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return PMGT_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%lld rows=%lld ld=%lld", (int)r, base, inner, rows, ld);
+    return PMGT_ERR_CUDA;
+  }
+  return PMGT_OK;
+}
+
+template <bool A_MN, bool B_MN, bool GA, bool GB, int STAGES>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelArgs& ka, dim3 grid, cudaStream_t st) {
+  auto kern = umma_gemm_kernel<A_MN, B_MN, GA, GB, STAGES>;
+  const int smem = 2 * STAGES * kOperandStageBytes + (int)sizeof(GemmSmem) + 1024;
+  static bool configured = false;  // one flag per instantiation
+  if (!configured) {
+    PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, ka);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+}  // namespace pmgt
+
+using namespace pmgt;
+
+extern "C" int pmgt_gemm_bf16(const pmgt_gemm_args* a, void* stream) {
+  PMGT_REQUIRE(a, "pmgt_gemm_bf16: null args");
+  PMGT_REQUIRE(a->M >= 0 && a->N >= 0 && a->K >= 0 && a->M < (1ll << 31) && a->N < (1ll << 31) && a->K < (1ll << 31),
+               "pmgt_gemm_bf16: bad shape M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K);
+  if (a->M == 0 || a->N == 0) return PMGT_OK;
+  PMGT_REQUIRE(a->K > 0, "pmgt_gemm_bf16: K must be > 0");
+  PMGT_REQUIRE(a->a && a->b && a->out, "pmgt_gemm_bf16: null operand");
+  PMGT_REQUIRE(a->N % 8 == 0, "pmgt_gemm_bf16: N (%lld) must be a multiple of 8", (long long)a->N);
+  PMGT_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "pmgt_gemm_bf16: lda/ldb must be multiples of 8 elements");
+  PMGT_REQUIRE(((uintptr_t)a->a & 15) == 0 && ((uintptr_t)a->b & 15) == 0 && ((uintptr_t)a->out & 15) == 0,
+               "pmgt_gemm_bf16: operands must be 16-byte aligned");
+  const bool ga = a->a_rows != nullptr, gb = a->b_rows != nullptr;
+  PMGT_REQUIRE(!(ga && a->a_mn), "pmgt_gemm_bf16: gathered A must be K-major (a_mn=0)");
+  PMGT_REQUIRE(!(gb && !a->b_mn), "pmgt_gemm_bf16: gathered B must be MN-major (b_mn=1)");
+  PMGT_REQUIRE(!(ga && gb), "pmgt_gemm_bf16: at most one gathered operand");
+  PMGT_REQUIRE(!ga || a->K % 8 == 0, "pmgt_gemm_bf16: gathered A needs K %% 8 == 0");
+  uint32_t epi = a->epi;
+  if (epi & PMGT_EPI_ATOMIC) epi |= PMGT_EPI_OUT_F32;
+  PMGT_REQUIRE(!(epi & PMGT_EPI_BIAS) || a->bias, "pmgt_gemm_bf16: EPI_BIAS without bias");
+  PMGT_REQUIRE(!(epi & (PMGT_EPI_GELU | PMGT_EPI_GELU_BWD)) || (a->aux && a->ld_aux % 8 == 0),
+               "pmgt_gemm_bf16: GELU epilogue needs aux with ld_aux %% 8 == 0");
+  PMGT_REQUIRE(!(epi & PMGT_EPI_ADDEND) || (a->addend && a->ld_addend % 8 == 0),
+               "pmgt_gemm_bf16: EPI_ADDEND needs addend with ld %% 8 == 0");
+  PMGT_REQUIRE(a->ldo % ((epi & PMGT_EPI_OUT_F32) ? 4 : 8) == 0, "pmgt_gemm_bf16: ldo alignment");
+  int split = a->split_k < 1 ? 1 : a->split_k;
+  PMGT_REQUIRE(split == 1 || (epi & PMGT_EPI_ATOMIC), "pmgt_gemm_bf16: split_k > 1 requires PMGT_EPI_ATOMIC");
+  PMGT_REQUIRE(split == 1 || !(epi & (PMGT_EPI_BIAS | PMGT_EPI_GELU | PMGT_EPI_GELU_BWD | PMGT_EPI_ADDEND)),
+               "pmgt_gemm_bf16: split_k > 1 supports only the plain atomic epilogue");
+
+  const int num_kb = (int)((a->K + BK - 1) / BK);
+  if (split > num_kb) split = num_kb;
+  const int kb_per = (num_kb + split - 1) / split;
+  split = (num_kb + kb_per - 1) / kb_per;
+
+  CUtensorMap ta, tb;
+  memset(&ta, 0, sizeof(ta));
+  memset(&tb, 0, sizeof(tb));
+  int rc;
+  if (!ga) {
+    rc = a->a_mn ? make_tmap(&ta, a->a, a->M, a->K, a->lda, 64, 64) : make_tmap(&ta, a->a, a->K, a->M, a->lda, 64, 128);
+    if (rc) return rc;
+  }
+  if (!gb) {
+    rc = a->b_mn ? make_tmap(&tb, a->b, a->N, a->K, a->ldb, 64, 64) : make_tmap(&tb, a->b, a->K, a->N, a->ldb, 64, 128);
+    if (rc) return rc;
+  }
+  GemmKernelArgs ka;
+  ka.M = (int)a->M; ka.N = (int)a->N; ka.K = (int)a->K;
+  ka.a_src = a->a; ka.lda = a->lda; ka.a_rows = (const long long*)a->a_rows; ka.a_src_rows = a->a_src_rows;
+  ka.b_src = a->b; ka.ldb = a->ldb; ka.b_rows = (const long long*)a->b_rows; ka.b_src_rows = a->b_src_rows;
+  ka.out = a->out; ka.ldo = a->ldo; ka.bias = a->bias;
+  ka.addend = a->addend; ka.ld_addend = a->ld_addend; ka.aux = a->aux; ka.ld_aux = a->ld_aux;
+  ka.alpha = a->alpha; ka.epi = epi; ka.kb_per_split = kb_per;
+  dim3 grid((unsigned)((a->N + BN - 1) / BN), (unsigned)((a->M + BM - 1) / BM), (unsigned)split);
+  PMGT_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "pmgt_gemm_bf16: grid too large (M tiles %u, split %u)", grid.y, grid.z);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool deep = kb_per > 2;
+
+#define PMGT_DISPATCH(AM, BMN, GA_, GB_)                                              \
+  return deep ? launch<AM, BMN, GA_, GB_, 4>(ta, tb, ka, grid, st) : launch<AM, BMN, GA_, GB_, 2>(ta, tb, ka, grid, st)
+  if (!a->a_mn && !a->b_mn && !ga) { PMGT_DISPATCH(false, false, false, false); }
+  if (!a->a_mn && !a->b_mn && ga) { PMGT_DISPATCH(false, false, true, false); }
+  if (!a->a_mn && a->b_mn && !ga && !gb) { PMGT_DISPATCH(false, true, false, false); }
+  if (a->a_mn && a->b_mn && !gb) { PMGT_DISPATCH(true, true, false, false); }
+  if (a->a_mn && a->b_mn && gb) { PMGT_DISPATCH(true, true, false, true); }
+#undef PMGT_DISPATCH
+  set_error("pmgt_gemm_bf16: unsupported operand layout a_mn=%d b_mn=%d gather_a=%d gather_b=%d", a->a_mn, a->b_mn,
+            (int)ga, (int)gb);
+  return PMGT_ERR_UNSUPPORTED;
+}

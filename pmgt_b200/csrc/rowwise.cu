@@ -1,0 +1,722 @@
+// Row-wise (one warp per token) kernels of the PMGT encoder:
+//   * PMGTEmbeddings fusion + LayerNorm (modeling_pmgt.py:199-208) fwd/bwd
+//   * BertSelfOutput / BertOutput "dropout + residual + LayerNorm" fwd/bwd
+//   * column sums (bias gradients), fp32->bf16 cast, row gather, sum of squares,
+//     fused AdamW (pmgt/optimizers.py:256-270)
+// All are HBM-bandwidth-bound streaming kernels: 8-byte coalesced bf16 loads,
+// fp32 math in registers, persistent grids of (SM count x resident CTAs).
+#include "common.cuh"
+
+namespace pmgt {
+
+constexpr int kRowThreads = 256;  // 8 warps per CTA
+
+// A token row of H values distributed over a warp: lane owns groups of 4
+// consecutive values, group index g = lane + 32*i, i < G.
+template <int G>
+struct RowRegs {
+  float v[G][4];
+};
+
+template <int G>
+__device__ __forceinline__ void load_row_bf16(const uint16_t* __restrict__ p, int H, int lane, RowRegs<G>& r) {
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    const int h = (lane + 32 * i) * 4;
+    if (h < H) {
+      const uint2 u = *reinterpret_cast<const uint2*>(p + h);
+      unpack_bf16x2(u.x, r.v[i][0], r.v[i][1]);
+      unpack_bf16x2(u.y, r.v[i][2], r.v[i][3]);
+    } else {
+      r.v[i][0] = r.v[i][1] = r.v[i][2] = r.v[i][3] = 0.f;
+    }
+  }
+}
+template <int G>
+__device__ __forceinline__ void load_row_f32(const float* __restrict__ p, int H, int lane, RowRegs<G>& r) {
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    const int h = (lane + 32 * i) * 4;
+    if (h < H) {
+      const float4 u = *reinterpret_cast<const float4*>(p + h);
+      r.v[i][0] = u.x; r.v[i][1] = u.y; r.v[i][2] = u.z; r.v[i][3] = u.w;
+    } else {
+      r.v[i][0] = r.v[i][1] = r.v[i][2] = r.v[i][3] = 0.f;
+    }
+  }
+}
+template <int G>
+__device__ __forceinline__ void store_row_bf16(uint16_t* __restrict__ p, int H, int lane, const RowRegs<G>& r) {
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    const int h = (lane + 32 * i) * 4;
+    if (h < H) {
+      uint2 u;
+      u.x = pack_bf16x2(r.v[i][0], r.v[i][1]);
+      u.y = pack_bf16x2(r.v[i][2], r.v[i][3]);
+      *reinterpret_cast<uint2*>(p + h) = u;
+    }
+  }
+}
+template <int G>
+__device__ __forceinline__ void store_row_f32(float* __restrict__ p, int H, int lane, const RowRegs<G>& r) {
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    const int h = (lane + 32 * i) * 4;
+    if (h < H) *reinterpret_cast<float4*>(p + h) = make_float4(r.v[i][0], r.v[i][1], r.v[i][2], r.v[i][3]);
+  }
+}
+
+// mean / rstd of a row (two-pass, values already in registers)
+template <int G>
+__device__ __forceinline__ void row_stats(const RowRegs<G>& z, int H, int lane, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < G; ++i)
+    if ((lane + 32 * i) * 4 < H) s += z.v[i][0] + z.v[i][1] + z.v[i][2] + z.v[i][3];
+  mean = warp_sum(s) / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < G; ++i)
+    if ((lane + 32 * i) * 4 < H) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float d = z.v[i][j] - mean; q += d * d; }
+    }
+  rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+}
+
+// per-warp shared accumulators: acc[k][h] += val, flushed with global atomics
+__device__ __forceinline__ void flush_acc(float* __restrict__ dst, float* acc, int H, int lane) {
+  if (!dst) return;
+  for (int h = lane; h < H; h += 32) {
+    const float v = acc[h];
+    if (v != 0.f) atomicAdd(dst + h, v);
+    acc[h] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// embeddings: modality attention fusion + position/role + LayerNorm + dropout
+// ---------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void embed_forward_row(const pmgt_embed_args& a, long long tok, int l, int lane,
+                                                  RowRegs<G>& ev, RowRegs<G>& et, RowRegs<G>& tv, RowRegs<G>& tt,
+                                                  RowRegs<G>& z, float& a0, float& a1, float& mean, float& rstd) {
+  const int H = a.H;
+  load_row_bf16<G>(a.ev + tok * H, H, lane, ev);
+  load_row_bf16<G>(a.et + tok * H, H, lane, et);
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    const int h = (lane + 32 * i) * 4;
+    if (h < H) {
+      const float4 w0v = *reinterpret_cast<const float4*>(a.w_att + h);
+      const float4 w0t = *reinterpret_cast<const float4*>(a.w_att + H + h);
+      const float4 w1v = *reinterpret_cast<const float4*>(a.w_att + 2 * H + h);
+      const float4 w1t = *reinterpret_cast<const float4*>(a.w_att + 3 * H + h);
+      const float w0va[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w0ta[4] = {w0t.x, w0t.y, w0t.z, w0t.w};
+      const float w1va[4] = {w1v.x, w1v.y, w1v.z, w1v.w}, w1ta[4] = {w1t.x, w1t.y, w1t.z, w1t.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        tv.v[i][j] = tanhf(ev.v[i][j]);
+        tt.v[i][j] = tanhf(et.v[i][j]);
+        s0 += w0va[j] * tv.v[i][j] + w0ta[j] * tt.v[i][j];
+        s1 += w1va[j] * tv.v[i][j] + w1ta[j] * tt.v[i][j];
+      }
+    }
+  }
+  s0 = warp_sum(s0) + a.b_att[0];
+  s1 = warp_sum(s1) + a.b_att[1];
+  const float mx = fmaxf(s0, s1);
+  const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx);
+  a0 = e0 / (e0 + e1);
+  a1 = e1 / (e0 + e1);
+  const float* pos = a.pos + (long long)l * H;
+  const float* role = a.role + (l > 0 ? H : 0);
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    const int h = (lane + 32 * i) * 4;
+    if (h < H) {
+      const float4 pp = *reinterpret_cast<const float4*>(pos + h);
+      const float4 rr = *reinterpret_cast<const float4*>(role + h);
+      z.v[i][0] = a0 * ev.v[i][0] + a1 * et.v[i][0] + pp.x + rr.x;
+      z.v[i][1] = a0 * ev.v[i][1] + a1 * et.v[i][1] + pp.y + rr.y;
+      z.v[i][2] = a0 * ev.v[i][2] + a1 * et.v[i][2] + pp.z + rr.z;
+      z.v[i][3] = a0 * ev.v[i][3] + a1 * et.v[i][3] + pp.w + rr.w;
+    } else {
+      z.v[i][0] = z.v[i][1] = z.v[i][2] = z.v[i][3] = 0.f;
+    }
+  }
+  row_stats<G>(z, H, lane, a.ln_eps, mean, rstd);
+}
+
+template <int G>
+__global__ void __launch_bounds__(kRowThreads) embed_fuse_fwd_kernel(const pmgt_embed_args a) {
+  const int lane = threadIdx.x & 31;
+  const long long T = a.rows * a.L;
+  const long long warp0 = (long long)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (kRowThreads / 32);
+  const int H = a.H;
+  const float keep_scale = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
+  for (long long tok = warp0; tok < T; tok += nwarps) {
+    const int l = (int)(tok % a.L);
+    RowRegs<G> ev, et, tv, tt, z;
+    float a0, a1, mean, rstd;
+    embed_forward_row<G>(a, tok, l, lane, ev, et, tv, tt, z, a0, a1, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int h = (lane + 32 * i) * 4;
+      if (h < H) {
+        const float4 g = *reinterpret_cast<const float4*>(a.ln_g + h);
+        const float4 b = *reinterpret_cast<const float4*>(a.ln_b + h);
+        const float ga[4] = {g.x, g.y, g.z, g.w}, ba[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float y = (z.v[i][j] - mean) * rstd * ga[j] + ba[j];
+          if (a.dropout_p > 0.f)
+            y = dropout_keep(a.dropout_seed, a.dropout_site, (uint64_t)tok * H + h + j, a.dropout_p) ? y * keep_scale : 0.f;
+          z.v[i][j] = y;
+        }
+      }
+    }
+    store_row_bf16<G>(a.x_out + tok * H, H, lane, z);
+  }
+}
+
+// Backward.  Work is ordered position-major (all rows of position l, then l+1)
+// so the position/role gradient of one l accumulates locally before a flush.
+// per-warp smem accumulators: [0]=d_ln_g [1]=d_ln_b [2]=d_pos(l) [3..6]=d_w_att (4 x H) [7]=dbias_v [8]=dbias_t
+template <int G>
+__global__ void __launch_bounds__(kRowThreads) embed_fuse_bwd_kernel(const pmgt_embed_args a) {
+  extern __shared__ float acc_all[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int H = a.H;
+  float* acc = acc_all + (size_t)wib * 9 * H;
+  for (int i = lane; i < 9 * H; i += 32) acc[i] = 0.f;
+  float db_att0 = 0.f, db_att1 = 0.f;
+  __syncwarp();
+  const long long warp0 = (long long)blockIdx.x * (kRowThreads / 32) + wib;
+  const long long nwarps = (long long)gridDim.x * (kRowThreads / 32);
+  const float keep_scale = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
+  for (int l = 0; l < a.L; ++l) {
+    for (long long row = warp0; row < a.rows; row += nwarps) {
+      const long long tok = row * a.L + l;
+      RowRegs<G> ev, et, tv, tt, z, dy;
+      float a0, a1, mean, rstd;
+      embed_forward_row<G>(a, tok, l, lane, ev, et, tv, tt, z, a0, a1, mean, rstd);
+      load_row_bf16<G>(a.dx + tok * H, H, lane, dy);
+      // LayerNorm backward
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int h = (lane + 32 * i) * 4;
+        if (h < H) {
+          const float4 g = *reinterpret_cast<const float4*>(a.ln_g + h);
+          const float ga[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float d = dy.v[i][j];
+            if (a.dropout_p > 0.f)
+              d = dropout_keep(a.dropout_seed, a.dropout_site, (uint64_t)tok * H + h + j, a.dropout_p) ? d * keep_scale : 0.f;
+            const float xh = (z.v[i][j] - mean) * rstd;
+            acc[0 * H + h + j] += d * xh;
+            acc[1 * H + h + j] += d;
+            const float dg = d * ga[j];
+            s1 += dg;
+            s2 += dg * xh;
+            dy.v[i][j] = dg;   // reuse: dy now holds dy*gamma
+            z.v[i][j] = xh;    // reuse: z now holds xhat
+          }
+        }
+      }
+      s1 = warp_sum(s1) / (float)H;
+      s2 = warp_sum(s2) / (float)H;
+      // dz -> d_pos / d_role ; d a0/a1 ; d ev / d et through the weighted sum
+      float da0 = 0.f, da1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int h = (lane + 32 * i) * 4;
+        if (h < H) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float dz = rstd * (dy.v[i][j] - s1 - z.v[i][j] * s2);
+            acc[2 * H + h + j] += dz;
+            da0 += dz * ev.v[i][j];
+            da1 += dz * et.v[i][j];
+            dy.v[i][j] = dz;  // reuse: dy now holds dz
+          }
+        }
+      }
+      da0 = warp_sum(da0);
+      da1 = warp_sum(da1);
+      // softmax over the two modality logits
+      const float dot = da0 * a0 + da1 * a1;
+      const float ds0 = a0 * (da0 - dot), ds1 = a1 * (da1 - dot);
+      db_att0 += ds0;
+      db_att1 += ds1;
+      RowRegs<G> dev, det;
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int h = (lane + 32 * i) * 4;
+        if (h < H) {
+          const float4 w0v = *reinterpret_cast<const float4*>(a.w_att + h);
+          const float4 w0t = *reinterpret_cast<const float4*>(a.w_att + H + h);
+          const float4 w1v = *reinterpret_cast<const float4*>(a.w_att + 2 * H + h);
+          const float4 w1t = *reinterpret_cast<const float4*>(a.w_att + 3 * H + h);
+          const float w0va[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w0ta[4] = {w0t.x, w0t.y, w0t.z, w0t.w};
+          const float w1va[4] = {w1v.x, w1v.y, w1v.z, w1v.w}, w1ta[4] = {w1t.x, w1t.y, w1t.z, w1t.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float thv = tv.v[i][j], tht = tt.v[i][j];
+            acc[3 * H + h + j] += ds0 * thv;
+            acc[4 * H + h + j] += ds0 * tht;
+            acc[5 * H + h + j] += ds1 * thv;
+            acc[6 * H + h + j] += ds1 * tht;
+            const float dv = a0 * dy.v[i][j] + (ds0 * w0va[j] + ds1 * w1va[j]) * (1.f - thv * thv);
+            const float dt = a1 * dy.v[i][j] + (ds0 * w0ta[j] + ds1 * w1ta[j]) * (1.f - tht * tht);
+            dev.v[i][j] = dv;
+            det.v[i][j] = dt;
+            // bias gradient of the projections = column sums of the bf16-rounded dev/det
+            acc[7 * H + h + j] += bf16_bits_to_float(float_to_bf16_bits(dv));
+            acc[8 * H + h + j] += bf16_bits_to_float(float_to_bf16_bits(dt));
+          }
+        } else {
+          dev.v[i][0] = dev.v[i][1] = dev.v[i][2] = dev.v[i][3] = 0.f;
+          det.v[i][0] = det.v[i][1] = det.v[i][2] = det.v[i][3] = 0.f;
+        }
+      }
+      store_row_bf16<G>(a.dev + tok * H, H, lane, dev);
+      store_row_bf16<G>(a.det + tok * H, H, lane, det);
+    }
+    // flush position / role gradient of this l
+    __syncwarp();
+    for (int h = lane; h < H; h += 32) {
+      const float v = acc[2 * H + h];
+      if (v != 0.f) {
+        atomicAdd(a.d_pos + (long long)l * H + h, v);
+        atomicAdd(a.d_role + (l > 0 ? H : 0) + h, v);
+      }
+      acc[2 * H + h] = 0.f;
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+  flush_acc(a.d_ln_g, acc + 0 * H, H, lane);
+  flush_acc(a.d_ln_b, acc + 1 * H, H, lane);
+  flush_acc(a.d_w_att + 0 * H, acc + 3 * H, H, lane);
+  flush_acc(a.d_w_att + 1 * H, acc + 4 * H, H, lane);
+  flush_acc(a.d_w_att + 2 * H, acc + 5 * H, H, lane);
+  flush_acc(a.d_w_att + 3 * H, acc + 6 * H, H, lane);
+  flush_acc(a.d_bias_v, acc + 7 * H, H, lane);
+  flush_acc(a.d_bias_t, acc + 8 * H, H, lane);
+  if (lane == 0) {
+    if (db_att0 != 0.f) atomicAdd(a.d_b_att + 0, db_att0);
+    if (db_att1 != 0.f) atomicAdd(a.d_b_att + 1, db_att1);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// y = LayerNorm(dropout(o) + res)
+// ---------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(kRowThreads) res_ln_fwd_kernel(const pmgt_resln_args a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (kRowThreads / 32);
+  const int H = a.H;
+  const float keep_scale = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
+  for (long long tok = warp0; tok < a.T; tok += nwarps) {
+    RowRegs<G> o, r;
+    load_row_bf16<G>(a.o + tok * H, H, lane, o);
+    load_row_bf16<G>(a.res + tok * H, H, lane, r);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int h = (lane + 32 * i) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = o.v[i][j];
+        if (a.dropout_p > 0.f && h < H)
+          v = dropout_keep(a.dropout_seed, a.dropout_site, (uint64_t)tok * H + h + j, a.dropout_p) ? v * keep_scale : 0.f;
+        o.v[i][j] = v + r.v[i][j];
+      }
+    }
+    float mean, rstd;
+    row_stats<G>(o, H, lane, a.ln_eps, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int h = (lane + 32 * i) * 4;
+      if (h < H) {
+        const float4 g = *reinterpret_cast<const float4*>(a.ln_g + h);
+        const float4 b = *reinterpret_cast<const float4*>(a.ln_b + h);
+        o.v[i][0] = (o.v[i][0] - mean) * rstd * g.x + b.x;
+        o.v[i][1] = (o.v[i][1] - mean) * rstd * g.y + b.y;
+        o.v[i][2] = (o.v[i][2] - mean) * rstd * g.z + b.z;
+        o.v[i][3] = (o.v[i][3] - mean) * rstd * g.w + b.w;
+      }
+    }
+    store_row_bf16<G>(a.y + tok * H, H, lane, o);
+    if (a.y_f32) store_row_f32<G>(a.y_f32 + tok * H, H, lane, o);
+  }
+}
+
+// per-warp smem accumulators: [0]=d_g [1]=d_b [2]=d_bias
+template <int G>
+__global__ void __launch_bounds__(kRowThreads) res_ln_bwd_kernel(const pmgt_resln_args a) {
+  extern __shared__ float acc_all[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int H = a.H;
+  float* acc = acc_all + (size_t)wib * 3 * H;
+  for (int i = lane; i < 3 * H; i += 32) acc[i] = 0.f;
+  __syncwarp();
+  const long long warp0 = (long long)blockIdx.x * (kRowThreads / 32) + wib;
+  const long long nwarps = (long long)gridDim.x * (kRowThreads / 32);
+  const float keep_scale = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
+  const bool sep_do = a.d_o != nullptr && a.d_o != a.dz;
+  for (long long tok = warp0; tok < a.T; tok += nwarps) {
+    RowRegs<G> z, r, dy;
+    load_row_bf16<G>(a.o + tok * H, H, lane, z);
+    load_row_bf16<G>(a.res + tok * H, H, lane, r);
+    if (a.dy) load_row_bf16<G>(a.dy + tok * H, H, lane, dy);
+    else {
+#pragma unroll
+      for (int i = 0; i < G; ++i) dy.v[i][0] = dy.v[i][1] = dy.v[i][2] = dy.v[i][3] = 0.f;
+    }
+    if (a.dy_f32) {
+      RowRegs<G> e;
+      load_row_f32<G>(a.dy_f32 + tok * H, H, lane, e);
+#pragma unroll
+      for (int i = 0; i < G; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dy.v[i][j] += e.v[i][j];
+    }
+    uint32_t keep_bits = 0xffffffffu;  // bit (i*4+j), G*4 <= 32
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int h = (lane + 32 * i) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = z.v[i][j];
+        if (a.dropout_p > 0.f && h < H) {
+          const bool k = dropout_keep(a.dropout_seed, a.dropout_site, (uint64_t)tok * H + h + j, a.dropout_p);
+          if (!k) keep_bits &= ~(1u << (i * 4 + j));
+          v = k ? v * keep_scale : 0.f;
+        }
+        z.v[i][j] = v + r.v[i][j];
+      }
+    }
+    float mean, rstd;
+    row_stats<G>(z, H, lane, a.ln_eps, mean, rstd);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int h = (lane + 32 * i) * 4;
+      if (h < H) {
+        const float4 g = *reinterpret_cast<const float4*>(a.ln_g + h);
+        const float ga[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float d = dy.v[i][j];
+          const float xh = (z.v[i][j] - mean) * rstd;
+          acc[0 * H + h + j] += d * xh;
+          acc[1 * H + h + j] += d;
+          const float dg = d * ga[j];
+          s1 += dg;
+          s2 += dg * xh;
+          dy.v[i][j] = dg;
+          z.v[i][j] = xh;
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+    RowRegs<G> dout;
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int h = (lane + 32 * i) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float dz = (h < H) ? rstd * (dy.v[i][j] - s1 - z.v[i][j] * s2) : 0.f;
+        dy.v[i][j] = dz;
+        const float dov = (keep_bits >> (i * 4 + j)) & 1u ? dz * keep_scale : 0.f;
+        dout.v[i][j] = dov;
+        if (h < H) acc[2 * H + h + j] += bf16_bits_to_float(float_to_bf16_bits(dov));
+      }
+    }
+    store_row_bf16<G>(a.dz + tok * H, H, lane, dy);
+    if (sep_do) store_row_bf16<G>(a.d_o + tok * H, H, lane, dout);
+  }
+  __syncwarp();
+  flush_acc(a.d_g, acc + 0 * H, H, lane);
+  flush_acc(a.d_b, acc + 1 * H, H, lane);
+  flush_acc(a.d_bias, acc + 2 * H, H, lane);
+}
+
+// ---------------------------------------------------------------------------
+// column sums of a bf16 matrix: out[n] += sum_t x[t][n]
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const uint16_t* __restrict__ x, long long T, int N, long long ldx,
+                                                     float* __restrict__ out, int rows_per_cta) {
+  // thread owns 8 consecutive columns; blockDim.x = threads per row * row groups
+  const int tpr = (N + 7) / 8;               // threads per row (<= 256)
+  const int groups = blockDim.x / tpr;       // rows processed concurrently
+  const int tg = threadIdx.x / tpr;
+  const int tc = threadIdx.x % tpr;
+  if (tg >= groups) return;
+  const int n = tc * 8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > T) r1 = T;
+  for (long long r = r0 + tg; r < r1; r += groups) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + r * ldx + n);
+    float f[8];
+    unpack_bf16x2(u.x, f[0], f[1]); unpack_bf16x2(u.y, f[2], f[3]);
+    unpack_bf16x2(u.z, f[4], f[5]); unpack_bf16x2(u.w, f[6], f[7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += f[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (n + j < N && s[j] != 0.f) atomicAdd(out + n + j, s[j]);
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst,
+                                                            long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(src + i);
+      uint2 u;
+      u.x = pack_bf16x2(v.x, v.y);
+      u.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(dst + i) = u;
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = float_to_bf16_bits(src[j]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  float s = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(out, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint16_t* __restrict__ src, long long ld_src,
+                                                          const long long* __restrict__ idx, long long n_rows, int D,
+                                                          uint16_t* __restrict__ out, long long ld_out) {
+  const int chunks = D / 8;
+  const long long total = n_rows * chunks;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / chunks;
+    const int c = (int)(i % chunks) * 8;
+    const long long s = idx[r];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (s >= 0) v = *reinterpret_cast<const uint4*>(src + s * ld_src + c);
+    *reinterpret_cast<uint4*>(out + r * ld_out + c) = v;
+  }
+}
+
+// AdamW, dense branch of DenseSparseAdamW (pmgt/optimizers.py:256-270)
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v,
+                                                    const uint8_t* __restrict__ decay_mask, long long n, float lr,
+                                                    float beta1, float beta2, float eps, float wd, float inv_sqrt_bc2,
+                                                    float step_size, float grad_scale,
+                                                    const float* __restrict__ grad_scale_dev) {
+  const float gs = grad_scale_dev ? *grad_scale_dev : grad_scale;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * gs;
+    float pi = p[i];
+    const float decay = (decay_mask == nullptr || decay_mask[i]) ? wd : 0.f;
+    pi *= 1.f - lr * decay;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+static int persistent_grid(long long work_warps, int warps_per_cta, int ctas_per_sm) {
+  long long need = (work_warps + warps_per_cta - 1) / warps_per_cta;
+  long long cap = (long long)num_sms() * ctas_per_sm;
+  if (need > cap) need = cap;
+  if (need < 1) need = 1;
+  return (int)need;
+}
+
+}  // namespace pmgt
+
+using namespace pmgt;
+
+#define PMGT_DISPATCH_G(H, CALL1, CALL8)        \
+  do {                                          \
+    if ((H) <= 128) { CALL1; } else { CALL8; }  \
+  } while (0)
+
+extern "C" {
+
+int pmgt_embed_fuse_fwd(const pmgt_embed_args* a, void* stream) {
+  PMGT_REQUIRE(a && a->ev && a->et && a->w_att && a->b_att && a->pos && a->role && a->ln_g && a->ln_b && a->x_out,
+               "pmgt_embed_fuse_fwd: null argument");
+  PMGT_REQUIRE(a->H % 4 == 0 && a->H >= 4 && a->H <= 1024, "pmgt_embed_fuse_fwd: H must be a multiple of 4 in [4,1024]");
+  PMGT_REQUIRE(a->L >= 1 && a->rows >= 0, "pmgt_embed_fuse_fwd: bad sizes");
+  if (a->rows == 0) return PMGT_OK;
+  const int grid = persistent_grid(a->rows * a->L, kRowThreads / 32, 8);
+  PMGT_DISPATCH_G(a->H, (embed_fuse_fwd_kernel<1><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)),
+                  (embed_fuse_fwd_kernel<8><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)));
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+int pmgt_embed_fuse_bwd(const pmgt_embed_args* a, void* stream) {
+  PMGT_REQUIRE(a && a->ev && a->et && a->w_att && a->b_att && a->pos && a->role && a->ln_g && a->ln_b && a->dx &&
+                   a->dev && a->det && a->d_w_att && a->d_b_att && a->d_pos && a->d_role && a->d_ln_g && a->d_ln_b &&
+                   a->d_bias_v && a->d_bias_t,
+               "pmgt_embed_fuse_bwd: null argument");
+  PMGT_REQUIRE(a->H % 4 == 0 && a->H >= 4 && a->H <= 1024, "pmgt_embed_fuse_bwd: H must be a multiple of 4 in [4,1024]");
+  if (a->rows == 0) return PMGT_OK;
+  const size_t smem = (size_t)(kRowThreads / 32) * 9 * a->H * sizeof(float);
+  const int grid = persistent_grid(a->rows, kRowThreads / 32, 2);
+  if (a->H <= 128) {
+    embed_fuse_bwd_kernel<1><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(*a);
+  } else {
+    static bool cfg = false;
+    if (!cfg) {
+      PMGT_CHECK_CUDA(cudaFuncSetAttribute(embed_fuse_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      cfg = true;
+    }
+    PMGT_REQUIRE(smem <= 227 * 1024, "pmgt_embed_fuse_bwd: H too large for shared-memory accumulators");
+    embed_fuse_bwd_kernel<8><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(*a);
+  }
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+int pmgt_res_ln_fwd(const pmgt_resln_args* a, void* stream) {
+  PMGT_REQUIRE(a && a->o && a->res && a->ln_g && a->ln_b && a->y, "pmgt_res_ln_fwd: null argument");
+  PMGT_REQUIRE(a->H % 4 == 0 && a->H >= 4 && a->H <= 1024, "pmgt_res_ln_fwd: H must be a multiple of 4 in [4,1024]");
+  if (a->T == 0) return PMGT_OK;
+  const int grid = persistent_grid(a->T, kRowThreads / 32, 8);
+  PMGT_DISPATCH_G(a->H, (res_ln_fwd_kernel<1><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)),
+                  (res_ln_fwd_kernel<8><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)));
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+int pmgt_res_ln_bwd(const pmgt_resln_args* a, void* stream) {
+  PMGT_REQUIRE(a && a->o && a->res && a->ln_g && (a->dy || a->dy_f32) && a->dz, "pmgt_res_ln_bwd: null argument");
+  PMGT_REQUIRE(a->H % 4 == 0 && a->H >= 4 && a->H <= 1024, "pmgt_res_ln_bwd: H must be a multiple of 4 in [4,1024]");
+  PMGT_REQUIRE(a->dropout_p == 0.f || (a->d_o && a->d_o != a->dz), "pmgt_res_ln_bwd: dropout needs a separate d_o buffer");
+  if (a->T == 0) return PMGT_OK;
+  const size_t smem = (size_t)(kRowThreads / 32) * 3 * a->H * sizeof(float);
+  const int grid = persistent_grid(a->T, kRowThreads / 32, 4);
+  if (a->H <= 128) {
+    res_ln_bwd_kernel<1><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(*a);
+  } else {
+    static bool cfg = false;
+    if (!cfg) {
+      PMGT_CHECK_CUDA(cudaFuncSetAttribute(res_ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      cfg = true;
+    }
+    res_ln_bwd_kernel<8><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(*a);
+  }
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+int pmgt_colsum_bf16(const uint16_t* x, int64_t T, int64_t N, int64_t ldx, float* out, void* stream) {
+  PMGT_REQUIRE(x && out, "pmgt_colsum_bf16: null argument");
+  PMGT_REQUIRE(N % 8 == 0 && N > 0 && ldx % 8 == 0, "pmgt_colsum_bf16: N and ldx must be multiples of 8");
+  if (T == 0) return PMGT_OK;
+  // wide matrices are processed in column panels of 2048
+  for (int64_t nb = 0; nb < N; nb += 2048) {
+    const int n = (int)((N - nb) < 2048 ? (N - nb) : 2048);
+    const int tpr = n / 8;
+    const int groups = 256 / tpr > 0 ? 256 / tpr : 1;
+    const int threads = tpr * groups;
+    long long ctas = (long long)num_sms() * 4;
+    long long rows_per = (T + ctas - 1) / ctas;
+    if (rows_per < groups) rows_per = groups;
+    ctas = (T + rows_per - 1) / rows_per;
+    colsum_kernel<<<(unsigned)ctas, threads, 0, (cudaStream_t)stream>>>(x + nb, T, n, ldx, out + nb, (int)rows_per);
+    PMGT_LAUNCH_CHECK();
+  }
+  return PMGT_OK;
+}
+
+int pmgt_cast_f32_bf16(const float* src, uint16_t* dst, int64_t n, void* stream) {
+  PMGT_REQUIRE(src && dst && n >= 0, "pmgt_cast_f32_bf16: bad argument");
+  PMGT_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "pmgt_cast_f32_bf16: alignment");
+  if (n == 0) return PMGT_OK;
+  long long blocks = (n / 4 + 255) / 256;
+  long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+int pmgt_sumsq_f32(const float* x, int64_t n, float* out, void* stream) {
+  PMGT_REQUIRE(x && out && n >= 0, "pmgt_sumsq_f32: bad argument");
+  if (n == 0) return PMGT_OK;
+  long long blocks = (n + 255) / 256;
+  long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+int pmgt_gather_rows_bf16(const uint16_t* src, int64_t ld_src, const int64_t* idx, int64_t n_rows, int64_t D,
+                          uint16_t* out, int64_t ld_out, void* stream) {
+  PMGT_REQUIRE(src && idx && out, "pmgt_gather_rows_bf16: null argument");
+  PMGT_REQUIRE(D % 8 == 0 && ld_src % 8 == 0 && ld_out % 8 == 0, "pmgt_gather_rows_bf16: D/ld must be multiples of 8");
+  if (n_rows == 0 || D == 0) return PMGT_OK;
+  long long total = n_rows * (D / 8);
+  long long blocks = (total + 255) / 256;
+  long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (const long long*)idx, n_rows, (int)D,
+                                                                        out, ld_out);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+int pmgt_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t* decay_mask, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                    const float* grad_scale_dev, void* stream) {
+  PMGT_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "pmgt_adamw_step: bad argument");
+  if (n == 0) return PMGT_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  long long blocks = (n + 255) / 256;
+  long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, decay_mask, n, lr, beta1, beta2, eps,
+                                                                  weight_decay, (float)(1.0 / sqrt(bc2)),
+                                                                  (float)(lr / bc1), grad_scale, grad_scale_dev);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+}  // extern "C"

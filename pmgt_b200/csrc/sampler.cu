@@ -1,0 +1,408 @@
+// K1 -- MCNSampling on the device: CSR item graph, per-row softmax CDF,
+// counter-based Philox4x32-10.  Replaces pmgt/pmgt/datasets.py:14-79 (context
+// sampler) and :125-183 (positive / negative pair selection) of the reference.
+//
+// One CTA (128 threads) builds one context:
+//   hop k: n_k = s_1*...*s_k draws; draw d has parent d / s_k in the previous
+//          hop's list; u -> upper_bound over the parent's CDF slice -> neighbour.
+//   scoring: smem open-addressing table  node -> (score += depth-k+1,
+//            first = min(global draw index)); the root itself is not scored.
+//   top-k: max_ctx rounds of a block-wide arg-max over
+//          key = (score << 32) | ~first  (score desc, first appearance asc --
+//          Python's stable sorted(..., reverse=True) over dict insertion order).
+// The CPU replay of the same stream is oracle/philox_sampler.c.
+#include "common.cuh"
+
+namespace pmgt {
+
+struct pmgt_graph_impl {
+  int device;
+  int64_t num_nodes;
+  int64_t num_edges;
+  int64_t* indptr;
+  int32_t* indices;
+  float* cdf;
+};
+
+constexpr int kSamplerThreads = 128;
+constexpr int kMaxDepth = 8;
+
+struct SamplerParams {
+  const int64_t* indptr;
+  const int32_t* indices;
+  const float* cdf;
+  const int64_t* roots;
+  const int64_t* keys;
+  int64_t n_ctx;
+  int64_t n_node_ids;  // num_nodes + 2
+  int depth;
+  int hops[kMaxDepth];
+  int max_ctx;
+  int list_cap;   // capacity of each hop list (largest stored level)
+  int table_cap;  // power of two
+  int table_shift;
+  uint32_t seed_lo, seed_hi;
+  int64_t* out_ids;
+  float* out_mask;
+  int64_t* out_visited_deg;
+};
+
+__device__ __forceinline__ int upper_bound_cdf(const float* __restrict__ cdf, int n, float u) {
+  // number of entries <= u  (numpy searchsorted(side="right")), clamped to n-1
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(cdf + mid) <= u) lo = mid + 1; else hi = mid;
+  }
+  return lo < n ? lo : n - 1;
+}
+
+__global__ void __launch_bounds__(kSamplerThreads)
+sample_contexts_kernel(const SamplerParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* list_a = reinterpret_cast<int32_t*>(smem_raw);
+  int32_t* list_b = list_a + p.list_cap;
+  int32_t* tkeys = list_b + p.list_cap;
+  uint32_t* tscore = reinterpret_cast<uint32_t*>(tkeys + p.table_cap);
+  uint32_t* tfirst = tscore + p.table_cap;
+  __shared__ unsigned long long red[kSamplerThreads / 32];
+  __shared__ unsigned long long best_sh;
+  __shared__ unsigned long long deg_sh;
+
+  const int tid = threadIdx.x;
+  const int L = p.max_ctx + 1;
+
+  for (int64_t ctx = blockIdx.x; ctx < p.n_ctx; ctx += gridDim.x) {
+    const int64_t root64 = p.roots[ctx];
+    const int32_t root = (int32_t)root64;
+    const uint64_t key = (uint64_t)p.keys[ctx];
+    const uint32_t key_lo = (uint32_t)key, key_hi = (uint32_t)(key >> 32);
+
+    for (int i = tid; i < p.table_cap; i += kSamplerThreads) {
+      tkeys[i] = 0; tscore[i] = 0u; tfirst[i] = 0xffffffffu;
+    }
+    if (tid == 0) deg_sh = 0ull;
+    __syncthreads();
+
+    int32_t* prev = list_a;
+    int32_t* cur = list_b;
+    uint32_t base = 0;       // global draw index of the first draw of this hop
+    uint32_t n_prev = 1;     // number of parents
+    unsigned long long my_deg = 0;
+    const bool root_ok = root64 >= 2 && root64 < p.n_node_ids;
+
+    for (int k = 1; k <= p.depth; ++k) {
+      const uint32_t s = (uint32_t)p.hops[k - 1];
+      const uint32_t n_k = n_prev * s;
+      const uint32_t hop_w = (uint32_t)(p.depth - k + 1);
+      const bool store = k < p.depth;
+      const uint32_t q_lo = base >> 2, q_hi = (base + n_k - 1) >> 2;
+      for (uint32_t q = q_lo + tid; q <= q_hi; q += kSamplerThreads) {
+        Philox4 r = philox4x32_10(q, PMGT_STREAM_CTX, key_lo, key_hi, p.seed_lo, p.seed_hi);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t gd = (q << 2) + w;
+          if (gd < base || gd >= base + n_k) continue;
+          const uint32_t d = gd - base;
+          const uint32_t ppos = d / s;
+          const int32_t parent = (k == 1) ? (root_ok ? root : 0) : prev[ppos];
+          int32_t nb = 0;
+          if (parent != 0) {
+            const int64_t rs = __ldg(p.indptr + parent);
+            const int deg = (int)(__ldg(p.indptr + parent + 1) - rs);
+            if (d - ppos * s == 0) my_deg += (unsigned long long)deg;
+            if (deg > 0) {
+              const float u = (float)(philox_word(r, w) >> 8) * (1.0f / 16777216.0f);
+              const int pos = upper_bound_cdf(p.cdf + rs, deg, u);
+              nb = __ldg(p.indices + rs + pos);
+            }
+          }
+          if (store) cur[d] = nb;
+          if (nb != 0 && nb != root) {
+            uint32_t slot = ((uint32_t)nb * 2654435761u) >> p.table_shift;
+            while (true) {
+              int32_t old = atomicCAS(&tkeys[slot], 0, nb);
+              if (old == 0 || old == nb) break;
+              slot = (slot + 1) & (uint32_t)(p.table_cap - 1);
+            }
+            atomicAdd(&tscore[slot], hop_w);
+            atomicMin(&tfirst[slot], gd);
+          }
+        }
+      }
+      __syncthreads();
+      int32_t* t = prev; prev = cur; cur = t;
+      base += n_k;
+      n_prev = n_k;
+    }
+
+    if (p.out_visited_deg) {
+      for (int o = 16; o > 0; o >>= 1) my_deg += __shfl_xor_sync(0xffffffffu, my_deg, o);
+      if ((tid & 31) == 0 && my_deg) atomicAdd(&deg_sh, my_deg);
+    }
+
+    // top-k by (score desc, first asc)
+    unsigned long long bound = ~0ull;
+    if (tid == 0) {
+      p.out_ids[ctx * L] = root64;
+      p.out_mask[ctx * L] = 1.0f;
+    }
+    for (int r = 0; r < p.max_ctx; ++r) {
+      unsigned long long best = 0ull;
+      for (int i = tid; i < p.table_cap; i += kSamplerThreads) {
+        if (tkeys[i] != 0) {
+          unsigned long long kk = ((unsigned long long)tscore[i] << 32) |
+                                  (unsigned long long)(0xffffffffu - tfirst[i]);
+          if (kk < bound && kk > best) best = kk;
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+      }
+      if ((tid & 31) == 0) red[tid >> 5] = best;
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long b = red[0];
+        for (int i = 1; i < kSamplerThreads / 32; ++i) b = red[i] > b ? red[i] : b;
+        best_sh = b;
+      }
+      __syncthreads();
+      best = best_sh;
+      // the winner's slot writes the node id (keys are unique: `first` is unique)
+      if (best != 0ull) {
+        for (int i = tid; i < p.table_cap; i += kSamplerThreads) {
+          if (tkeys[i] != 0) {
+            unsigned long long kk = ((unsigned long long)tscore[i] << 32) |
+                                    (unsigned long long)(0xffffffffu - tfirst[i]);
+            if (kk == best) {
+              p.out_ids[ctx * L + 1 + r] = (int64_t)tkeys[i];
+              p.out_mask[ctx * L + 1 + r] = 1.0f;
+            }
+          }
+        }
+        bound = best;
+      } else {
+        if (tid == 0) {
+          p.out_ids[ctx * L + 1 + r] = 0;
+          p.out_mask[ctx * L + 1 + r] = 0.0f;
+        }
+        bound = 0ull;
+      }
+    }
+    __syncthreads();
+    if (p.out_visited_deg && tid == 0) p.out_visited_deg[ctx] = (int64_t)deg_sh;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pair selection: one warp per target
+// ---------------------------------------------------------------------------
+constexpr int kPairMaxPos = 32;
+
+struct PairParams {
+  const int64_t* indptr;
+  const int32_t* indices;
+  const int64_t* targets;
+  const int64_t* keys;
+  int64_t n_tgt;
+  int64_t num_nodes;
+  int max_pos, min_neg, max_total, stride;
+  uint32_t seed_lo, seed_hi;
+  int64_t* out_pairs;
+  float* out_labels;
+  int64_t* out_num;
+};
+
+__device__ __forceinline__ uint32_t philox_draw(uint32_t draw, uint32_t stream, uint32_t key_lo,
+                                                uint32_t key_hi, uint32_t s0, uint32_t s1) {
+  Philox4 r = philox4x32_10(draw >> 2, stream, key_lo, key_hi, s0, s1);
+  return philox_word(r, (int)(draw & 3));
+}
+
+__global__ void __launch_bounds__(128) sample_pairs_kernel(const PairParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t t = warp; t < p.n_tgt; t += n_warps) {
+    const int64_t tgt = p.targets[t];
+    const uint64_t key = (uint64_t)p.keys[t];
+    const uint32_t key_lo = (uint32_t)key, key_hi = (uint32_t)(key >> 32);
+    int64_t rs = 0; int deg = 0;
+    if (tgt >= 2 && tgt < p.num_nodes + 2) {
+      rs = __ldg(p.indptr + tgt);
+      deg = (int)(__ldg(p.indptr + tgt + 1) - rs);
+    }
+    int64_t* row = p.out_pairs + t * p.stride;
+    float* lab = p.out_labels + t * p.stride;
+    for (int i = lane; i < p.stride; i += 32) { row[i] = 0; lab[i] = 0.0f; }
+    __syncwarp();
+    const int n_pos = p.max_pos < deg ? p.max_pos : deg;
+    int n_neg = p.max_total - n_pos;
+    if (n_neg < p.min_neg) n_neg = p.min_neg;
+    if (lane == 0) {
+      // partial Fisher-Yates over positions 0..deg-1 with a sparse swap list
+      int sw_from[kPairMaxPos], sw_to[kPairMaxPos];
+      int n_sw = 0;
+      for (int i = 0; i < n_pos; ++i) {
+        uint32_t w = philox_draw((uint32_t)i, PMGT_STREAM_POS, key_lo, key_hi, p.seed_lo, p.seed_hi);
+        int j = i + (int)(((uint64_t)w * (uint64_t)(deg - i)) >> 32);
+        // value currently at position j and at position i
+        int vj = j, vi = i;
+        for (int s = 0; s < n_sw; ++s) { if (sw_from[s] == j) vj = sw_to[s]; if (sw_from[s] == i) vi = sw_to[s]; }
+        // perm[i] = vj ; perm[j] = vi
+        bool found = false;
+        for (int s = 0; s < n_sw; ++s) if (sw_from[s] == j) { sw_to[s] = vi; found = true; }
+        if (!found && n_sw < kPairMaxPos) { sw_from[n_sw] = j; sw_to[n_sw] = vi; ++n_sw; }
+        row[i] = (int64_t)__ldg(p.indices + rs + vj);
+        lab[i] = 1.0f;
+      }
+      p.out_num[t] = (int64_t)(n_pos + n_neg);
+    }
+    for (int n = 0; n < n_neg; ++n) {
+      int64_t cand = 0;
+      for (int a = 0; a < PMGT_MAX_NEG_ATTEMPTS; ++a) {
+        uint32_t w = philox_draw((uint32_t)(n * PMGT_MAX_NEG_ATTEMPTS + a), PMGT_STREAM_NEG, key_lo,
+                                 key_hi, p.seed_lo, p.seed_hi);
+        cand = 2 + (int64_t)(((uint64_t)w * (uint64_t)p.num_nodes) >> 32);
+        bool hit = false;
+        for (int j = lane; j < deg; j += 32) hit |= ((int64_t)__ldg(p.indices + rs + j) == cand);
+        if (!__any_sync(0xffffffffu, hit)) break;
+      }
+      if (lane == 0) { row[n_pos + n] = cand; lab[n_pos + n] = 0.0f; }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace pmgt
+
+using namespace pmgt;
+
+extern "C" {
+
+int pmgt_graph_create(pmgt_graph** out, int device, int64_t num_nodes, int64_t num_edges,
+                      const int64_t* indptr_host, const int32_t* indices_host,
+                      const float* cdf_host) {
+  PMGT_REQUIRE(out && indptr_host && (num_edges == 0 || (indices_host && cdf_host)),
+               "pmgt_graph_create: null argument");
+  PMGT_REQUIRE(num_nodes > 0 && num_edges >= 0 && num_nodes < (int64_t)0x7fffffff - 2,
+               "pmgt_graph_create: bad sizes (num_nodes=%lld num_edges=%lld)", (long long)num_nodes,
+               (long long)num_edges);
+  PMGT_REQUIRE(indptr_host[0] == 0 && indptr_host[num_nodes + 2] == num_edges,
+               "pmgt_graph_create: indptr must have num_nodes+3 entries spanning [0, num_edges]");
+  PMGT_CHECK_CUDA(cudaSetDevice(device));
+  pmgt_graph_impl* g = new pmgt_graph_impl();
+  g->device = device; g->num_nodes = num_nodes; g->num_edges = num_edges;
+  g->indptr = nullptr; g->indices = nullptr; g->cdf = nullptr;
+  cudaError_t e = cudaMalloc(&g->indptr, sizeof(int64_t) * (num_nodes + 3));
+  if (e == cudaSuccess) e = cudaMalloc(&g->indices, sizeof(int32_t) * (num_edges > 0 ? num_edges : 1));
+  if (e == cudaSuccess) e = cudaMalloc(&g->cdf, sizeof(float) * (num_edges > 0 ? num_edges : 1));
+  if (e == cudaSuccess) e = cudaMemcpy(g->indptr, indptr_host, sizeof(int64_t) * (num_nodes + 3), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && num_edges) e = cudaMemcpy(g->indices, indices_host, sizeof(int32_t) * num_edges, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && num_edges) e = cudaMemcpy(g->cdf, cdf_host, sizeof(float) * num_edges, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("pmgt_graph_create: %s", cudaGetErrorString(e));
+    cudaFree(g->indptr); cudaFree(g->indices); cudaFree(g->cdf);
+    delete g;
+    return PMGT_ERR_CUDA;
+  }
+  *out = reinterpret_cast<pmgt_graph*>(g);
+  return PMGT_OK;
+}
+
+int pmgt_graph_destroy(pmgt_graph* gh) {
+  if (!gh) return PMGT_OK;
+  pmgt_graph_impl* g = reinterpret_cast<pmgt_graph_impl*>(gh);
+  cudaFree(g->indptr); cudaFree(g->indices); cudaFree(g->cdf);
+  delete g;
+  return PMGT_OK;
+}
+
+int64_t pmgt_graph_num_nodes(const pmgt_graph* g) { return g ? reinterpret_cast<const pmgt_graph_impl*>(g)->num_nodes : -1; }
+int64_t pmgt_graph_num_edges(const pmgt_graph* g) { return g ? reinterpret_cast<const pmgt_graph_impl*>(g)->num_edges : -1; }
+const int64_t* pmgt_graph_indptr(const pmgt_graph* g) { return g ? reinterpret_cast<const pmgt_graph_impl*>(g)->indptr : nullptr; }
+const int32_t* pmgt_graph_indices(const pmgt_graph* g) { return g ? reinterpret_cast<const pmgt_graph_impl*>(g)->indices : nullptr; }
+const float* pmgt_graph_cdf(const pmgt_graph* g) { return g ? reinterpret_cast<const pmgt_graph_impl*>(g)->cdf : nullptr; }
+
+int pmgt_sample_contexts(const pmgt_graph* gh, const int64_t* roots, const int64_t* ctx_keys,
+                         int64_t n_ctx, const int32_t* hops_host, int depth, int max_ctx,
+                         uint64_t seed, int64_t* out_ids, float* out_mask,
+                         int64_t* out_visited_deg, void* stream) {
+  PMGT_REQUIRE(gh && roots && ctx_keys && hops_host && out_ids && out_mask,
+               "pmgt_sample_contexts: null argument");
+  PMGT_REQUIRE(depth >= 1 && depth <= kMaxDepth, "pmgt_sample_contexts: depth must be in [1,%d]", kMaxDepth);
+  PMGT_REQUIRE(max_ctx >= 1 && max_ctx <= 1024, "pmgt_sample_contexts: max_ctx out of range");
+  if (n_ctx == 0) return PMGT_OK;
+  PMGT_REQUIRE(n_ctx > 0, "pmgt_sample_contexts: negative n_ctx");
+  const pmgt_graph_impl* g = reinterpret_cast<const pmgt_graph_impl*>(gh);
+  SamplerParams p{};
+  p.indptr = g->indptr; p.indices = g->indices; p.cdf = g->cdf;
+  p.roots = roots; p.keys = ctx_keys; p.n_ctx = n_ctx; p.n_node_ids = g->num_nodes + 2;
+  p.depth = depth; p.max_ctx = max_ctx;
+  int64_t level = 1, total = 0, stored = 1;
+  for (int k = 0; k < depth; ++k) {
+    PMGT_REQUIRE(hops_host[k] >= 1, "pmgt_sample_contexts: hop size must be >= 1");
+    p.hops[k] = hops_host[k];
+    level *= hops_host[k];
+    total += level;
+    PMGT_REQUIRE(total <= 16384, "pmgt_sample_contexts: more than 16384 draws per context");
+    if (k < depth - 1) stored = level;
+  }
+  p.list_cap = (int)stored;
+  int cap = 64;
+  while (cap < (total * 3 + 1) / 2) cap <<= 1;
+  p.table_cap = cap;
+  int lg = 0; while ((1 << lg) < cap) ++lg;
+  p.table_shift = 32 - lg;
+  p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+  p.out_ids = out_ids; p.out_mask = out_mask; p.out_visited_deg = out_visited_deg;
+  size_t smem = sizeof(int32_t) * 2 * (size_t)p.list_cap + 12 * (size_t)cap;
+  PMGT_CHECK_CUDA(cudaSetDevice(g->device));
+  if (smem > 48 * 1024)
+    PMGT_CHECK_CUDA(cudaFuncSetAttribute(sample_contexts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  PMGT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_contexts_kernel, kSamplerThreads, smem));
+  if (occ < 1) occ = 1;
+  int64_t grid = (int64_t)num_sms() * occ;
+  if (grid > n_ctx) grid = n_ctx;
+  sample_contexts_kernel<<<(unsigned)grid, kSamplerThreads, smem, (cudaStream_t)stream>>>(p);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+int pmgt_sample_pairs(const pmgt_graph* gh, const int64_t* targets, const int64_t* tgt_keys,
+                      int64_t n_tgt, int max_pos, int min_neg, int max_total, int pair_stride,
+                      uint64_t seed, int64_t* out_pairs, float* out_labels,
+                      int64_t* out_num_pairs, void* stream) {
+  PMGT_REQUIRE(gh && targets && tgt_keys && out_pairs && out_labels && out_num_pairs,
+               "pmgt_sample_pairs: null argument");
+  PMGT_REQUIRE(max_pos >= 0 && max_pos <= kPairMaxPos, "pmgt_sample_pairs: max_pos must be in [0,%d]", kPairMaxPos);
+  PMGT_REQUIRE(min_neg >= 0 && max_total >= 0, "pmgt_sample_pairs: negative sizes");
+  int need = max_pos + (min_neg > max_total ? min_neg : max_total);
+  PMGT_REQUIRE(pair_stride >= 1 && pair_stride <= 4096, "pmgt_sample_pairs: bad pair_stride");
+  {
+    // worst case row length: n_pos + max(min_neg, max_total - n_pos) <= max(max_pos + min_neg, max_total)
+    int worst = max_pos + min_neg > max_total ? max_pos + min_neg : max_total;
+    PMGT_REQUIRE(pair_stride >= worst, "pmgt_sample_pairs: pair_stride %d < %d", pair_stride, worst);
+    (void)need;
+  }
+  if (n_tgt == 0) return PMGT_OK;
+  const pmgt_graph_impl* g = reinterpret_cast<const pmgt_graph_impl*>(gh);
+  PairParams p{};
+  p.indptr = g->indptr; p.indices = g->indices; p.targets = targets; p.keys = tgt_keys;
+  p.n_tgt = n_tgt; p.num_nodes = g->num_nodes;
+  p.max_pos = max_pos; p.min_neg = min_neg; p.max_total = max_total; p.stride = pair_stride;
+  p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+  p.out_pairs = out_pairs; p.out_labels = out_labels; p.out_num = out_num_pairs;
+  PMGT_CHECK_CUDA(cudaSetDevice(g->device));
+  int64_t blocks = (n_tgt + 3) / 4;
+  int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  sample_pairs_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(p);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+"""Item graph in CSR form -- the device-resident replacement for the weighted
+``nx.Graph`` the reference samples from (``pmgt/pmgt/trainer.py:34-41``,
+``pmgt/pmgt/datasets.py:27-32``).
+
+Node-id space is the reference's: 0 = ``<pad>``, 1 = ``<mask>``, real nodes
+``2..N+1`` (datasets.py:96-102).  ``indptr`` is indexed by node id and has
+``N + 3`` entries.  Row order is the graph's adjacency *insertion* order, so an
+inverse-CDF position means the same neighbour as in the reference.
+"""
+from typing import Optional
+
+import numpy as np
+
+
+def _row_softmax_cdf(indptr: np.ndarray, weights: np.ndarray) -> np.ndarray:
+    """Running softmax CDF per CSR row (vectorised), fp64 math, fp32 result.
+
+    Reference: ``ss.softmax(weights)`` (datasets.py:27-29) followed by numpy's
+    legacy ``choice``: ``cdf = p.cumsum(); cdf /= cdf[-1]``.
+    """
+    n_rows = len(indptr) - 1
+    deg = np.diff(indptr)
+    if len(weights) == 0:
+        return np.zeros(0, dtype=np.float32)
+    w = np.asarray(weights, dtype=np.float64)
+    row_of = np.repeat(np.arange(n_rows), deg)
+    row_max = np.full(n_rows, -np.inf)
+    np.maximum.at(row_max, row_of, w)
+    e = np.exp(w - row_max[row_of])
+    c = np.cumsum(e)
+    starts = indptr[:-1]
+    nz = deg > 0
+    # subtract the running total before each row
+    before = np.zeros(n_rows)
+    before[nz] = np.where(starts[nz] > 0, c[np.maximum(starts[nz] - 1, 0)], 0.0)
+    c = c - before[row_of]
+    row_sum = np.zeros(n_rows)
+    row_sum[nz] = c[indptr[1:][nz] - 1]
+    cdf = (c / row_sum[row_of]).astype(np.float32)
+    cdf[indptr[1:][nz] - 1] = 1.0
+    return cdf
+
+
+class ItemGraph:
+    """CSR item graph + per-row softmax CDF; optionally resident on a GPU."""
+
+    def __init__(self, num_nodes: int, indptr: np.ndarray, indices: np.ndarray,
+                 weights: np.ndarray, cdf: Optional[np.ndarray] = None):
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        weights = np.ascontiguousarray(weights, dtype=np.float32)
+        if indptr.shape != (num_nodes + 3,):
+            raise ValueError(f"indptr must have num_nodes+3={num_nodes + 3} entries, got {indptr.shape}")
+        if indptr[0] != 0 or indptr[-1] != len(indices) or np.any(np.diff(indptr) < 0):
+            raise ValueError("indptr is not a valid CSR row-pointer array")
+        if indptr[2] != 0:
+            raise ValueError("rows 0 (<pad>) and 1 (<mask>) must be empty")
+        if len(indices) and (indices.min() < 2 or indices.max() > num_nodes + 1):
+            raise ValueError("neighbour ids must lie in [2, num_nodes+1]")
+        if len(weights) != len(indices):
+            raise ValueError("weights and indices differ in length")
+        self.num_nodes = int(num_nodes)
+        self.indptr = indptr
+        self.indices = indices
+        self.weights = weights
+        self.cdf = np.ascontiguousarray(cdf, dtype=np.float32) if cdf is not None else _row_softmax_cdf(indptr, weights)
+        self._handles = {}  # device index -> opaque pmgt_graph*
+
+    # -- nx.Graph-like surface used by the reference's callers -----------------
+    def __len__(self) -> int:  # len(graph) == number of nodes (trainer.py:127, datasets.py:101)
+        return self.num_nodes
+
+    @property
+    def num_edges_directed(self) -> int:
+        return int(len(self.indices))
+
+    def degree(self, node: int) -> int:
+        return int(self.indptr[node + 1] - self.indptr[node])
+
+    def neighbors(self, node: int) -> np.ndarray:
+        return self.indices[self.indptr[node]: self.indptr[node + 1]]
+
+    # -- constructors -----------------------------------------------------------
+    @classmethod
+    def from_networkx(cls, graph) -> "ItemGraph":
+        """Convert a weighted ``nx.Graph`` whose nodes are already relabelled to
+        ints ``2..N+1`` (trainer.py:38-41), keeping adjacency insertion order."""
+        n = len(graph)
+        indptr = np.zeros(n + 3, dtype=np.int64)
+        idx, wts = [], []
+        for node in range(2, n + 2):
+            if node not in graph:
+                raise ValueError(f"graph nodes must be labelled 2..{n + 1}; {node} is missing")
+            adj = graph[node]
+            idx.extend(adj.keys())
+            wts.extend(d["weight"] for d in adj.values())
+            indptr[node + 1] = len(idx)
+        return cls(n, indptr, np.asarray(idx, dtype=np.int32), np.asarray(wts, dtype=np.float32))
+
+    @classmethod
+    def from_edge_list(cls, num_nodes: int, src: np.ndarray, dst: np.ndarray, weight: np.ndarray) -> "ItemGraph":
+        """Undirected edge list (node ids in ``2..N+1``) -> CSR, reproducing the
+        adjacency insertion order ``nx.Graph.add_weighted_edges_from`` would give
+        (edge i appends dst to src's row and src to dst's row, in edge order)."""
+        src = np.asarray(src, dtype=np.int64)
+        dst = np.asarray(dst, dtype=np.int64)
+        weight = np.asarray(weight, dtype=np.float32)
+        m = len(src)
+        order = np.arange(m, dtype=np.int64)
+        rows = np.concatenate([src, dst])
+        cols = np.concatenate([dst, src])
+        wts = np.concatenate([weight, weight])
+        seq = np.concatenate([2 * order, 2 * order + 1])
+        loops = src == dst
+        if loops.any():  # a self loop is a single adjacency entry
+            keep = np.concatenate([np.ones(m, bool), ~loops])
+            rows, cols, wts, seq = rows[keep], cols[keep], wts[keep], seq[keep]
+        perm = np.lexsort((seq, rows))
+        rows, cols, wts = rows[perm], cols[perm], wts[perm]
+        counts = np.bincount(rows, minlength=num_nodes + 2)
+        indptr = np.zeros(num_nodes + 3, dtype=np.int64)
+        np.cumsum(counts, out=indptr[1:])
+        return cls(num_nodes, indptr, cols.astype(np.int32), wts)
+
+    # -- device residency ---------------------------------------------------------
+    def device_handle(self, device_index: int):
+        """Opaque ``pmgt_graph*`` for ``cuda:device_index`` (created on first use)."""
+        from . import _lib
+
+        h = self._handles.get(device_index)
+        if h is None:
+            h = _lib.graph_create(device_index, self.num_nodes, self.indptr, self.indices, self.cdf)
+            self._handles[device_index] = h
+        return h
+
+    def isolated_nodes(self) -> np.ndarray:
+        deg = np.diff(self.indptr)[2:]
+        return np.nonzero(deg == 0)[0] + 2
+
+    def __del__(self):
+        try:
+            from . import _lib
+
+            for h in self._handles.values():
+                _lib.graph_destroy(h)
+        except Exception:
+            pass
+        self._handles = {}
