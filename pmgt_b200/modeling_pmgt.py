@@ -1,0 +1,715 @@
+"""Host-side mirror of ``pmgt/pmgt/modeling_pmgt.py``.
+
+Same class names, constructor arguments, forward signatures and state-dict keys
+as the reference; the computation underneath is ``libpmgt_b200.so`` (sm_100a
+CUDA through the C ABI).  ``nn.Linear`` / ``nn.Embedding`` / ``nn.LayerNorm``
+objects are used purely as *parameter containers* so that
+``state_dict()`` / ``load_state_dict()`` interchange with reference checkpoints
+both ways; their ``forward`` is never called.
+
+Numerics: parameters are fp32 (master copy); every GEMM runs on tcgen05 tensor
+cores with bf16 operands and fp32 accumulation; activations are stored in
+bf16; softmax / LayerNorm / losses are computed in fp32.
+
+There is no CPU path: calling ``forward`` with CPU tensors raises.
+"""
+from dataclasses import dataclass, fields
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import PMGTError
+from .configuration_pmgt import PMGTConfig
+
+BF16 = torch.bfloat16
+_ALIGN = 8  # elements: 16-byte alignment of every bf16 tensor (TMA / vector loads); tensors whose numel is a
+# multiple of 8 are packed back to back, which the [4H, H] "span" views over q/k/v/ctx rely on
+
+
+# ---------------------------------------------------------------------------
+# outputs (modeling_pmgt.py:572-579, transformers ModelOutput semantics)
+# ---------------------------------------------------------------------------
+class _ModelOutput:
+    """Minimal ``transformers.file_utils.ModelOutput``: attribute + key access,
+    and integer indexing over the non-``None`` fields (which is why the
+    reference's ``net(x)[0]`` is the loss in training and ``last_hidden_state``
+    at inference, trainer.py:153-157)."""
+
+    def to_tuple(self):
+        return tuple(getattr(self, f.name) for f in fields(self) if getattr(self, f.name) is not None)
+
+    def __getitem__(self, k):
+        if isinstance(k, str):
+            v = getattr(self, k)
+            if v is None:
+                raise KeyError(k)
+            return v
+        return self.to_tuple()[k]
+
+    def __iter__(self):
+        return iter(self.to_tuple())
+
+    def __len__(self):
+        return len(self.to_tuple())
+
+    def keys(self):
+        return [f.name for f in fields(self) if getattr(self, f.name) is not None]
+
+
+@dataclass
+class BaseModelOutputWithPooling(_ModelOutput):
+    last_hidden_state: torch.Tensor = None
+    pooler_output: Optional[torch.Tensor] = None
+    hidden_states: Optional[Tuple[torch.Tensor]] = None
+    attentions: Optional[Tuple[torch.Tensor]] = None
+
+
+@dataclass
+class PMGTForPreTrainingOutput(_ModelOutput):
+    loss: Optional[torch.Tensor] = None
+    prediction_logits: Optional[torch.Tensor] = None
+    last_hidden_state: torch.Tensor = None
+    pooler_output: Optional[torch.Tensor] = None
+    hidden_states: Optional[Tuple[torch.Tensor]] = None
+    attentions: Optional[Tuple[torch.Tensor]] = None
+
+
+# ---------------------------------------------------------------------------
+# parameter containers (names == reference state-dict keys)
+# ---------------------------------------------------------------------------
+class PMGTEmbeddings(nn.Module):
+    """modeling_pmgt.py:155-187."""
+
+    def __init__(self, config):
+        super().__init__()
+        H = config.hidden_size
+        self.position_embeddings = nn.Embedding(config.max_position_embeddings, H)
+        self.role_embeddings = nn.Embedding(2, H)
+        self.feat_linear = nn.ModuleList(nn.Linear(d, H) for d in config.feat_hidden_sizes)
+        n = len(config.feat_hidden_sizes)
+        self.attention = nn.Sequential(nn.Tanh(), nn.Linear(n * H, n), nn.Softmax(dim=-1))
+        self.LayerNorm = nn.LayerNorm(H, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self.register_buffer("position_ids", torch.arange(config.max_position_embeddings).unsqueeze(0))
+        self.register_buffer("role_ids", torch.LongTensor([0] + [1] * (config.max_position_embeddings - 1)).unsqueeze(0))
+
+
+class PMGTSelfAttention(nn.Module):
+    """modeling_pmgt.py:378-399."""
+
+    def __init__(self, config):
+        super().__init__()
+        if config.hidden_size % config.num_attention_heads != 0:
+            raise ValueError(
+                f"The hidden size ({config.hidden_size}) is not a multiple of the number of attention "
+                f"heads ({config.num_attention_heads})")
+        H = config.hidden_size
+        self.num_attention_heads = config.num_attention_heads
+        self.attention_head_size = H // config.num_attention_heads
+        self.all_head_size = H
+        self.beta = config.beta
+        self.query = nn.Linear(H, H)
+        self.key = nn.Linear(H, H)
+        self.value = nn.Linear(H, H)
+        self.ctx_attention = nn.Linear(H, H)
+        self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
+
+
+class _DenseLN(nn.Module):
+    """BertSelfOutput / BertOutput parameter layout: ``dense`` + ``LayerNorm``."""
+
+    def __init__(self, in_f, out_f, eps, p):
+        super().__init__()
+        self.dense = nn.Linear(in_f, out_f)
+        self.LayerNorm = nn.LayerNorm(out_f, eps=eps)
+        self.dropout = nn.Dropout(p)
+
+
+class _Dense(nn.Module):
+    """BertIntermediate parameter layout: ``dense``."""
+
+    def __init__(self, in_f, out_f):
+        super().__init__()
+        self.dense = nn.Linear(in_f, out_f)
+
+
+class PMGTAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.self = PMGTSelfAttention(config)
+        self.output = _DenseLN(config.hidden_size, config.hidden_size, config.layer_norm_eps, config.hidden_dropout_prob)
+
+
+class PMGTLayer(nn.Module):
+    """modeling_pmgt.py:287-295."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.attention = PMGTAttention(config)
+        self.intermediate = _Dense(config.hidden_size, config.intermediate_size)
+        self.output = _DenseLN(config.intermediate_size, config.hidden_size, config.layer_norm_eps,
+                               config.hidden_dropout_prob)
+
+
+class PMGTEncoder(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.layer = nn.ModuleList([PMGTLayer(config) for _ in range(config.num_hidden_layers)])
+        self.gradient_checkpointing = False
+
+
+# ---------------------------------------------------------------------------
+# flat parameter storage
+# ---------------------------------------------------------------------------
+class FlatParams:
+    """All trainable parameters of a root module as views into ONE fp32 buffer
+    (so the bf16 shadow cast, the gradient allreduce and AdamW are single
+    launches), in an order that makes [Wq;Wk;Wv;Wc] one [4H, H] matrix."""
+
+    def __init__(self, named_params: List[Tuple[str, nn.Parameter]]):
+        self.names = [n for n, _ in named_params]
+        self.params = [p for _, p in named_params]
+        self.offsets = {}
+        self.shapes = {}
+        off = 0
+        for n, p in named_params:
+            self.offsets[n] = off
+            self.shapes[n] = tuple(p.shape)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.total = off
+        self.flat = None
+        self.flat_bf16 = None
+        self._views32 = {}
+        self._views16 = {}
+
+    def ensure(self):
+        """(Re)attach parameters to the flat buffer if ``.to()`` / ``.cuda()`` moved them."""
+        p0 = self.params[0]
+        dev = p0.device
+        if dev.type != "cuda":
+            raise PMGTError("pmgt_b200 modules must live on a CUDA device (no CPU fallback); call .cuda() first")
+        ok = self.flat is not None and self.flat.device == dev
+        if ok:
+            base = self.flat.data_ptr()
+            for n, p in zip(self.names, self.params):
+                if p.data_ptr() != base + 4 * self.offsets[n] or p.dtype != torch.float32:
+                    ok = False
+                    break
+        if not ok:
+            flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+            with torch.no_grad():
+                for n, p in zip(self.names, self.params):
+                    v = flat[self.offsets[n]: self.offsets[n] + p.numel()].view(p.shape)
+                    v.copy_(p.data.to(torch.float32))
+                    p.data = v
+            self.flat = flat
+            self.flat_bf16 = torch.empty(self.total, dtype=BF16, device=dev)
+            self._views32, self._views16 = {}, {}
+        return self
+
+    def refresh_bf16(self):
+        ops.cast_f32_bf16(self.flat, self.flat_bf16)
+
+    def _view(self, buf, cache, name, span=None):
+        key = (name, span)
+        v = cache.get(key)
+        if v is None:
+            off = self.offsets[name]
+            shape = self.shapes[name]
+            if span is not None:  # `span` consecutive same-shaped tensors as one matrix / vector
+                shape = (shape[0] * span,) + shape[1:]
+            n = 1
+            for s in shape:
+                n *= s
+            v = buf[off: off + n].view(shape)
+            cache[key] = v
+        return v
+
+    def f32(self, name, span=None):
+        return self._view(self.flat, self._views32, name, span)
+
+    def bf16(self, name, span=None):
+        return self._view(self.flat_bf16, self._views16, name, span)
+
+
+class GradArena:
+    """One fp32 buffer per backward pass holding every parameter gradient in
+    FlatParams order; autograd receives views of it."""
+
+    def __init__(self, fp: FlatParams):
+        self.fp = fp
+        self.buf = None
+
+    def get(self):
+        if self.buf is None:
+            self.buf = torch.zeros(self.fp.total, dtype=torch.float32, device=self.fp.flat.device)
+        return self.buf
+
+    def view(self, name, span=None):
+        fp = self.fp
+        off = fp.offsets[name]
+        shape = fp.shapes[name]
+        if span is not None:
+            shape = (shape[0] * span,) + shape[1:]
+        n = 1
+        for s in shape:
+            n *= s
+        return self.get()[off: off + n].view(shape)
+
+
+def encoder_param_order(bert: "PMGTModel", prefix: str = "") -> List[Tuple[str, nn.Parameter]]:
+    """Flat order of the encoder's trainable parameters (names carry ``prefix``)."""
+    e = bert.embeddings
+    out = [
+        ("embeddings.feat_linear.0.weight", e.feat_linear[0].weight),
+        ("embeddings.feat_linear.1.weight", e.feat_linear[1].weight),
+        ("embeddings.feat_linear.0.bias", e.feat_linear[0].bias),
+        ("embeddings.feat_linear.1.bias", e.feat_linear[1].bias),
+        ("embeddings.attention.1.weight", e.attention[1].weight),
+        ("embeddings.attention.1.bias", e.attention[1].bias),
+        ("embeddings.position_embeddings.weight", e.position_embeddings.weight),
+        ("embeddings.role_embeddings.weight", e.role_embeddings.weight),
+        ("embeddings.LayerNorm.weight", e.LayerNorm.weight),
+        ("embeddings.LayerNorm.bias", e.LayerNorm.bias),
+    ]
+    for i, l in enumerate(bert.encoder.layer):
+        p = f"encoder.layer.{i}."
+        s = l.attention.self
+        out += [(p + f"attention.self.{n}.weight", getattr(s, n).weight) for n in ("query", "key", "value", "ctx_attention")]
+        out += [(p + f"attention.self.{n}.bias", getattr(s, n).bias) for n in ("query", "key", "value", "ctx_attention")]
+        out += [
+            (p + "attention.output.dense.weight", l.attention.output.dense.weight),
+            (p + "attention.output.dense.bias", l.attention.output.dense.bias),
+            (p + "attention.output.LayerNorm.weight", l.attention.output.LayerNorm.weight),
+            (p + "attention.output.LayerNorm.bias", l.attention.output.LayerNorm.bias),
+            (p + "intermediate.dense.weight", l.intermediate.dense.weight),
+            (p + "intermediate.dense.bias", l.intermediate.dense.bias),
+            (p + "output.dense.weight", l.output.dense.weight),
+            (p + "output.dense.bias", l.output.dense.bias),
+            (p + "output.LayerNorm.weight", l.output.LayerNorm.weight),
+            (p + "output.LayerNorm.bias", l.output.LayerNorm.bias),
+        ]
+    return [(prefix + n, p) for n, p in out]
+
+
+# ---------------------------------------------------------------------------
+# encoder forward / backward orchestration
+# ---------------------------------------------------------------------------
+class _EncoderRun:
+    """Activations of one encoder pass kept for the backward pass."""
+    __slots__ = ("R", "L", "T", "mask", "rows_idx", "src", "src_rows", "ev", "et", "x0", "layers", "seed", "p_hid",
+                 "p_att", "hidden_f32")
+
+
+def _encode_forward(fp: FlatParams, pre: str, cfg: PMGTConfig, src: List[torch.Tensor], rows_idx, R: int, L: int,
+                    mask: torch.Tensor, training: bool, seed: int, keep: bool):
+    """PMGTModel.forward (modeling_pmgt.py:80-152) on ``R`` sequences of length ``L``.
+
+    ``src``: per modality either the bf16 feature table (``rows_idx`` = flat int64
+    node ids, fused gather) or a dense bf16 ``[T, D]`` matrix (``rows_idx`` None).
+    Returns (hidden_f32 [R, L, H], run-or-None).
+    """
+    H, I, heads = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
+    T = R * L
+    dev = mask.device
+    p_hid = float(cfg.hidden_dropout_prob) if training else 0.0
+    p_att = float(cfg.attention_probs_dropout_prob) if training else 0.0
+    E = pre + "embeddings."
+
+    def new(*shape, dtype=BF16):
+        return torch.empty(shape, dtype=dtype, device=dev)
+
+    # K2: (gathered) per-modality projections on tensor cores, then the fusion kernel
+    proj = []
+    for m in range(2):
+        out = new(T, H)
+        ops.linear_fwd(src[m], fp.bf16(f"{E}feat_linear.{m}.weight"), fp.f32(f"{E}feat_linear.{m}.bias"), out,
+                       rows=rows_idx, src_rows=(src[m].shape[0] if rows_idx is not None else 0))
+        proj.append(out)
+    x = new(T, H)
+    ea = ops.embed_args(R, L, H, proj[0], proj[1], fp.f32(E + "attention.1.weight"), fp.f32(E + "attention.1.bias"),
+                        fp.f32(E + "position_embeddings.weight"), fp.f32(E + "role_embeddings.weight"),
+                        fp.f32(E + "LayerNorm.weight"), fp.f32(E + "LayerNorm.bias"), cfg.layer_norm_eps, p_hid, seed, 0,
+                        x_out=x)
+    ops.embed_fuse_fwd(ea)
+
+    run = None
+    if keep:
+        run = _EncoderRun()
+        run.R, run.L, run.T, run.mask, run.rows_idx = R, L, T, mask, rows_idx
+        run.src, run.src_rows = src, [s.shape[0] for s in src]
+        run.ev, run.et, run.x0, run.layers = proj[0], proj[1], x, []
+        run.seed, run.p_hid, run.p_att = seed, p_hid, p_att
+
+    n_layers = cfg.num_hidden_layers
+    hidden_f32 = new(T, H, dtype=torch.float32)
+    for i in range(n_layers):
+        P = f"{pre}encoder.layer.{i}."
+        site = 10 * (i + 1)
+        qkvc = new(T, 4 * H)
+        ops.linear_fwd(x, fp.bf16(P + "attention.self.query.weight", 4), fp.f32(P + "attention.self.query.bias", 4), qkvc)
+        ctx = new(T, H)
+        ops.attn_core_fwd(ops.attn_args(R, L, H, heads, float(cfg.beta), qkvc, mask, p_att, seed, site, ctx=ctx))
+        o1 = new(T, H)
+        ops.linear_fwd(ctx, fp.bf16(P + "attention.output.dense.weight"), fp.f32(P + "attention.output.dense.bias"), o1)
+        a = new(T, H)
+        ops.res_ln_fwd(ops.resln_args(T, H, o1, x, fp.f32(P + "attention.output.LayerNorm.weight"),
+                                      fp.f32(P + "attention.output.LayerNorm.bias"), cfg.layer_norm_eps, p_hid, seed,
+                                      site + 3, y=a))
+        h_pre = new(T, I)
+        h = new(T, I)
+        ops.linear_fwd(a, fp.bf16(P + "intermediate.dense.weight"), fp.f32(P + "intermediate.dense.bias"), h,
+                       gelu_aux=h_pre)
+        o2 = new(T, H)
+        ops.linear_fwd(h, fp.bf16(P + "output.dense.weight"), fp.f32(P + "output.dense.bias"), o2)
+        y = new(T, H)
+        last = i == n_layers - 1
+        ops.res_ln_fwd(ops.resln_args(T, H, o2, a, fp.f32(P + "output.LayerNorm.weight"),
+                                      fp.f32(P + "output.LayerNorm.bias"), cfg.layer_norm_eps, p_hid, seed, site + 4,
+                                      y=y, y_f32=(hidden_f32 if last else None)))
+        if keep:
+            run.layers.append((x, qkvc, ctx, o1, a, h_pre, h, o2))
+        x = y
+    if n_layers == 0:
+        hidden_f32 = x.float()
+    return hidden_f32.view(R, L, H), run
+
+
+def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun, d_hidden: torch.Tensor,
+                     arena: GradArena):
+    """Reverse of ``_encode_forward``; parameter gradients are accumulated into ``arena``."""
+    H, I, heads = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
+    R, L, T = run.R, run.L, run.T
+    dev = d_hidden.device
+    seed, p_hid, p_att = run.seed, run.p_hid, run.p_att
+
+    def new(*shape, dtype=BF16):
+        return torch.empty(shape, dtype=dtype, device=dev)
+
+    G = arena.view
+    dy_f32 = d_hidden.contiguous().view(T, H)
+    dy = None
+    for i in reversed(range(cfg.num_hidden_layers)):
+        P = f"{pre}encoder.layer.{i}."
+        site = 10 * (i + 1)
+        x, qkvc, ctx, o1, a, h_pre, h, o2 = run.layers[i]
+        # ---- BertOutput: LayerNorm(dropout(dense(h)) + a)
+        dz2 = new(T, H)
+        do2 = new(T, H) if p_hid > 0 else dz2
+        ops.res_ln_bwd(ops.resln_args(T, H, o2, a, fp.f32(P + "output.LayerNorm.weight"), None, cfg.layer_norm_eps,
+                                      p_hid, seed, site + 4, dy=dy, dy_f32=dy_f32, dz=dz2, d_o=do2,
+                                      d_g=G(P + "output.LayerNorm.weight"), d_b=G(P + "output.LayerNorm.bias"),
+                                      d_bias=G(P + "output.dense.bias")))
+        dy_f32 = None
+        ops.linear_dw(do2, h, G(P + "output.dense.weight"))
+        dh_pre = new(T, I)
+        ops.linear_dx(do2, fp.bf16(P + "output.dense.weight"), dh_pre, gelu_bwd_aux=h_pre)
+        # ---- BertIntermediate
+        ops.colsum(dh_pre, G(P + "intermediate.dense.bias"))
+        ops.linear_dw(dh_pre, a, G(P + "intermediate.dense.weight"))
+        da = new(T, H)
+        ops.linear_dx(dh_pre, fp.bf16(P + "intermediate.dense.weight"), da, addend=dz2)
+        # ---- BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x)
+        dz1 = new(T, H)
+        do1 = new(T, H) if p_hid > 0 else dz1
+        ops.res_ln_bwd(ops.resln_args(T, H, o1, x, fp.f32(P + "attention.output.LayerNorm.weight"), None,
+                                      cfg.layer_norm_eps, p_hid, seed, site + 3, dy=da, dz=dz1, d_o=do1,
+                                      d_g=G(P + "attention.output.LayerNorm.weight"),
+                                      d_b=G(P + "attention.output.LayerNorm.bias"),
+                                      d_bias=G(P + "attention.output.dense.bias")))
+        ops.linear_dw(do1, ctx, G(P + "attention.output.dense.weight"))
+        dctx = new(T, H)
+        ops.linear_dx(do1, fp.bf16(P + "attention.output.dense.weight"), dctx)
+        # ---- dual-softmax attention core
+        dqkvc = new(T, 4 * H)
+        ops.attn_core_bwd(ops.attn_args(R, L, H, heads, float(cfg.beta), qkvc, run.mask, p_att, seed, site, dctx=dctx,
+                                        dqkvc=dqkvc, d_bias_qkvc=G(P + "attention.self.query.bias", 4)))
+        ops.linear_dw(dqkvc, x, G(P + "attention.self.query.weight", 4))
+        dx = new(T, H)
+        ops.linear_dx(dqkvc, fp.bf16(P + "attention.self.query.weight", 4), dx, addend=dz1)
+        dy = dx
+    if dy is None:  # zero layers
+        dy = dy_f32.to(BF16)
+    # ---- embeddings
+    E = pre + "embeddings."
+    dev_, det_ = new(T, H), new(T, H)
+    ea = ops.embed_args(R, L, H, run.ev, run.et, fp.f32(E + "attention.1.weight"), fp.f32(E + "attention.1.bias"),
+                        fp.f32(E + "position_embeddings.weight"), fp.f32(E + "role_embeddings.weight"),
+                        fp.f32(E + "LayerNorm.weight"), fp.f32(E + "LayerNorm.bias"), cfg.layer_norm_eps, p_hid, seed, 0,
+                        dx=dy, dev=dev_, det=det_, d_w_att=G(E + "attention.1.weight"), d_b_att=G(E + "attention.1.bias"),
+                        d_pos=G(E + "position_embeddings.weight"), d_role=G(E + "role_embeddings.weight"),
+                        d_ln_g=G(E + "LayerNorm.weight"), d_ln_b=G(E + "LayerNorm.bias"),
+                        d_bias_v=G(E + "feat_linear.0.bias"), d_bias_t=G(E + "feat_linear.1.bias"))
+    ops.embed_fuse_bwd(ea)
+    for m, d in enumerate((dev_, det_)):
+        ops.linear_dw(d, run.src[m], G(f"{E}feat_linear.{m}.weight"), rows=run.rows_idx,
+                      src_rows=(run.src_rows[m] if run.rows_idx is not None else 0), x_cols=run.src[m].shape[1])
+
+
+class _EncodeFn(torch.autograd.Function):
+    """Autograd node for one batched encoder pass.  ``params`` are passed only so
+    that autograd routes their gradients; the data is read from ``fp``."""
+
+    @staticmethod
+    def forward(ctx, host, src_v, src_t, rows_idx, mask, R, L, training, seed, arena, keep, *params):
+        fp, pre, cfg = host._fp, host._fp_prefix, host.config
+        hidden, run = _encode_forward(fp, pre, cfg, [src_v, src_t], rows_idx, R, L, mask, training, seed, keep)
+        ctx.host, ctx.run, ctx.arena, ctx.n_params = host, run, arena, len(params)
+        return hidden
+
+    @staticmethod
+    def backward(ctx, d_hidden):
+        host, run, arena = ctx.host, ctx.run, ctx.arena
+        if run is None:
+            raise PMGTError("encoder backward called but activations were not kept")
+        fp, pre, cfg = host._fp, host._fp_prefix, host.config
+        _encode_backward(fp, pre, cfg, run, d_hidden, arena)
+        ctx.run = None
+        grads = tuple(arena.view(n) for n in host._encoder_param_names)
+        return (None,) * 11 + grads
+
+
+class PMGTPretrainedModel(nn.Module):
+    """Weight init of modeling_pmgt.py:34-62 (N(0, initializer_range) for Linear /
+    Embedding weights, zeros for biases, ones/zeros for LayerNorm)."""
+
+    config_class = PMGTConfig
+    base_model_prefix = "pmgt"
+    supports_gradient_checkpointing = True
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+
+    def _init_weights(self, module):
+        if isinstance(module, nn.Linear):
+            module.weight.data.normal_(mean=0.0, std=self.config.initializer_range)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.Embedding):
+            module.weight.data.normal_(mean=0.0, std=self.config.initializer_range)
+            if module.padding_idx is not None:
+                module.weight.data[module.padding_idx].zero_()
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+
+    def init_weights(self):
+        self.apply(self._init_weights)
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+
+_seed_counter = [0]
+
+
+def next_dropout_seed() -> int:
+    """A fresh 64-bit Philox seed per forward pass, derived from torch's seed."""
+    _seed_counter[0] += 1
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _seed_counter[0] * 0xD1342543DE82EF95) & 0xFFFFFFFFFFFFFFFF
+
+
+class PMGTModel(PMGTPretrainedModel):
+    """modeling_pmgt.py:65-152.  ``forward(*input_feat_embeds, attention_mask=...)``
+    keeps the reference signature (dense per-modality features); the fused
+    gather path used by ``PMGT`` is ``encode_ids``."""
+
+    def __init__(self, config, add_pooling_layer=False):
+        super().__init__(config)
+        if add_pooling_layer:
+            raise ValueError("the reference never enables the pooler (modeling_pmgt.py:66-72); not implemented")
+        self.embeddings = PMGTEmbeddings(config)
+        self.encoder = PMGTEncoder(config)
+        self.pooler = None
+        self.init_weights()
+        self._fp = None
+        self._fp_prefix = ""
+        self._encoder_param_names = [n for n, _ in encoder_param_order(self)]
+
+    # -- flat storage: standalone use owns its own FlatParams; inside PMGT the parent's is shared
+    def _attach(self, fp: FlatParams, prefix: str):
+        self._fp, self._fp_prefix = fp, prefix
+        self._encoder_param_names = [prefix + n for n, _ in encoder_param_order(self)]
+
+    def _flat(self) -> FlatParams:
+        if self._fp is None:
+            self._fp = FlatParams(encoder_param_order(self))
+        return self._fp.ensure()
+
+    def _encoder_params(self):
+        return [p for _, p in encoder_param_order(self)]
+
+    def encode(self, src_v, src_t, rows_idx, mask, R, L, arena=None, refresh=True):
+        fp = self._flat()
+        if refresh:
+            fp.refresh_bf16()
+        if arena is None:
+            arena = GradArena(fp)
+        seed = next_dropout_seed()
+        mask = mask.to(torch.float32).contiguous()
+        params = self._encoder_params()
+        keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _EncodeFn.apply(self, src_v, src_t, rows_idx, mask, R, L, self.training, seed, arena, keep, *params)
+
+    def forward(self, *input_feat_embeds, attention_mask=None, head_mask=None, output_attentions=None,
+                output_hidden_states=None, return_dict=None):
+        first = input_feat_embeds[0]
+        assert all(first.size()[:-1] == f.size()[:-1] for f in input_feat_embeds[1:]), \
+            "All features are same dim except last one"
+        if head_mask is not None or output_attentions or output_hidden_states:
+            raise NotImplementedError("head_mask / output_attentions / output_hidden_states are not produced by the "
+                                      "fused kernels (the reference's trainer never requests them)")
+        if not first.is_cuda:
+            raise PMGTError("PMGTModel.forward needs CUDA tensors: pmgt_b200 has no CPU fallback")
+        R, L = first.shape[:2]
+        return_dict = return_dict if return_dict is not None else self.config.use_return_dict
+        if attention_mask is None:
+            attention_mask = torch.ones(R, L, device=first.device)
+        dense = [f.reshape(R * L, f.shape[-1]).to(BF16).contiguous() for f in input_feat_embeds]
+        seq = self.encode(dense[0], dense[1], None, attention_mask, R, L)
+        if not return_dict:
+            return (seq, None)
+        return BaseModelOutputWithPooling(last_hidden_state=seq, pooler_output=None)
+
+
+# ---------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------
+class _GsrFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tgt_h0, pair_h0, pair_off, labels):
+        B, H = tgt_h0.shape
+        SP = pair_h0.shape[0]
+        dev = tgt_h0.device
+        tgt_h0 = tgt_h0 if tgt_h0.stride(1) == 1 else tgt_h0.contiguous()
+        pair_h0 = pair_h0 if pair_h0.stride(1) == 1 else pair_h0.contiguous()
+        logits = torch.empty(SP, dtype=torch.float32, device=dev)
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        ops.gsr(True, B, SP, H, tgt_h0, tgt_h0.stride(0), pair_h0, pair_h0.stride(0), pair_off, labels, logits=logits,
+                loss_out=loss)
+        ctx.save_for_backward(tgt_h0, pair_h0, pair_off, labels)
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_logits):
+        tgt_h0, pair_h0, pair_off, labels = ctx.saved_tensors
+        B, H = tgt_h0.shape
+        SP = pair_h0.shape[0]
+        d_t = torch.empty(B, H, dtype=torch.float32, device=tgt_h0.device)
+        d_p = torch.zeros(SP, H, dtype=torch.float32, device=tgt_h0.device)
+        g = g_loss.to(torch.float32).contiguous()
+        ops.gsr(False, B, SP, H, tgt_h0, tgt_h0.stride(0), pair_h0, pair_h0.stride(0), pair_off, labels, grad_out=g,
+                d_tgt=d_t, d_pair=d_p)
+        return d_t, d_p, None, None
+
+
+class PMGTGraphConstructLoss(nn.Module):
+    """modeling_pmgt.py:537-546.  ``forward(hidden_states, other_hidden_states,
+    labels)`` keeps the reference's per-target signature; ``batched`` is the
+    whole-batch form PMGT uses (one launch instead of a Python loop with a
+    device sync per target, models.py:111-124)."""
+
+    def __init__(self, config=None):
+        super().__init__()
+
+    def forward(self, hidden_states, other_hidden_states, labels):
+        off = torch.tensor([0, hidden_states.shape[0]], dtype=torch.int64, device=hidden_states.device)
+        loss, logits = _GsrFn.apply(other_hidden_states.reshape(1, -1).float(), hidden_states.float(), off,
+                                    labels.float().contiguous())
+        return loss, logits
+
+    @staticmethod
+    def batched(tgt_h0, pair_h0, pair_off, labels):
+        return _GsrFn.apply(tgt_h0, pair_h0, pair_off, labels)
+
+
+class _NfrFn(torch.autograd.Function):
+    """Projections (tensor-core GEMM) + MSE against gathered table rows, both modalities."""
+
+    @staticmethod
+    def forward(ctx, host, h_masked, target_ids, tables, arena, *params):
+        fp, pre = host._fp, host._fp_prefix
+        Mm, H = h_masked.shape
+        dev = h_masked.device
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        hb = h_masked.to(BF16).contiguous()
+        projs = []
+        n_mod = len(tables)
+        for m, table in enumerate(tables):
+            D = table.shape[1]
+            proj = torch.empty(Mm, D, dtype=BF16, device=dev)
+            if Mm > 0:
+                ops.linear_fwd(hb, fp.bf16(f"{pre}projections.{m}.weight"), fp.f32(f"{pre}projections.{m}.bias"), proj)
+            ops.nfr_mse(True, Mm, D, proj, table, target_ids, 1.0 / n_mod, loss_out=loss)
+            projs.append(proj)
+        ctx.host, ctx.arena, ctx.tables, ctx.n_params = host, arena, tables, len(params)
+        ctx.save_for_backward(hb, target_ids, *projs)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        host, arena, tables = ctx.host, ctx.arena, ctx.tables
+        fp, pre = host._fp, host._fp_prefix
+        hb, target_ids, *projs = ctx.saved_tensors
+        Mm, H = hb.shape
+        dev = hb.device
+        g = g_loss.to(torch.float32).contiguous()
+        dh = None
+        n_mod = len(tables)
+        for m, table in enumerate(tables):
+            D = table.shape[1]
+            if Mm == 0:
+                continue
+            dproj = torch.empty(Mm, D, dtype=BF16, device=dev)
+            ops.nfr_mse(False, Mm, D, projs[m], table, target_ids, 1.0 / n_mod, grad_out=g, dproj=dproj)
+            ops.colsum(dproj, arena.view(f"{pre}projections.{m}.bias"))
+            ops.linear_dw(dproj, hb, arena.view(f"{pre}projections.{m}.weight"))
+            out = torch.empty(Mm, H, dtype=BF16, device=dev)
+            ops.linear_dx(dproj, fp.bf16(f"{pre}projections.{m}.weight"), out, addend=dh)
+            dh = out
+        d_h = dh.float() if dh is not None else torch.zeros(Mm, H, dtype=torch.float32, device=dev)
+        grads = tuple(arena.view(n) for n in host._param_names)
+        return (None, d_h, None, None, None) + grads
+
+
+class PMGTNodeConstructLoss(nn.Module):
+    """modeling_pmgt.py:549-569."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.projections = nn.ModuleList([nn.Linear(config.hidden_size, d) for d in config.feat_hidden_sizes])
+        self._fp = None
+        self._fp_prefix = ""
+        self._param_names = [n for n, _ in self.param_order()]
+
+    def param_order(self, prefix: str = ""):
+        out = []
+        for m, l in enumerate(self.projections):
+            out += [(f"{prefix}projections.{m}.weight", l.weight), (f"{prefix}projections.{m}.bias", l.bias)]
+        return out
+
+    def _attach(self, fp: FlatParams, prefix: str):
+        self._fp, self._fp_prefix = fp, prefix
+        self._param_names = [n for n, _ in self.param_order(prefix)]
+
+    def from_ids(self, h_masked, target_ids, tables_bf16, arena=None):
+        if self._fp is None:
+            self._fp = FlatParams(self.param_order())
+        fp = self._fp.ensure()
+        if arena is None:
+            fp.refresh_bf16()
+            arena = GradArena(fp)
+        return _NfrFn.apply(self, h_masked, target_ids, tables_bf16, arena, *[p for _, p in self.param_order()])
+
+    def forward(self, inputs, targets):
+        """Reference signature: ``targets`` are the already-gathered feature rows."""
+        assert len(targets) == len(self.projections), f"# of multi-modal features must be {len(self.projections)}"
+        ids = torch.arange(inputs.shape[0], dtype=torch.int64, device=inputs.device)
+        tables = [t.to(BF16).contiguous() for t in targets]
+        return self.from_ids(inputs, ids, tables)

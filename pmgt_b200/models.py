@@ -1,0 +1,215 @@
+"""Host-side mirror of ``pmgt/pmgt/models.py``: the ``PMGT`` pre-training module.
+
+Same constructor / ``forward`` signature, outputs and state-dict keys as the
+reference.  What changed underneath:
+
+* the reference encodes the pair contexts in a Python loop over targets with a
+  device->host sync per target (models.py:111-124) and runs three separate
+  encoder calls; here targets, all pairs and the masked targets go through ONE
+  batched encoder pass (rows are independent, so the math is identical);
+* feature rows are gathered inside the projection GEMM from bf16 copies of the
+  frozen tables instead of being materialised by ``nn.Embedding``;
+* both losses are fused reduction kernels.
+
+The NFR corruption (models.py:131-151) stays host PyTorch code issued in the
+reference's order, so the same ``torch.manual_seed`` corrupts the same nodes.
+"""
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ._lib import PMGTError
+from .configuration_pmgt import PMGTConfig
+from .modeling_pmgt import (BF16, FlatParams, GradArena, PMGTForPreTrainingOutput, PMGTGraphConstructLoss, PMGTModel,
+                            PMGTNodeConstructLoss, PMGTPretrainedModel, encoder_param_order)
+from .utils import get_input_feat_embeds  # noqa: F401  (re-exported like the reference module)
+
+
+class _TakeRows(torch.autograd.Function):
+    """rows = hidden_flat[idx]; backward scatters into one zero buffer (idx unique)."""
+
+    @staticmethod
+    def forward(ctx, hidden_flat, idx):
+        ctx.save_for_backward(idx)
+        ctx.shape = hidden_flat.shape
+        return hidden_flat.index_select(0, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        out = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
+        out.index_copy_(0, idx, g)
+        return out, None
+
+
+class PMGT(PMGTPretrainedModel):
+    def __init__(
+        self,
+        node_size: int,
+        random_node_ratio: float = 0.2 * 0.1,
+        mask_node_ratio: float = 0.2 * 0.8,
+        config: PMGTConfig = None,
+        feat_init_emb: Optional[List[np.ndarray]] = None,
+    ) -> None:
+        config = config if config is not None else PMGTConfig()
+        super().__init__(config)
+        self.node_size = node_size
+        self.random_node_ratio = random_node_ratio
+        self.mask_node_ratio = mask_node_ratio
+        self.config = config
+        self.bert = PMGTModel(config)
+        self.gsr_loss = PMGTGraphConstructLoss(config)
+        self.nfr_loss = PMGTNodeConstructLoss(config)
+
+        # idx 0 is <pad>, idx 1 is <mask> (models.py:40-47).  The tables are frozen
+        # feature stores; torch tensors (any device / dtype) are adopted without a copy.
+        tables = []
+        for m, d in enumerate(config.feat_hidden_sizes):
+            if feat_init_emb is not None and isinstance(feat_init_emb[m], torch.Tensor):
+                w = feat_init_emb[m]
+                assert tuple(w.shape) == (node_size + 2, d), f"feature table {m} must be {(node_size + 2, d)}"
+                emb = nn.Embedding(1, 1, padding_idx=0)
+                emb.num_embeddings, emb.embedding_dim = node_size + 2, d
+                emb.weight = nn.Parameter(w, requires_grad=False)
+            else:
+                emb = nn.Embedding(node_size + 2, d, padding_idx=0)
+                if feat_init_emb is not None:
+                    with torch.no_grad():
+                        emb.weight.copy_(torch.from_numpy(np.asarray(feat_init_emb[m])))
+            emb.requires_grad_(False)
+            tables.append(emb)
+        if feat_init_emb is not None:
+            assert len(feat_init_emb) == len(tables)
+        self.feat_embeddings = nn.ModuleList(tables)
+
+        self._root_fp = None
+        self._tables_bf16 = None
+        self._tables_key = None
+
+    # ------------------------------------------------------------------
+    def _flat(self) -> FlatParams:
+        if self._root_fp is None:
+            order = encoder_param_order(self.bert, "bert.") + self.nfr_loss.param_order("nfr_loss.")
+            self._root_fp = FlatParams(order)
+            self.bert._attach(self._root_fp, "bert.")
+            self.nfr_loss._attach(self._root_fp, "nfr_loss.")
+        return self._root_fp.ensure()
+
+    def flat_parameters(self) -> torch.Tensor:
+        """All trainable parameters as one fp32 vector (views, FlatParams order)."""
+        return self._flat().flat
+
+    def flat_decay_mask(self, no_decay=("bias", "LayerNorm.weight")) -> torch.Tensor:
+        """uint8 per element: 1 where weight decay applies (base_trainer.py:35-59)."""
+        fp = self._flat()
+        mask = torch.zeros(fp.total, dtype=torch.uint8)
+        for n, p in zip(fp.names, fp.params):
+            if not any(nd in n for nd in no_decay):
+                mask[fp.offsets[n]: fp.offsets[n] + p.numel()] = 1
+        return mask.to(fp.flat.device)
+
+    def feature_tables_bf16(self) -> List[torch.Tensor]:
+        """bf16 device copies of the frozen feature tables (built once, rebuilt if the tables change)."""
+        key = tuple((e.weight.data_ptr(), e.weight._version, str(e.weight.device)) for e in self.feat_embeddings)
+        if self._tables_bf16 is None or key != self._tables_key:
+            out = []
+            for e in self.feat_embeddings:
+                w = e.weight.data
+                if not w.is_cuda:
+                    raise PMGTError("PMGT must be moved to a CUDA device before forward (no CPU fallback)")
+                out.append(w if w.dtype == BF16 else w.to(BF16).contiguous())
+            self._tables_bf16, self._tables_key = out, key
+        return self._tables_bf16
+
+    def mask_nodes(self, node_ids: torch.Tensor):
+        """models.py:131-151, same RNG consumption order (rand, randint, rand)."""
+        device = node_ids.device
+        masked_input_ids = node_ids.clone()
+        shape = masked_input_ids.size()
+        rand = torch.rand(shape[0], shape[1] - 1, device=device)
+        mask = (rand < self.random_node_ratio) * (masked_input_ids[:, 1:] != 0)
+        masked_input_ids[:, 1:][mask] = torch.randint(2, self.node_size + 2, (int(mask.sum()),), device=device)
+        rand = torch.rand(shape[0], shape[1] - 1, device=device)
+        mask = (rand < self.mask_node_ratio) * (masked_input_ids[:, 1:] != 0)
+        target_idx = masked_input_ids[:, 1:][mask]
+        masked_input_ids[:, 1:][mask] = 1  # Fill mask index
+        return masked_input_ids, mask, target_idx
+
+    # ------------------------------------------------------------------
+    def forward(
+        self,
+        target_node_inputs: Dict[str, torch.Tensor],
+        pair_node_inputs: Optional[Dict[str, torch.Tensor]] = None,
+        num_pairs: torch.LongTensor = None,
+        labels: Optional[torch.FloatTensor] = None,
+        output_attentions: Optional[bool] = None,
+        output_hidden_states: Optional[bool] = None,
+        return_dict: Optional[bool] = None,
+        masked_inputs=None,
+    ):
+        if pair_node_inputs is not None:
+            assert labels is not None, "labels must be passed, when set pair_node_inputs"
+            assert num_pairs is not None, "num_pairs must be passed, when set pair_node_inputs"
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("attention maps / per-layer hidden states are not produced by the fused kernels")
+        return_dict = return_dict if return_dict is not None else self.config.use_return_dict
+
+        t_ids = target_node_inputs["node_ids"]
+        t_mask = target_node_inputs["attention_mask"]
+        if not t_ids.is_cuda:
+            raise PMGTError("PMGT.forward needs CUDA tensors: pmgt_b200 has no CPU fallback")
+        B, L = t_ids.shape
+        fp = self._flat()
+        fp.refresh_bf16()
+        tables = self.feature_tables_bf16()
+        arena = GradArena(fp)
+
+        ids = [t_ids]
+        masks = [t_mask]
+        SP = 0
+        nfr_on = False
+        if pair_node_inputs is not None:
+            p_ids = pair_node_inputs["node_ids"]
+            SP = p_ids.shape[0]
+            ids.append(p_ids)
+            masks.append(pair_node_inputs["attention_mask"])
+            if self.training:
+                nfr_on = True
+                if masked_inputs is None:
+                    masked_inputs = self.mask_nodes(t_ids)
+                m_ids, m_mask, target_idx = masked_inputs
+                ids.append(m_ids)
+                masks.append(t_mask)
+        ids_all = ids[0] if len(ids) == 1 else torch.cat(ids, dim=0)
+        mask_all = masks[0] if len(masks) == 1 else torch.cat(masks, dim=0)
+        R = ids_all.shape[0]
+        hidden = self.bert.encode(tables[0], tables[1], ids_all.reshape(-1).contiguous(), mask_all, R, L,
+                                  arena=arena, refresh=False)  # (R, L, H) fp32
+        H = hidden.shape[-1]
+        last_hidden_state = hidden[:B]
+
+        loss = None
+        prediction_logits = None
+        if pair_node_inputs is not None:
+            dev = hidden.device
+            # tokens the losses read: position 0 of targets and pairs, masked positions of the masked rows
+            tok = [torch.arange(0, (B + SP) * L, L, device=dev)]
+            if nfr_on:
+                pos = m_mask.nonzero(as_tuple=False)  # (Mm, 2): row, position-1
+                tok.append((B + SP + pos[:, 0]) * L + pos[:, 1] + 1)
+            rows = _TakeRows.apply(hidden.view(R * L, H), torch.cat(tok) if len(tok) > 1 else tok[0])
+            pair_off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(num_pairs.to(dev), 0, out=pair_off[1:])
+            gsr_loss, prediction_logits = self.gsr_loss.batched(rows[:B], rows[B: B + SP], pair_off,
+                                                                labels.to(torch.float32).contiguous())
+            loss = gsr_loss
+            if nfr_on:
+                nfr = self.nfr_loss.from_ids(rows[B + SP:], target_idx.contiguous(), tables, arena=arena)
+                loss = gsr_loss + nfr
+
+        if not return_dict:
+            return (loss, prediction_logits, last_hidden_state, None)
+        return PMGTForPreTrainingOutput(loss=loss, prediction_logits=prediction_logits,
+                                        last_hidden_state=last_hidden_state)

@@ -1,0 +1,121 @@
+"""tcgen05 GEMM (pmgt_gemm_bf16) against torch fp32 matmul on the same bf16 inputs.
+Tolerance: fp32 accumulation of bf16 products, result rounded to bf16 -> 1e-2
+relative to the row scale; fp32 outputs 2e-3."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def _ops():
+    from pmgt_b200 import ops
+    return ops
+
+
+def _close(got, want, tol):
+    scale = want.abs().max().clamp_min(1e-6)
+    err = (got.float() - want).abs().max() / scale
+    assert torch.isfinite(got.float()).all(), "non-finite output"
+    assert err < tol, f"max scaled error {float(err):.4g} >= {tol}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 128), (256, 128, 256), (300, 128, 128), (77, 32, 40),
+                                   (1000, 512, 128), (512, 128, 1536), (129, 264, 200)])
+def test_linear_fwd(M, N, K):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g).to(BF16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.1).to(BF16)
+    b = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda", dtype=BF16)
+    ops.linear_fwd(x, w, b, out)
+    _close(out, x.float() @ w.float().t() + b, 1e-2)
+
+
+def test_linear_fwd_gelu_epilogue():
+    ops = _ops()
+    M, N, K = 333, 128, 128
+    x = torch.randn(M, K, device="cuda").to(BF16)
+    w = (torch.randn(N, K, device="cuda") * 0.1).to(BF16)
+    b = torch.randn(N, device="cuda") * 0.1
+    out = torch.empty(M, N, device="cuda", dtype=BF16)
+    pre = torch.empty(M, N, device="cuda", dtype=BF16)
+    ops.linear_fwd(x, w, b, out, gelu_aux=pre)
+    want_pre = x.float() @ w.float().t() + b
+    _close(pre, want_pre, 1e-2)
+    _close(out, torch.nn.functional.gelu(want_pre), 1e-2)
+
+
+@pytest.mark.parametrize("M,D,K,nrows", [(256, 128, 1536, 500), (700, 128, 768, 50), (100, 64, 128, 30)])
+def test_linear_fwd_gathered_rows(M, D, K, nrows):
+    """A rows fetched through an index vector (the fused feature gather)."""
+    ops = _ops()
+    table = torch.randn(nrows, K, device="cuda").to(BF16)
+    table[0] = 0
+    idx = torch.randint(0, nrows, (M,), device="cuda", dtype=torch.int64)
+    w = (torch.randn(D, K, device="cuda") * 0.05).to(BF16)
+    b = torch.randn(D, device="cuda") * 0.1
+    out = torch.empty(M, D, device="cuda", dtype=BF16)
+    ops.linear_fwd(table, w, b, out, rows=idx, src_rows=nrows)
+    _close(out, table[idx].float() @ w.float().t() + b, 1e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 128), (300, 128, 512), (1000, 128, 128), (130, 96, 64), (257, 1536, 128)])
+def test_linear_dx(M, N, K):
+    """dX[M,K] = dY[M,N] @ W[N,K]  (B operand MN-major)."""
+    ops = _ops()
+    dy = torch.randn(M, N, device="cuda").to(BF16)
+    w = (torch.randn(N, K, device="cuda") * 0.1).to(BF16)
+    add = torch.randn(M, K, device="cuda").to(BF16)
+    out = torch.empty(M, K, device="cuda", dtype=BF16)
+    ops.linear_dx(dy, w, out)
+    _close(out, dy.float() @ w.float(), 1e-2)
+    ops.linear_dx(dy, w, out, addend=add)
+    _close(out, dy.float() @ w.float() + add.float(), 1e-2)
+
+
+def test_linear_dx_gelu_bwd():
+    ops = _ops()
+    M, N, K = 200, 128, 96
+    dy = torch.randn(M, N, device="cuda").to(BF16)
+    w = (torch.randn(N, K, device="cuda") * 0.1).to(BF16)
+    pre = torch.randn(M, K, device="cuda").to(BF16)
+    out = torch.empty(M, K, device="cuda", dtype=BF16)
+    ops.linear_dx(dy, w, out, gelu_bwd_aux=pre)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).backward(dy.float() @ w.float())
+    _close(out, x.grad, 1e-2)
+
+
+@pytest.mark.parametrize("T,N,K", [(256, 128, 128), (1000, 128, 128), (5000, 512, 128), (333, 96, 64), (4096, 128, 1536)])
+def test_linear_dw(T, N, K):
+    """dW[N,K] += dY[T,N]^T @ X[T,K]  (both operands MN-major, split over T, fp32 atomics)."""
+    ops = _ops()
+    dy = (torch.randn(T, N, device="cuda") * 0.1).to(BF16)
+    x = torch.randn(T, K, device="cuda").to(BF16)
+    dw = torch.ones(N, K, device="cuda", dtype=torch.float32)  # accumulates on top
+    ops.linear_dw(dy, x, dw)
+    _close(dw, dy.float().t() @ x.float() + 1.0, 2e-3)
+
+
+def test_linear_dw_gathered_rows():
+    ops = _ops()
+    T, N, K, nrows = 3000, 128, 768, 400
+    table = torch.randn(nrows, K, device="cuda").to(BF16)
+    idx = torch.randint(0, nrows, (T,), device="cuda", dtype=torch.int64)
+    dy = (torch.randn(T, N, device="cuda") * 0.1).to(BF16)
+    dw = torch.zeros(N, K, device="cuda", dtype=torch.float32)
+    ops.linear_dw(dy, table, dw, rows=idx, src_rows=nrows, x_cols=K)
+    _close(dw, dy.float().t() @ table[idx].float(), 2e-3)
+
+
+def test_gemm_rejects_bad_arguments():
+    from pmgt_b200 import _lib
+    ops = _ops()
+    x = torch.randn(64, 60, device="cuda").to(BF16)
+    w = torch.randn(64, 60, device="cuda").to(BF16)
+    out = torch.empty(64, 64, device="cuda", dtype=BF16)
+    with pytest.raises(_lib.PMGTError):
+        ops.linear_fwd(x, w, None, out)  # lda not a multiple of 8
