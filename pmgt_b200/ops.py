@@ -14,6 +14,38 @@ from ._lib import AttnArgs, EmbedArgs, GemmArgs, GsrArgs, NfrArgs, ResLnArgs, ch
 EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_ADDEND, EPI_OUT_F32, EPI_ATOMIC = 1, 2, 4, 8, 16, 32
 BF16 = torch.bfloat16
 
+# -- instrumentation ---------------------------------------------------------------------------
+# LAUNCHES counts kernels launched by this library (bench.py's `gpu_launches`).  When PROFILE is
+# a list, every C-ABI call is bracketed by CUDA events on the launching stream and recorded as
+# (tag, start_event, end_event, algorithmic_bytes, flops); bench.py aggregates them after a sync.
+LAUNCHES = [0]
+PROFILE = None
+
+
+def _run(tag, fn, args, launches=1, nbytes=0, flops=0):
+    LAUNCHES[0] += launches
+    if PROFILE is None:
+        check(fn(*args), tag)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn(*args), tag)
+    e1.record()
+    PROFILE.append((tag, e0, e1, nbytes, flops))
+
+
+def profile_summary(records):
+    """{tag: dict(ms, calls, bytes, flops)} from PROFILE records (call after torch.cuda.synchronize())."""
+    out = {}
+    for tag, e0, e1, nbytes, flops in records:
+        d = out.setdefault(tag, dict(ms=0.0, calls=0, bytes=0, flops=0))
+        d["ms"] += e0.elapsed_time(e1)
+        d["calls"] += 1
+        d["bytes"] += nbytes
+        d["flops"] += flops
+    return out
+
 
 def _require_cuda(t: torch.Tensor, name: str):
     if not t.is_cuda:
@@ -25,15 +57,23 @@ def _num_sms(dev) -> int:
 
 
 def gemm(a, b, out, *, M, N, K, lda, ldb, ldo, a_mn=False, b_mn=False, a_rows=None, a_src_rows=0, b_rows=None,
-         b_src_rows=0, bias=None, addend=None, ld_addend=0, aux=None, ld_aux=0, alpha=1.0, epi=0, split_k=1):
+         b_src_rows=0, bias=None, addend=None, ld_addend=0, aux=None, ld_aux=0, alpha=1.0, epi=0, split_k=1,
+         tag="gemm"):
     """``pmgt_gemm_bf16``: D[M,N] (+)= op(A) op(B); see the header for operand layouts."""
     _require_cuda(a, "a")
     g = GemmArgs(M, N, K, ptr(a), lda, int(a_mn), ptr(a_rows), a_src_rows, ptr(b), ldb, int(b_mn), ptr(b_rows),
                  b_src_rows, ptr(out), ldo, ptr(bias), ptr(addend), ld_addend, ptr(aux), ld_aux, alpha, epi, split_k)
-    check(_lib.lib().pmgt_gemm_bf16(C.byref(g), cur_stream()), "pmgt_gemm_bf16")
+    # algorithmic (compulsory) bytes: each operand element once, the output once, epilogue side inputs once
+    osz = 4 if epi & (EPI_OUT_F32 | EPI_ATOMIC) else 2
+    nbytes = 2 * M * K + 2 * N * K + osz * M * N
+    if epi & EPI_ADDEND:
+        nbytes += 2 * M * N
+    if epi & (EPI_GELU | EPI_GELU_BWD):
+        nbytes += 2 * M * N
+    _run(tag, _lib.lib().pmgt_gemm_bf16, (C.byref(g), cur_stream()), 1, nbytes, 2 * M * N * K)
 
 
-def linear_fwd(x, w, bias, out, *, rows=None, src_rows=0, gelu_aux=None):
+def linear_fwd(x, w, bias, out, *, rows=None, src_rows=0, gelu_aux=None, tag=None):
     """out[T,N] = x[T,K] @ w[N,K]^T + bias   (x optionally gathered through ``rows``)."""
     N, K = w.shape
     T = out.shape[0]
@@ -41,10 +81,11 @@ def linear_fwd(x, w, bias, out, *, rows=None, src_rows=0, gelu_aux=None):
     if gelu_aux is not None:
         epi |= EPI_GELU
     gemm(x, w, out, M=T, N=N, K=K, lda=x.stride(0), ldb=w.stride(0), ldo=out.stride(0), a_rows=rows,
-         a_src_rows=src_rows, bias=bias, aux=gelu_aux, ld_aux=(gelu_aux.stride(0) if gelu_aux is not None else 0), epi=epi)
+         a_src_rows=src_rows, bias=bias, aux=gelu_aux, ld_aux=(gelu_aux.stride(0) if gelu_aux is not None else 0), epi=epi,
+         tag=tag or ("gemm_fwd_gather" if rows is not None else "gemm_fwd"))
 
 
-def linear_dx(dy, w, out, *, addend=None, gelu_bwd_aux=None):
+def linear_dx(dy, w, out, *, addend=None, gelu_bwd_aux=None, tag="gemm_dx"):
     """out[T,K] = dy[T,N] @ w[N,K] (+ addend) (* gelu'(aux))."""
     N, K = w.shape
     T = dy.shape[0]
@@ -55,10 +96,10 @@ def linear_dx(dy, w, out, *, addend=None, gelu_bwd_aux=None):
         epi |= EPI_GELU_BWD
     gemm(dy, w, out, M=T, N=K, K=N, lda=dy.stride(0), ldb=w.stride(0), ldo=out.stride(0), b_mn=True,
          addend=addend, ld_addend=(addend.stride(0) if addend is not None else 0),
-         aux=gelu_bwd_aux, ld_aux=(gelu_bwd_aux.stride(0) if gelu_bwd_aux is not None else 0), epi=epi)
+         aux=gelu_bwd_aux, ld_aux=(gelu_bwd_aux.stride(0) if gelu_bwd_aux is not None else 0), epi=epi, tag=tag)
 
 
-def linear_dw(dy, x, dw_f32, *, rows=None, src_rows=0, x_cols=None):
+def linear_dw(dy, x, dw_f32, *, rows=None, src_rows=0, x_cols=None, tag=None):
     """dw[N,K] += dy[T,N]^T @ x[T,K]  (fp32 atomic accumulation, split over T).
 
     ``x`` may be a table whose rows are fetched through ``rows`` (T int64 ids)."""
@@ -68,7 +109,8 @@ def linear_dw(dy, x, dw_f32, *, rows=None, src_rows=0, x_cols=None):
     num_kb = (T + 63) // 64
     split = max(1, min(num_kb, (2 * _num_sms(dy.device) + tiles - 1) // tiles))
     gemm(dy, x, dw_f32, M=N, N=K, K=T, lda=dy.stride(0), ldb=x.stride(0), ldo=dw_f32.stride(0), a_mn=True, b_mn=True,
-         b_rows=rows, b_src_rows=src_rows, epi=EPI_ATOMIC, split_k=split)
+         b_rows=rows, b_src_rows=src_rows, epi=EPI_ATOMIC, split_k=split,
+         tag=tag or ("gemm_dw_gather" if rows is not None else "gemm_dw"))
 
 
 def embed_args(rows, L, H, ev, et, w_att, b_att, pos, role, ln_g, ln_b, eps, p, seed, site, **kw):
@@ -83,11 +125,13 @@ def embed_args(rows, L, H, ev, et, w_att, b_att, pos, role, ln_g, ln_b, eps, p, 
 
 
 def embed_fuse_fwd(a: EmbedArgs):
-    check(_lib.lib().pmgt_embed_fuse_fwd(C.byref(a), cur_stream()), "pmgt_embed_fuse_fwd")
+    T = a.rows * a.L
+    _run("embed_fuse_fwd", _lib.lib().pmgt_embed_fuse_fwd, (C.byref(a), cur_stream()), 1, 6 * T * a.H)
 
 
 def embed_fuse_bwd(a: EmbedArgs):
-    check(_lib.lib().pmgt_embed_fuse_bwd(C.byref(a), cur_stream()), "pmgt_embed_fuse_bwd")
+    T = a.rows * a.L
+    _run("embed_fuse_bwd", _lib.lib().pmgt_embed_fuse_bwd, (C.byref(a), cur_stream()), 1, 10 * T * a.H)
 
 
 def attn_args(rows, L, H, heads, beta, qkvc, mask, p, seed, site, **kw):
@@ -101,11 +145,16 @@ def attn_args(rows, L, H, heads, beta, qkvc, mask, p, seed, site, **kw):
 
 
 def attn_core_fwd(a: AttnArgs):
-    check(_lib.lib().pmgt_attn_core_fwd(C.byref(a), cur_stream()), "pmgt_attn_core_fwd")
+    T = a.rows * a.L
+    _run("attn_core_fwd", _lib.lib().pmgt_attn_core_fwd, (C.byref(a), cur_stream()), 1, 10 * T * a.H,
+         6 * T * a.L * a.H)
 
 
 def attn_core_bwd(a: AttnArgs):
-    check(_lib.lib().pmgt_attn_core_bwd(C.byref(a), cur_stream()), "pmgt_attn_core_bwd")
+    T = a.rows * a.L
+    n_col = (4 * a.H + 2047) // 2048 if a.d_bias_qkvc else 0
+    _run("attn_core_bwd", _lib.lib().pmgt_attn_core_bwd, (C.byref(a), cur_stream()), 1 + n_col,
+         (18 + (8 if n_col else 0)) * T * a.H, 14 * T * a.L * a.H)
 
 
 def resln_args(T, H, o, res, ln_g, ln_b, eps, p, seed, site, **kw):
@@ -119,16 +168,18 @@ def resln_args(T, H, o, res, ln_g, ln_b, eps, p, seed, site, **kw):
 
 
 def res_ln_fwd(a: ResLnArgs):
-    check(_lib.lib().pmgt_res_ln_fwd(C.byref(a), cur_stream()), "pmgt_res_ln_fwd")
+    _run("res_ln_fwd", _lib.lib().pmgt_res_ln_fwd, (C.byref(a), cur_stream()), 1, (6 + (4 if a.y_f32 else 0)) * a.T * a.H)
 
 
 def res_ln_bwd(a: ResLnArgs):
-    check(_lib.lib().pmgt_res_ln_bwd(C.byref(a), cur_stream()), "pmgt_res_ln_bwd")
+    per = 4 + (2 if a.dy else 0) + (4 if a.dy_f32 else 0) + 2 + (2 if (a.d_o and a.d_o != a.dz) else 0)
+    _run("res_ln_bwd", _lib.lib().pmgt_res_ln_bwd, (C.byref(a), cur_stream()), 1, per * a.T * a.H)
 
 
 def colsum(x, out_f32):
     T, N = x.shape
-    check(_lib.lib().pmgt_colsum_bf16(ptr(x), T, N, x.stride(0), ptr(out_f32), cur_stream()), "pmgt_colsum_bf16")
+    _run("colsum", _lib.lib().pmgt_colsum_bf16, (ptr(x), T, N, x.stride(0), ptr(out_f32), cur_stream()),
+         (N + 2047) // 2048, 2 * T * N)
 
 
 def gsr(fwd: bool, B, SP, H, tgt_h, ld_t, pair_h, ld_p, pair_off, labels, logits=None, loss_out=None, grad_out=None,
@@ -136,42 +187,44 @@ def gsr(fwd: bool, B, SP, H, tgt_h, ld_t, pair_h, ld_p, pair_off, labels, logits
     a = GsrArgs(B, SP, H, ptr(tgt_h), ld_t, ptr(pair_h), ld_p, ptr(pair_off), ptr(labels), ptr(logits), ptr(loss_out),
                 ptr(grad_out), ptr(d_tgt), ptr(d_pair))
     fn = _lib.lib().pmgt_gsr_fwd if fwd else _lib.lib().pmgt_gsr_bwd
-    check(fn(C.byref(a), cur_stream()), "pmgt_gsr")
+    _run("gsr_fwd" if fwd else "gsr_bwd", fn, (C.byref(a), cur_stream()), 1, (4 if fwd else 8) * (B + SP) * H)
 
 
 def nfr_mse(fwd: bool, Mm, D, proj, table, target_ids, weight, loss_out=None, grad_out=None, dproj=None):
     a = NfrArgs(Mm, D, ptr(proj), proj.stride(0) if proj is not None else 0, ptr(table), table.stride(0),
                 ptr(target_ids), weight, ptr(loss_out), ptr(grad_out), ptr(dproj))
     fn = _lib.lib().pmgt_nfr_mse_fwd if fwd else _lib.lib().pmgt_nfr_mse_bwd
-    check(fn(C.byref(a), cur_stream()), "pmgt_nfr_mse")
+    _run("nfr_mse_fwd" if fwd else "nfr_mse_bwd", fn, (C.byref(a), cur_stream()), 1, (4 if fwd else 6) * Mm * D)
 
 
 def cast_f32_bf16(src, dst):
-    check(_lib.lib().pmgt_cast_f32_bf16(ptr(src), ptr(dst), src.numel(), cur_stream()), "pmgt_cast_f32_bf16")
+    _run("cast_f32_bf16", _lib.lib().pmgt_cast_f32_bf16, (ptr(src), ptr(dst), src.numel(), cur_stream()), 1, 6 * src.numel())
 
 
 def sumsq(x, out):
-    check(_lib.lib().pmgt_sumsq_f32(ptr(x), x.numel(), ptr(out), cur_stream()), "pmgt_sumsq_f32")
+    _run("sumsq", _lib.lib().pmgt_sumsq_f32, (ptr(x), x.numel(), ptr(out), cur_stream()), 1, 4 * x.numel())
 
 
 def gather_rows(src, idx, out):
-    check(_lib.lib().pmgt_gather_rows_bf16(ptr(src), src.stride(0), ptr(idx), idx.numel(), src.shape[1], ptr(out),
-                                           out.stride(0), cur_stream()), "pmgt_gather_rows_bf16")
+    _run("gather_rows", _lib.lib().pmgt_gather_rows_bf16, (ptr(src), src.stride(0), ptr(idx), idx.numel(), src.shape[1],
+                                                           ptr(out), out.stride(0), cur_stream()), 1,
+         4 * idx.numel() * src.shape[1])
 
 
 def adamw_step(p, g, m, v, decay_mask, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, grad_scale_dev=None):
-    check(_lib.lib().pmgt_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(decay_mask), p.numel(), lr, beta1, beta2, eps,
-                                     weight_decay, step, grad_scale, ptr(grad_scale_dev), cur_stream()), "pmgt_adamw_step")
+    _run("adamw", _lib.lib().pmgt_adamw_step, (ptr(p), ptr(g), ptr(m), ptr(v), ptr(decay_mask), p.numel(), lr, beta1, beta2,
+                                               eps, weight_decay, step, grad_scale, ptr(grad_scale_dev), cur_stream()),
+         1, 29 * p.numel())
 
 
 def sample_contexts(graph_handle, roots, keys, hops, max_ctx, seed, out_ids, out_mask, out_visited_deg=None):
     h = (C.c_int32 * len(hops))(*hops)
-    check(_lib.lib().pmgt_sample_contexts(graph_handle, ptr(roots), ptr(keys), roots.numel(), h, len(hops), max_ctx,
-                                          seed, ptr(out_ids), ptr(out_mask), ptr(out_visited_deg), cur_stream()),
-          "pmgt_sample_contexts")
+    _run("sample_contexts", _lib.lib().pmgt_sample_contexts,
+         (graph_handle, ptr(roots), ptr(keys), roots.numel(), h, len(hops), max_ctx, seed, ptr(out_ids), ptr(out_mask),
+          ptr(out_visited_deg), cur_stream()), 1, 0)
 
 
 def sample_pairs(graph_handle, targets, keys, max_pos, min_neg, max_total, stride, seed, out_pairs, out_labels, out_num):
-    check(_lib.lib().pmgt_sample_pairs(graph_handle, ptr(targets), ptr(keys), targets.numel(), max_pos, min_neg,
-                                       max_total, stride, seed, ptr(out_pairs), ptr(out_labels), ptr(out_num),
-                                       cur_stream()), "pmgt_sample_pairs")
+    _run("sample_pairs", _lib.lib().pmgt_sample_pairs,
+         (graph_handle, ptr(targets), ptr(keys), targets.numel(), max_pos, min_neg, max_total, stride, seed,
+          ptr(out_pairs), ptr(out_labels), ptr(out_num), cur_stream()), 1, 0)

@@ -1,0 +1,371 @@
+"""Host-side mirror of ``pmgt/pmgt/trainer.py`` (+ the parts of
+``pmgt/base_trainer.py`` the PMGT path uses), re-hosted on a plain loop.
+
+The reference drives everything through pytorch-lightning / mlflow / optuna
+(absent here and out of scope); this module keeps the reference's entry
+functions -- ``check_args``, ``init_run``, ``init_dataloader``, ``init_model``,
+``train``, ``test``, ``inference`` -- with the same ``args`` fields
+(train.py:18-70,223-288), and ``PMGTTrainerModel`` with the same step methods.
+
+What is different by design:
+ * batches come from ``PMGTDataset.sample_batch`` (GPU sampler) instead of
+   DataLoader worker processes; a "dataloader" here is an index-batch iterator;
+ * data parallelism is explicit: one process per GPU, targets sharded by rank,
+   ONE NCCL allreduce of the flat gradient buffer per step (the reference gets
+   bucketed DDP implicitly from Lightning, base_trainer.py:309-322);
+ * optimizer = fused ``DenseSparseAdamW`` over the flat parameter buffer with
+   the reference's two parameter groups (base_trainer.py:35-59) and optional
+   ``clip_grad_norm_`` (``gradient_max_norm``, base_trainer.py:314).
+"""
+import os
+import pickle
+import time
+from typing import Dict, Iterator, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .configuration_pmgt import PMGTConfig
+from .datasets import PMGTDataset
+from .graph import ItemGraph
+from .models import PMGT
+from .optimizers import DenseSparseAdamW
+from .utils import set_seed
+
+
+class AttrDict(dict):
+    """Minimal ``attrdict.AttrDict``: attribute access over a dict; missing keys read as None."""
+
+    def __getattr__(self, k):
+        return self.get(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+DEFAULTS = dict(  # train.py:18-70 (shared flags) and 223-288 (PMGT flags)
+    mode="train", seed=0, model_name="PMGT", dataset_name="VG", data_dir="./data", log_dir="./logs",
+    num_epochs=20, train_batch_size=256, test_batch_size=256, no_cuda=False, num_workers=8, lr=1e-3, decay=1e-2,
+    optim="adamw", early=10, early_criterion="loss", valid_size=0.2, mp_enabled=False, gradient_max_norm=None,
+    accumulation_step=1, scheduler_type=None, run_id=None, inference_result_path=None,
+    max_ctx_neigh=5, hop_sampling_sizes=[16, 8, 4], max_total_samples=10, min_neg_samples=5,
+    hidden_size=128, intermediate_size=128, num_hidden_layers=5, num_attention_heads=1, beta=0.5,
+    random_node_ratio=0.2 * 0.1, mask_node_ratio=0.2 * 0.8, synthetic=None,
+)
+
+
+def make_args(**over) -> AttrDict:
+    a = AttrDict(DEFAULTS)
+    a.update(over)
+    return a
+
+
+# ---------------------------------------------------------------------------
+# distributed helpers
+# ---------------------------------------------------------------------------
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_indices(perm: np.ndarray, step: int, batch_per_rank: int, rank: int, world_size: int) -> np.ndarray:
+    """Targets of ``rank`` at ``step``: perm[step*B*W + rank*B : ... + B]  (SURVEY section 8e)."""
+    lo = step * batch_per_rank * world_size + rank * batch_per_rank
+    return perm[lo: lo + batch_per_rank]
+
+
+def epoch_permutation(n: int, seed: int, epoch: int) -> np.ndarray:
+    """Same permutation on every rank, derived from (seed, epoch)."""
+    return np.random.default_rng([int(seed), int(epoch)]).permutation(n)
+
+
+# ---------------------------------------------------------------------------
+# reference entry points
+# ---------------------------------------------------------------------------
+def check_args(args: AttrDict) -> None:
+    """trainer.py:213-218 / base_trainer.py check_args."""
+    if args.early_criterion not in ["loss", "auc"]:
+        raise ValueError(f"early_criterion must be one of ['loss', 'auc'], got {args.early_criterion}")
+    if args.model_name not in ["PMGT"]:
+        raise ValueError(f"model_name must be one of ['PMGT'], got {args.model_name}")
+    if args.dataset_name not in ["VG", "TG"] and not args.synthetic:
+        raise ValueError(f"dataset_name must be one of ['VG', 'TG'], got {args.dataset_name}")
+    if args.optim != "adamw":
+        raise ValueError(f"Optimizer {args.optim} is not supported")
+    if args.scheduler_type is not None:
+        raise ValueError("LR schedulers are not wired in the reference's PMGT path (base_trainer.py:71-90 recurses)")
+
+
+def init_run(args: AttrDict) -> None:
+    """base_trainer.py:194-200."""
+    set_seed(args.seed)
+    if not torch.cuda.is_available() or args.no_cuda:
+        raise RuntimeError("pmgt_b200 trains on CUDA devices only (no CPU fallback)")
+    args.device = torch.device("cuda", torch.cuda.current_device())
+    args.num_gpus = world()[1]
+
+
+def _load_graph_and_features(args: AttrDict):
+    """trainer.py:30-41,112-116; ``args.synthetic`` substitutes seeded synthetic inputs."""
+    if args.synthetic:
+        from . import synthetic
+
+        name = args.synthetic
+        graph = synthetic.make_item_graph(name)
+        seed = synthetic.SHAPES[name][3] if isinstance(name, str) and name in synthetic.SHAPES else 1234
+        if graph.num_nodes > 200_000:
+            feats = synthetic.make_features_device(graph.num_nodes, seed=seed, device=args.device)
+        else:
+            feats = synthetic.make_features(graph.num_nodes, seed=seed)
+        return graph, feats
+    import joblib
+    import networkx as nx
+
+    data_dir = os.path.join(args.data_dir, args.dataset_name)
+    node_encoder = joblib.load(os.path.join(data_dir, "node_encoder"))
+    with open(os.path.join(data_dir, "graph.gpickle"), "rb") as f:  # nx.read_gpickle (networkx 2.6) == pickle.load
+        g = pickle.load(f)
+    # idx 0 is <pad>, idx 1 is <mask>
+    mapping = {label: i + 2 for i, label in enumerate(node_encoder.classes_)}
+    g = nx.relabel_nodes(g, mapping)
+    feats = [np.load(os.path.join(data_dir, "visual_init_emb.npy")), np.load(os.path.join(data_dir, "textual_init_emb.npy"))]
+    return ItemGraph.from_networkx(g), feats
+
+
+def _split(n_nodes: int, valid_size: float, seed: int):
+    """sklearn.model_selection.train_test_split(np.arange(2, N+2), test_size, random_state) (trainer.py:45-52)."""
+    from sklearn.model_selection import train_test_split
+
+    return train_test_split(np.arange(start=2, stop=n_nodes + 2), test_size=valid_size, random_state=seed)
+
+
+def init_dataloader(args: AttrDict) -> None:
+    if args.graph is None:
+        args.graph, args.feat_init_emb = _load_graph_and_features(args)
+    train_nodes, valid_nodes = _split(len(args.graph), args.valid_size, args.seed)
+    args.train_dataset = PMGTDataset(args.graph, train_nodes, args.max_ctx_neigh, args.hop_sampling_sizes,
+                                     args.max_total_samples, args.min_neg_samples, seed=args.seed)
+    args.valid_dataset = PMGTDataset(args.graph, valid_nodes, args.max_ctx_neigh, args.hop_sampling_sizes,
+                                     is_training=False, seed=args.seed + 1)
+    args.test_dataset = args.valid_dataset  # trainer.py:71 returns the validation set twice
+
+
+def init_model(args: AttrDict) -> None:
+    if args.graph is None:
+        args.graph, args.feat_init_emb = _load_graph_and_features(args)
+    feats = args.feat_init_emb
+    config = PMGTConfig(hidden_size=args.hidden_size, feat_hidden_sizes=[int(feats[0].shape[-1]), int(feats[1].shape[-1])],
+                        intermediate_size=args.intermediate_size, num_hidden_layers=args.num_hidden_layers,
+                        num_attention_heads=args.num_attention_heads, beta=args.beta,
+                        **({"hidden_dropout_prob": args.hidden_dropout_prob} if args.hidden_dropout_prob is not None else {}),
+                        **({"attention_probs_dropout_prob": args.attention_probs_dropout_prob}
+                           if args.attention_probs_dropout_prob is not None else {}))
+    model = PMGT(node_size=len(args.graph), random_node_ratio=args.random_node_ratio,
+                 mask_node_ratio=args.mask_node_ratio, config=config, feat_init_emb=feats)
+    args.model = model.to(args.device)
+
+
+def get_optimizer(args: AttrDict) -> DenseSparseAdamW:
+    """base_trainer.py:35-68: no weight decay for names containing "bias" or "LayerNorm.weight"."""
+    no_decay = ["bias", "LayerNorm.weight"]
+    named = [(n, p) for n, p in args.model.named_parameters() if p.requires_grad]
+    groups = [
+        {"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": args.decay, "lr": args.lr},
+        {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0, "lr": args.lr},
+    ]
+    return DenseSparseAdamW(groups)
+
+
+class PMGTTrainerModel:
+    """trainer.py:150-206 without Lightning: holds the net + optimizer and implements the step methods."""
+
+    def __init__(self, args: AttrDict):
+        self.args = args
+        self.net: PMGT = args.model
+        self.optimizer = get_optimizer(args)
+        self.global_step = 0
+        self._sumsq = None
+
+    # -- inference: net(x)[0][:, 0] (trainer.py:153-154)
+    def forward(self, x):
+        return self.net(x)[0][:, 0].cpu().numpy()
+
+    __call__ = forward
+
+    def training_step(self, batch, batch_idx: int = 0) -> torch.Tensor:
+        return self.net(*batch)[0]
+
+    def _validation_and_test_step(self, batch):
+        outputs = self.net(*batch)
+        loss, logits, labels = outputs[0], outputs[1], batch[-1]
+        return loss, logits.sigmoid().cpu().numpy(), labels.cpu().numpy()
+
+    # -- one optimisation step on a sampled batch (sample -> fwd -> bwd -> allreduce -> AdamW)
+    def train_on_indices(self, dataset: PMGTDataset, indices, epoch: int) -> torch.Tensor:
+        args = self.args
+        self.net.train()
+        batch = dataset.sample_batch(indices, epoch=epoch)
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.training_step(batch)
+        loss.backward()
+        rank, ws = world()
+        scale = 1.0
+        fv = self.optimizer.flat_views()
+        if ws > 1:
+            if fv is None or fv[1] is None:
+                raise RuntimeError("data-parallel training needs the flat gradient buffer")
+            dist.all_reduce(fv[1])  # ONE allreduce of the flat gradient (sum); mean folded into the step
+            scale = 1.0 / ws
+        scale_dev = None
+        if args.gradient_max_norm:
+            # torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)), on the averaged gradient
+            if self._sumsq is None:
+                self._sumsq = torch.zeros(1, dtype=torch.float32, device=loss.device)
+            self._sumsq.zero_()
+            if fv is not None and fv[1] is not None:
+                ops.sumsq(fv[1], self._sumsq)
+            else:
+                for p in self.net.parameters():
+                    if p.grad is not None:
+                        ops.sumsq(p.grad.contiguous().view(-1), self._sumsq)
+            norm = self._sumsq.sqrt() * scale
+            scale_dev = (scale * torch.clamp(args.gradient_max_norm / (norm + 1e-6), max=1.0)).to(torch.float32)
+        self.optimizer.step(grad_scale=scale, grad_scale_dev=scale_dev)
+        self.global_step += 1
+        return loss.detach()
+
+    @torch.no_grad()
+    def evaluate(self, dataset: PMGTDataset, batch_size: int) -> Dict[str, float]:
+        """validation/test epoch (trainer.py:162-206): mean loss + ROC-AUC of sigmoid(logits)."""
+        from sklearn.metrics import roc_auc_score
+
+        self.net.eval()
+        rank, ws = world()
+        preds, labels, losses = [], [], []
+        idx_all = np.arange(len(dataset))[rank::ws]
+        for lo in range(0, len(idx_all), batch_size):
+            loss, p, l = self._validation_and_test_step(dataset.sample_batch(idx_all[lo: lo + batch_size], epoch=0))
+            preds.append(p)
+            labels.append(l)
+            losses.append(float(loss))
+        preds, labels = np.concatenate(preds), np.concatenate(labels)
+        if ws > 1:
+            gathered = [None] * ws
+            dist.all_gather_object(gathered, (preds, labels, losses))
+            preds = np.concatenate([g[0] for g in gathered])
+            labels = np.concatenate([g[1] for g in gathered])
+            losses = sum((g[2] for g in gathered), [])
+        return {"loss": float(np.mean(losses)), "auc": float(roc_auc_score(labels, preds))}
+
+    def state_dict(self):
+        return {"state_dict": {"net." + k: v for k, v in self.net.state_dict().items()},  # Lightning's "net." prefix
+                "optimizer": self.optimizer.state_dict(), "global_step": self.global_step}
+
+    def load_state_dict(self, ckpt):
+        self.net.load_state_dict({k[len("net."):]: v for k, v in ckpt["state_dict"].items()})
+        self.global_step = ckpt.get("global_step", 0)
+
+
+def _ckpt_dir(args: AttrDict) -> str:
+    d = os.path.join(args.log_dir, args.run_id or "pmgt_b200_run", "checkpoints")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def train(args: AttrDict, is_hptuning: bool = False, trial=None, enable_trial_pruning: bool = False):
+    """base_trainer.py:266-341: fit with early stopping + last/best checkpoints.  Returns (best_score, trainer)."""
+    tm = PMGTTrainerModel(args)
+    rank, ws = world()
+    ds: PMGTDataset = args.train_dataset
+    B = args.train_batch_size
+    steps_per_epoch = len(ds) // (B * ws)
+    if steps_per_epoch == 0:
+        raise ValueError("train_batch_size x world_size exceeds the number of training nodes")
+    monitor = "loss" if args.early_criterion == "loss" else "auc"
+    best, bad_epochs, best_path = None, 0, None
+    ckpt_dir = _ckpt_dir(args)
+    last_path = os.path.join(ckpt_dir, "last.ckpt")
+    if args.run_id is not None and os.path.exists(last_path):  # resume (base_trainer.py:324-332)
+        tm.load_state_dict(torch.load(last_path, map_location=args.device, weights_only=False))
+    args.history = []
+    for epoch in range(args.num_epochs):
+        perm = epoch_permutation(len(ds), args.seed, epoch)
+        t0 = time.time()
+        running = []
+        for step in range(steps_per_epoch):
+            loss = tm.train_on_indices(ds, shard_indices(perm, step, B, rank, ws), epoch)
+            running.append(loss)
+        train_loss = float(torch.stack(running).mean())
+        val = tm.evaluate(args.valid_dataset, args.test_batch_size)
+        args.history.append({"epoch": epoch, "loss/train": train_loss, "loss/val": val["loss"], "val/auc": val["auc"],
+                             "sec": time.time() - t0})
+        score = val[monitor]
+        improved = best is None or (score < best if monitor == "loss" else score > best)
+        if rank == 0:
+            torch.save(tm.state_dict(), last_path)
+        if improved:
+            best, bad_epochs = score, 0
+            best_path = os.path.join(ckpt_dir, f"epoch={epoch}.ckpt")
+            if rank == 0:
+                torch.save(tm.state_dict(), best_path)
+        else:
+            bad_epochs += 1
+            if args.early and bad_epochs >= args.early:
+                break
+    args.best_model_path = best_path
+    return best, tm
+
+
+def test(args: AttrDict, trainer: Optional[PMGTTrainerModel] = None, is_hptuning: bool = False) -> Dict[str, float]:
+    """base_trainer.py test(): AUC on the test split with the best checkpoint."""
+    tm = trainer or PMGTTrainerModel(args)
+    if args.best_model_path and os.path.exists(args.best_model_path):
+        tm.load_state_dict(torch.load(args.best_model_path, map_location=args.device, weights_only=False))
+    res = tm.evaluate(args.test_dataset, args.test_batch_size)
+    return {"test/auc": res["auc"]}
+
+
+@torch.no_grad()
+def inference(args: AttrDict) -> np.ndarray:
+    """trainer.py:259-275 + base_trainer.py:382-409: (N, H) float32 embeddings, row i <-> node id i+2,
+    node range sharded contiguously across ranks; rank 0 saves ``inference_result_path`` (.npy)."""
+    tm = PMGTTrainerModel(args)
+    if args.best_model_path and os.path.exists(args.best_model_path):
+        tm.load_state_dict(torch.load(args.best_model_path, map_location=args.device, weights_only=False))
+    tm.net.eval()
+    ds = PMGTDataset(args.graph, max_ctx_neigh=args.max_ctx_neigh, hop_sampling_sizes=args.hop_sampling_sizes,
+                     is_training=False, is_inference=True, seed=args.seed)
+    rank, ws = world()
+    n = len(ds)
+    lo, hi = n * rank // ws, n * (rank + 1) // ws
+    out = torch.empty((hi - lo, args.hidden_size), dtype=torch.float32, device=args.device)
+    bs = args.test_batch_size
+    for s in range(lo, hi, bs):
+        e = min(s + bs, hi)
+        out[s - lo: e - lo] = tm.net(ds.sample_batch(np.arange(s, e)))[0][:, 0]
+    res = out.cpu().numpy()
+    if ws > 1:
+        parts = [None] * ws
+        dist.all_gather_object(parts, res)
+        res = np.concatenate(parts)
+    if args.inference_result_path and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.inference_result_path)), exist_ok=True)
+        np.save(args.inference_result_path, res)
+    return res
+
+
+def train_model(**over):
+    """train.py:298-344 dispatcher for ``train-pmgt``."""
+    args = make_args(**over)
+    check_args(args)
+    init_run(args)
+    init_dataloader(args)
+    init_model(args)
+    if args.mode == "inference":
+        return inference(args)
+    best, tm = train(args)
+    res = test(args, tm)
+    return best, res

@@ -1,0 +1,121 @@
+"""CPU-only tests of the host-side mirror of the reference API: state-dict keys, config, collate,
+ModelOutput indexing, synthetic inputs, graph ingestion, embedding remap."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from pmgt_b200 import PMGT, PMGTConfig, pmgt_collate_fn, synthetic
+from pmgt_b200.graph import ItemGraph
+from pmgt_b200.modeling_pmgt import FlatParams, PMGTForPreTrainingOutput, encoder_param_order
+from pmgt_b200.utils import remap_node_embeddings
+
+
+def test_state_dict_keys_match_reference_golden(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "model_golden.pt"), weights_only=False)["default"]
+    net = PMGT(g["node_size"], config=PMGTConfig())
+    trainable = {n for n, p in net.named_parameters() if p.requires_grad}
+    assert trainable == set(g["grad_norms"].keys())            # the reference's 104 trainable tensors, same names
+    sd = net.state_dict()
+    assert {"feat_embeddings.0.weight", "feat_embeddings.1.weight", "bert.embeddings.position_ids",
+            "bert.embeddings.role_ids"} <= set(sd)
+    assert sum(p.numel() for p in net.parameters() if p.requires_grad) == 1_186_690
+    assert not any(p.requires_grad for p in net.feat_embeddings.parameters())
+
+
+@pytest.mark.needs_reference
+def test_state_dict_roundtrip_with_live_reference():
+    from oracle import ref_shim
+    R = ref_shim.load()
+    ref = R.PMGT(30, config=R.PMGTConfig(num_hidden_layers=2))
+    ours = PMGT(30, config=PMGTConfig(num_hidden_layers=2))
+    assert list(ref.state_dict().keys()) == list(ours.state_dict().keys())
+    ours.load_state_dict(ref.state_dict())          # reference checkpoint -> ours
+    ref.load_state_dict(ours.state_dict())          # and back
+    for (k1, v1), (k2, v2) in zip(ref.state_dict().items(), ours.state_dict().items()):
+        assert k1 == k2 and v1.shape == v2.shape and v1.dtype == v2.dtype
+
+
+def test_config_defaults_and_validation():
+    c = PMGTConfig()
+    assert (c.hidden_size, c.feat_hidden_sizes, c.num_hidden_layers, c.num_attention_heads, c.intermediate_size) == \
+        (128, [1536, 768], 5, 1, 128)
+    assert (c.hidden_dropout_prob, c.attention_probs_dropout_prob, c.max_position_embeddings, c.layer_norm_eps, c.beta) == \
+        (0.1, 0.1, 100, 1e-12, 0.5)
+    assert c.use_return_dict and not c.output_attentions and c.chunk_size_feed_forward == 0
+    with pytest.raises(ValueError, match="not a multiple of the number of attention"):
+        PMGTConfig(hidden_size=100, num_attention_heads=3)
+
+
+def test_flat_param_order_makes_qkvc_one_matrix():
+    net = PMGT(10, config=PMGTConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2))
+    order = encoder_param_order(net.bert, "bert.") + net.nfr_loss.param_order("nfr_loss.")
+    fp = FlatParams(order)
+    assert len(order) == sum(1 for p in net.parameters() if p.requires_grad)
+    o = fp.offsets
+    H = 32
+    for i in range(2):
+        p = f"bert.encoder.layer.{i}.attention.self."
+        assert o[p + "key.weight"] - o[p + "query.weight"] == H * H
+        assert o[p + "ctx_attention.weight"] - o[p + "query.weight"] == 3 * H * H
+        assert o[p + "ctx_attention.bias"] - o[p + "query.bias"] == 3 * H
+    assert all(v % 8 == 0 for v in o.values())
+
+
+def test_model_output_indexing_like_transformers():
+    out = PMGTForPreTrainingOutput(loss=None, prediction_logits=None, last_hidden_state=torch.zeros(2, 6, 4))
+    assert out[0] is out.last_hidden_state                       # inference: net(x)[0] (trainer.py:153-154)
+    out = PMGTForPreTrainingOutput(loss=torch.tensor(1.0), prediction_logits=torch.zeros(3), last_hidden_state=torch.zeros(1))
+    assert out[0] is out.loss and out[1] is out.prediction_logits and out["loss"] is out.loss and len(out) == 3
+
+
+def test_forward_asserts_like_the_reference():
+    net = PMGT(10, config=PMGTConfig(num_hidden_layers=1))
+    x = {"node_ids": torch.zeros(1, 6, dtype=torch.long), "attention_mask": torch.ones(1, 6)}
+    with pytest.raises(AssertionError, match="labels must be passed"):
+        net(x, x)
+    with pytest.raises(AssertionError, match="num_pairs must be passed"):
+        net(x, x, labels=torch.zeros(1))
+
+
+def test_collate_layout():
+    L = 6
+    item = lambda p: ((torch.arange(L), torch.ones(L)), (torch.zeros(p, L, dtype=torch.long), torch.ones(p, L)), torch.ones(p))
+    t, p, n, lab = pmgt_collate_fn([item(10), item(7)])
+    assert t["node_ids"].shape == (2, L) and p["node_ids"].shape == (17, L) and n.tolist() == [10, 7] and lab.shape == (17,)
+    assert n.dtype == torch.int64
+    inf = pmgt_collate_fn([((torch.arange(L), torch.ones(L)),)] * 3)
+    assert set(inf) == {"node_ids", "attention_mask"} and inf["node_ids"].shape == (3, L)
+
+
+def test_synthetic_graph_shapes_and_weights():
+    g = synthetic.make_item_graph("VG")
+    assert g.num_nodes == 7252 and g.num_edges_directed == 2 * 88606
+    assert len(g.isolated_nodes()) == 0
+    deg = np.diff(g.indptr)[2:]
+    assert deg.max() > 20 * np.median(deg)                       # heavy tail
+    assert g.weights.min() > 0 and np.all(g.cdf <= 1.0) and np.all(g.cdf > 0)
+    # undirected: every (u, v) has its (v, u)
+    rows = np.repeat(np.arange(len(g.indptr) - 1), np.diff(g.indptr))
+    fwd = set(zip(rows[:2000].tolist(), g.indices[:2000].tolist()))
+    allp = set(zip(rows.tolist(), g.indices.tolist()))
+    assert all((v, u) in allp for u, v in fwd)
+    f = synthetic.make_features(100, dims=(16, 8), seed=1)
+    assert f[0].shape == (102, 16) and not f[0][:2].any() and abs(float(f[0][2:].std()) - 1) < 0.1
+
+
+def test_item_graph_validation():
+    with pytest.raises(ValueError):
+        ItemGraph(3, np.array([0, 0, 1, 1, 1, 1]), np.array([3]), np.array([1.0]))   # row 1 (<mask>) not empty
+    with pytest.raises(ValueError):
+        ItemGraph(3, np.array([0, 0, 0, 1, 1, 1]), np.array([9]), np.array([1.0]))   # neighbour id out of range
+
+
+def test_remap_node_embeddings_like_load_node_init_emb():
+    emb = np.arange(12, dtype=np.float32).reshape(3, 4) + 1
+    np.random.seed(0)
+    out = remap_node_embeddings(["b", "zz", "a"], ["a", "b", "c"], emb, normalize=True)
+    assert np.allclose(out[0], emb[1] / np.linalg.norm(emb[1])) and np.allclose(out[2], emb[0] / np.linalg.norm(emb[0]))
+    assert np.isclose(np.linalg.norm(out[1]), 1.0)               # missing item: random row, normalised
+    assert out.dtype == np.float32
