@@ -302,6 +302,9 @@ static int attn_launch_cfg(const pmgt_attn_args* a, bool bwd, AttnSmemLayout& la
   return PMGT_OK;
 }
 
+int attn_small_fwd(const pmgt_attn_args* a, cudaStream_t st);  // attention_small.cu
+int attn_small_bwd(const pmgt_attn_args* a, cudaStream_t st);
+
 }  // namespace pmgt
 
 using namespace pmgt;
@@ -311,6 +314,12 @@ extern "C" {
 int pmgt_attn_core_fwd(const pmgt_attn_args* a, void* stream) {
   PMGT_REQUIRE(a && a->qkvc && a->mask && a->ctx, "pmgt_attn_core_fwd: null argument");
   if (a->rows == 0) return PMGT_OK;
+  PMGT_REQUIRE(a->heads >= 1 && a->H % a->heads == 0, "attention: H must be divisible by heads");
+  {  // register-resident kernel for the short-sequence shapes (default PMGT: L = 6, dh = 128)
+    const int r = attn_small_fwd(a, (cudaStream_t)stream);
+    if (r < 0) return r;
+    if (r > 0) return PMGT_OK;
+  }
   AttnSmemLayout lay; int warps; size_t smem;
   int rc = attn_launch_cfg(a, false, lay, warps, smem);
   if (rc) return rc;
@@ -328,17 +337,22 @@ int pmgt_attn_core_fwd(const pmgt_attn_args* a, void* stream) {
 int pmgt_attn_core_bwd(const pmgt_attn_args* a, void* stream) {
   PMGT_REQUIRE(a && a->qkvc && a->mask && a->dctx && a->dqkvc, "pmgt_attn_core_bwd: null argument");
   if (a->rows == 0) return PMGT_OK;
-  AttnSmemLayout lay; int warps; size_t smem;
-  int rc = attn_launch_cfg(a, true, lay, warps, smem);
-  if (rc) return rc;
-  if (smem > 48 * 1024)
-    PMGT_CHECK_CUDA(cudaFuncSetAttribute(attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  long long items = a->rows * a->heads;
-  long long ctas = (items + warps - 1) / warps;
-  long long cap = (long long)num_sms() * 8;
-  if (ctas > cap) ctas = cap;
-  attn_core_bwd_kernel<<<(unsigned)ctas, 128, smem, (cudaStream_t)stream>>>(*a, warps, lay);
-  PMGT_LAUNCH_CHECK();
+  PMGT_REQUIRE(a->heads >= 1 && a->H % a->heads == 0, "attention: H must be divisible by heads");
+  int rc = attn_small_bwd(a, (cudaStream_t)stream);
+  if (rc < 0) return rc;
+  if (rc == 0) {
+    AttnSmemLayout lay; int warps; size_t smem;
+    rc = attn_launch_cfg(a, true, lay, warps, smem);
+    if (rc) return rc;
+    if (smem > 48 * 1024)
+      PMGT_CHECK_CUDA(cudaFuncSetAttribute(attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long items = a->rows * a->heads;
+    long long ctas = (items + warps - 1) / warps;
+    long long cap = (long long)num_sms() * 8;
+    if (ctas > cap) ctas = cap;
+    attn_core_bwd_kernel<<<(unsigned)ctas, 128, smem, (cudaStream_t)stream>>>(*a, warps, lay);
+    PMGT_LAUNCH_CHECK();
+  }
   if (a->d_bias_qkvc) {
     rc = pmgt_colsum_bf16(a->dqkvc, a->rows * a->L, 4ll * a->H, 4ll * a->H, a->d_bias_qkvc, stream);
     if (rc) return rc;

@@ -456,30 +456,55 @@ __global__ void __launch_bounds__(kRowThreads) res_ln_bwd_kernel(const pmgt_resl
 // ---------------------------------------------------------------------------
 // column sums of a bf16 matrix: out[n] += sum_t x[t][n]
 // ---------------------------------------------------------------------------
+// 256 threads = (N / 8) column threads x `groups` row groups; every thread keeps 8 column sums of the rows
+// it streams (4 independent 16-byte loads in flight), the row groups are then reduced through shared memory
+// and ONE atomic per column per CTA is issued (contended same-address atomics were the old bottleneck).
 __global__ void __launch_bounds__(256) colsum_kernel(const uint16_t* __restrict__ x, long long T, int N, long long ldx,
                                                      float* __restrict__ out, int rows_per_cta) {
-  // thread owns 8 consecutive columns; blockDim.x = threads per row * row groups
+  __shared__ float red[256 * 8];
   const int tpr = (N + 7) / 8;               // threads per row (<= 256)
   const int groups = blockDim.x / tpr;       // rows processed concurrently
   const int tg = threadIdx.x / tpr;
   const int tc = threadIdx.x % tpr;
-  if (tg >= groups) return;
   const int n = tc * 8;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   long long r1 = r0 + rows_per_cta;
   if (r1 > T) r1 = T;
-  for (long long r = r0 + tg; r < r1; r += groups) {
-    const uint4 u = *reinterpret_cast<const uint4*>(x + r * ldx + n);
-    float f[8];
-    unpack_bf16x2(u.x, f[0], f[1]); unpack_bf16x2(u.y, f[2], f[3]);
-    unpack_bf16x2(u.z, f[4], f[5]); unpack_bf16x2(u.w, f[6], f[7]);
+  if (tg < groups) {
+    long long r = r0 + tg;
+    for (; r + 3ll * groups < r1; r += 4ll * groups) {
+      uint4 u[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] += f[j];
+      for (int q = 0; q < 4; ++q) u[q] = *reinterpret_cast<const uint4*>(x + (r + (long long)q * groups) * ldx + n);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float f[8];
+        unpack_bf16x2(u[q].x, f[0], f[1]); unpack_bf16x2(u[q].y, f[2], f[3]);
+        unpack_bf16x2(u[q].z, f[4], f[5]); unpack_bf16x2(u[q].w, f[6], f[7]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += f[j];
+      }
+    }
+    for (; r < r1; r += groups) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + r * ldx + n);
+      float f[8];
+      unpack_bf16x2(u.x, f[0], f[1]); unpack_bf16x2(u.y, f[2], f[3]);
+      unpack_bf16x2(u.z, f[4], f[5]); unpack_bf16x2(u.w, f[6], f[7]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += f[j];
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (n + j < N && s[j] != 0.f) atomicAdd(out + n + j, s[j]);
+  for (int j = 0; j < 8; ++j) red[j * 256 + threadIdx.x] = (tg < groups) ? s[j] : 0.f;
+  __syncthreads();
+  // thread c < N sums column c over the row groups
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    const int tcc = c >> 3, j = c & 7;
+    float v = 0.f;
+    for (int gI = 0; gI < groups; ++gI) v += red[j * 256 + gI * tpr + tcc];
+    if (v != 0.f) atomicAdd(out + c, v);
+  }
 }
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst,
@@ -653,7 +678,7 @@ int pmgt_colsum_bf16(const uint16_t* x, int64_t T, int64_t N, int64_t ldx, float
     const int tpr = n / 8;
     const int groups = 256 / tpr > 0 ? 256 / tpr : 1;
     const int threads = tpr * groups;
-    long long ctas = (long long)num_sms() * 4;
+    long long ctas = (long long)num_sms() * 8;
     long long rows_per = (T + ctas - 1) / ctas;
     if (rows_per < groups) rows_per = groups;
     ctas = (T + rows_per - 1) / rows_per;
