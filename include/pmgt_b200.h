@@ -252,6 +252,79 @@ typedef struct pmgt_resln_args {
 int pmgt_res_ln_fwd(const pmgt_resln_args* a, void* stream);
 int pmgt_res_ln_bwd(const pmgt_resln_args* a, void* stream);
 
+/*
+ * Persistent tcgen05 "token-tile" kernels: the fast path of the nn.Linear layers of the encoder when every
+ * dimension is a multiple of 128 and the weight fits in shared memory (the default PMGT encoder, H = I = 128;
+ * modeling_pmgt.py:429-433,371,322-325 forward, and their autograd backward).  A CTA per SM loops over tiles of
+ * 128 tokens; activations arrive by TMA, weights stay resident, accumulators live in TMEM, results leave by
+ * TMA store.  Shapes outside pmgt_linear_tile_supported() go through pmgt_gemm_bf16.
+ *
+ *   epi PMGT_LT_BIAS      out = x w^T + bias                                   (w_mn = 0)
+ *       PMGT_LT_GELU      aux_out = x w^T + bias ; out = gelu_erf(aux_out)      (w_mn = 0; BertIntermediate)
+ *       PMGT_LT_RES_LN    z = dropout(x w^T + bias) + e_in ; aux_out = z ; out = LayerNorm(z)
+ *                         (w_mn = 0; BertSelfOutput / BertOutput; N == 128; out_f32 optional fp32 copy)
+ *       PMGT_LT_PLAIN     out = x w                                             (w_mn = 1; dX of a Linear)
+ *       PMGT_LT_GELU_BWD  out = (x w) * gelu_erf'(e_in)                          (w_mn = 1)
+ *   w_mn = 0: w is [N][K] (nn.Linear weight, y = x w^T); w_mn = 1: w is [K][N] (dx = dy w, same storage).
+ *   Dropout element index = token * N + column (the same stream pmgt_ln_bwd regenerates).
+ */
+#define PMGT_LT_BIAS 0
+#define PMGT_LT_GELU 1
+#define PMGT_LT_RES_LN 2
+#define PMGT_LT_PLAIN 3
+#define PMGT_LT_GELU_BWD 4
+
+typedef struct pmgt_linear_tile_args {
+  int64_t T; int K; int N;
+  const uint16_t* x; int64_t ldx;          /* [T][K] bf16 */
+  const uint16_t* w; int64_t ldw; int w_mn;
+  int epi;
+  const float* bias;                        /* [N] fp32 */
+  uint16_t* out; int64_t ldo;               /* [T][N] bf16 */
+  uint16_t* aux_out; int64_t ld_aux_out;    /* GELU: pre-activation; RES_LN: z */
+  const uint16_t* e_in; int64_t ld_e;       /* RES_LN: residual; GELU_BWD: pre-activation */
+  const float* ln_g; const float* ln_b; float ln_eps;
+  float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
+  float* out_f32;                           /* RES_LN only, optional, [T][N] fp32 */
+} pmgt_linear_tile_args;
+
+int pmgt_linear_tile_supported(int64_t K, int64_t N, int w_mn, int epi);
+int pmgt_linear_tile(const pmgt_linear_tile_args* a, void* stream);
+
+/*
+ * dw[N][K] += dy^T x and dbias[N] += column sums of dy (fp32, accumulated): the weight / bias gradient of a
+ * Linear.  Accumulators stay in TMEM over all token tiles of a CTA and are flushed once.  K == 128,
+ * N in {128, 512}; other shapes: pmgt_gemm_bf16 (split-K) + pmgt_colsum_bf16.
+ */
+typedef struct pmgt_dw_tile_args {
+  int64_t T; int N; int K;
+  const uint16_t* dy; int64_t ld_dy;        /* [T][N] bf16 */
+  const uint16_t* x; int64_t ldx;           /* [T][K] bf16 */
+  float* dw; int64_t ld_dw;                 /* [N][K] fp32 */
+  float* dbias;                             /* [N] fp32, may be NULL */
+} pmgt_dw_tile_args;
+
+int pmgt_dw_tile_supported(int64_t N, int64_t K);
+int pmgt_dw_tile(const pmgt_dw_tile_args* a, void* stream);
+
+/*
+ * LayerNorm backward from the saved pre-LayerNorm input z (PMGT_LT_RES_LN's aux_out): dy = dy_a + dy_b +
+ * dy_f32 (any subset), dz = gradient wrt z (and wrt the residual), d_o = dz with the dropout mask of the
+ * forward re-applied (gradient wrt the dense output; may alias dz when dropout_p == 0), d_g / d_b fp32
+ * accumulated.  H == 128.
+ */
+typedef struct pmgt_lnbwd_args {
+  int64_t T; int H;
+  const uint16_t* z;
+  const uint16_t* dy_a; const uint16_t* dy_b; const float* dy_f32;
+  const float* ln_g; float ln_eps;
+  float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
+  uint16_t* dz; uint16_t* d_o;
+  float* d_g; float* d_b;
+} pmgt_lnbwd_args;
+
+int pmgt_ln_bwd(const pmgt_lnbwd_args* a, void* stream);
+
 /* column sums: out[n] += sum_t x[t][n]  (bias gradients), x bf16 [T][N] */
 int pmgt_colsum_bf16(const uint16_t* x, int64_t T, int64_t N, int64_t ldx, float* out, void* stream);
 

@@ -83,6 +83,44 @@ class ResLnArgs(C.Structure):
     ]
 
 
+class LinearTileArgs(C.Structure):
+    _fields_ = [
+        ("T", C.c_int64), ("K", C.c_int), ("N", C.c_int),
+        ("x", c_vp), ("ldx", C.c_int64),
+        ("w", c_vp), ("ldw", C.c_int64), ("w_mn", C.c_int),
+        ("epi", C.c_int),
+        ("bias", c_vp),
+        ("out", c_vp), ("ldo", C.c_int64),
+        ("aux_out", c_vp), ("ld_aux_out", C.c_int64),
+        ("e_in", c_vp), ("ld_e", C.c_int64),
+        ("ln_g", c_vp), ("ln_b", c_vp), ("ln_eps", C.c_float),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("dropout_site", C.c_uint32),
+        ("out_f32", c_vp),
+    ]
+
+
+class DwTileArgs(C.Structure):
+    _fields_ = [
+        ("T", C.c_int64), ("N", C.c_int), ("K", C.c_int),
+        ("dy", c_vp), ("ld_dy", C.c_int64),
+        ("x", c_vp), ("ldx", C.c_int64),
+        ("dw", c_vp), ("ld_dw", C.c_int64),
+        ("dbias", c_vp),
+    ]
+
+
+class LnBwdArgs(C.Structure):
+    _fields_ = [
+        ("T", C.c_int64), ("H", C.c_int),
+        ("z", c_vp),
+        ("dy_a", c_vp), ("dy_b", c_vp), ("dy_f32", c_vp),
+        ("ln_g", c_vp), ("ln_eps", C.c_float),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("dropout_site", C.c_uint32),
+        ("dz", c_vp), ("d_o", c_vp),
+        ("d_g", c_vp), ("d_b", c_vp),
+    ]
+
+
 class GsrArgs(C.Structure):
     _fields_ = [
         ("B", C.c_int64), ("SP", C.c_int64), ("H", C.c_int),
@@ -126,6 +164,11 @@ SIGNATURES = {
     "pmgt_attn_core_bwd": (C.c_int, [C.POINTER(AttnArgs), c_vp]),
     "pmgt_res_ln_fwd": (C.c_int, [C.POINTER(ResLnArgs), c_vp]),
     "pmgt_res_ln_bwd": (C.c_int, [C.POINTER(ResLnArgs), c_vp]),
+    "pmgt_linear_tile_supported": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "pmgt_linear_tile": (C.c_int, [C.POINTER(LinearTileArgs), c_vp]),
+    "pmgt_dw_tile_supported": (C.c_int, [C.c_int64, C.c_int64]),
+    "pmgt_dw_tile": (C.c_int, [C.POINTER(DwTileArgs), c_vp]),
+    "pmgt_ln_bwd": (C.c_int, [C.POINTER(LnBwdArgs), c_vp]),
     "pmgt_colsum_bf16": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp]),
     "pmgt_gsr_fwd": (C.c_int, [C.POINTER(GsrArgs), c_vp]),
     "pmgt_gsr_bwd": (C.c_int, [C.POINTER(GsrArgs), c_vp]),

@@ -89,6 +89,19 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint6
   return u >= p;
 }
 
+// keep bits of the 4 consecutive elements idx4 .. idx4+3 (idx4 a multiple of 4): ONE Philox call, same
+// stream as dropout_keep (bit j = keep element idx4 + j).
+__device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint32_t site, uint64_t idx4, float p) {
+  const Philox4 r = philox4x32_10((uint32_t)(idx4 >> 2), (uint32_t)(idx4 >> 34), site, 0x5eedu, (uint32_t)seed,
+                                  (uint32_t)(seed >> 32));
+  uint32_t m = 0;
+  m |= ((float)(r.x >> 8) * (1.0f / 16777216.0f) >= p) ? 1u : 0u;
+  m |= ((float)(r.y >> 8) * (1.0f / 16777216.0f) >= p) ? 2u : 0u;
+  m |= ((float)(r.z >> 8) * (1.0f / 16777216.0f) >= p) ? 4u : 0u;
+  m |= ((float)(r.w >> 8) * (1.0f / 16777216.0f) >= p) ? 8u : 0u;
+  return m;
+}
+
 // ---------------------------------------------------------------------------
 // small device utilities
 // ---------------------------------------------------------------------------

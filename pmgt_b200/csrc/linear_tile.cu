@@ -1,0 +1,679 @@
+// Persistent tcgen05 "token-tile" kernels for the small hidden sizes of the default PMGT encoder
+// (H = I = 128): every nn.Linear of PMGTSelfAttention / BertSelfOutput / BertIntermediate / BertOutput
+// (pmgt/pmgt/modeling_pmgt.py:429-433,371,322-325), forward and backward, with the element-wise work
+// that follows it in the reference fused into the epilogue.
+//
+// Unit of work: a tile of 128 consecutive tokens.  One CTA per SM loops over tiles.  All operands are
+// "images": a [128 rows][128 cols] bf16 block stored as two 64-column slabs of 128 rows x 128 bytes with
+// the 128-byte TMA/UMMA swizzle (32 KiB).  The same image serves as a K-major operand (K = its columns)
+// and as an MN-major operand (K = its rows), so activations are loaded ONCE by TMA and weights stay
+// resident in shared memory for the whole kernel.
+//
+//   linear_tile_kernel   out[T][N] = epi(sum_kc X_kc * W_kc):  y = x W^T (+ bias, GELU, residual + dropout +
+//                        LayerNorm) or dx = dy W (* gelu').  Warp roles: TMA producer | MMA issuer |
+//                        1-2 epilogue groups of 4 warps (TMEM -> registers -> swizzled staging -> TMA store).
+//                        Four 128-column TMEM accumulator slots are handed between MMA and epilogue through
+//                        mbarriers, so the MMAs of the next items overlap the epilogue of the current one.
+//   dw_tile_kernel       dW[N][K] += dY^T X and dbias += colsum(dY): both operands MN-major images, the
+//                        accumulators stay in TMEM across ALL tiles of the CTA and are flushed once with
+//                        vector reductions; four extra warps form the column sums from the staged images.
+//
+// Everything here is HBM-bound by construction (<= 128 FLOP/B); the roofline is the measured copy bandwidth.
+#include "umma.cuh"
+
+namespace pmgt {
+
+constexpr int kImgBytes = 32768;
+constexpr int kSlabBytes = 16384;
+constexpr int kAccSlots = 4;
+
+enum { LT_BIAS = PMGT_LT_BIAS, LT_GELU = PMGT_LT_GELU, LT_RES_LN = PMGT_LT_RES_LN, LT_PLAIN = PMGT_LT_PLAIN,
+       LT_GELU_BWD = PMGT_LT_GELU_BWD };
+
+struct LtParams {
+  int T, num_tiles, N;
+  const float* bias;
+  const float* ln_g;
+  const float* ln_b;
+  float ln_eps;
+  float dropout_p;
+  uint64_t seed;
+  uint32_t site;
+  float* out_f32;
+};
+
+// 16-byte chunk c8 (8 columns) of row r of an image
+__device__ __forceinline__ uint32_t img_off(int r, int c8) {
+  return (uint32_t)((c8 >> 3) * kSlabBytes + r * 128 + (((c8 & 7) ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ void mma_128x128x128(uint32_t tmem_d, uint32_t a_img, bool a_mn, uint32_t b_img, bool b_mn,
+                                                uint32_t idesc, bool accumulate_first) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint64_t da = a_mn ? umma_desc(a_img + ks * 2048, kSlabBytes, 1024)
+                             : umma_desc(a_img + (ks >> 2) * kSlabBytes + (ks & 3) * 32, 16, 1024);
+    const uint64_t db = b_mn ? umma_desc(b_img + ks * 2048, kSlabBytes, 1024)
+                             : umma_desc(b_img + (ks >> 2) * kSlabBytes + (ks & 3) * 32, 16, 1024);
+    umma_bf16(tmem_d, da, db, idesc, (accumulate_first || ks > 0) ? 1u : 0u);
+  }
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <int NC, int KC, int EPI, int NG, int SA, int SE>
+struct LtLayout {
+  static constexpr bool kHasE = (EPI == LT_RES_LN || EPI == LT_GELU_BWD);
+  static constexpr int kNOut = (EPI == LT_GELU) ? 2 : 1;
+  static constexpr int kW = 0;
+  static constexpr int kA = kW + NC * KC * kImgBytes;
+  static constexpr int kE = kA + SA * kImgBytes;
+  static constexpr int kStg = kE + (kHasE ? SE : 0) * kImgBytes;
+  static constexpr int kBar = kStg + NG * kNOut * kImgBytes;
+  static constexpr int kTotal = kBar + 256 + 1024;  // barriers + alignment slack
+};
+
+struct LtBars {
+  uint64_t w_full;
+  uint64_t a_full[4], a_empty[4];
+  uint64_t e_full[4], e_empty[4];
+  uint64_t acc_full[kAccSlots], acc_empty[kAccSlots];
+  uint32_t tmem_base;
+};
+
+template <int NC, int KC, bool B_MN, int EPI, int NG, int SA, int SE>
+__global__ void __launch_bounds__(64 + 128 * NG, 1)
+linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                   const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_out,
+                   const __grid_constant__ CUtensorMap tm_aux, const LtParams p) {
+  using Lay = LtLayout<NC, KC, EPI, NG, SA, SE>;
+  constexpr bool kHasE = Lay::kHasE;
+  constexpr int kNOut = Lay::kNOut;
+  static_assert(!kHasE || NC == 1, "epilogue-input variants are single-chunk");
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  LtBars* bars = reinterpret_cast<LtBars*>(smem + Lay::kBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars->w_full, 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&bars->a_full[s], 1);
+      mbar_init(&bars->a_empty[s], 1);
+      mbar_init(&bars->e_full[s], 1);
+      mbar_init(&bars->e_empty[s], 1);
+    }
+    for (int s = 0; s < kAccSlots; ++s) {
+      mbar_init(&bars->acc_full[s], 1);
+      mbar_init(&bars->acc_empty[s], 128);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tm_x);
+    prefetch_tmap(&tm_w);
+    prefetch_tmap(&tm_out);
+    if (kHasE) prefetch_tmap(&tm_e);
+    if (EPI == LT_GELU || EPI == LT_RES_LN) prefetch_tmap(&tm_aux);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->w_full, (uint32_t)(NC * KC * kImgBytes));
+      for (int kc = 0; kc < KC; ++kc)
+        for (int n = 0; n < NC; ++n) {
+          const uint32_t dst = smem_u32(smem + Lay::kW + (kc * NC + n) * kImgBytes);
+          const int row0 = B_MN ? kc * 128 : n * 128, col0 = B_MN ? n * 128 : kc * 128;
+          tma_load_2d(dst, &tm_w, &bars->w_full, col0, row0);
+          tma_load_2d(dst + kSlabBytes, &tm_w, &bars->w_full, col0 + 64, row0);
+        }
+      uint32_t ia = 0, ie = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < KC; ++kc, ++ia) {
+          const int s = ia % SA;
+          mbar_wait(&bars->a_empty[s], ((ia / SA) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&bars->a_full[s], (uint32_t)kImgBytes);
+          const uint32_t dst = smem_u32(smem + Lay::kA + s * kImgBytes);
+          tma_load_2d(dst, &tm_x, &bars->a_full[s], kc * 128, tile * 128);
+          tma_load_2d(dst + kSlabBytes, &tm_x, &bars->a_full[s], kc * 128 + 64, tile * 128);
+        }
+        if (kHasE) {
+          const int s = ie % SE;
+          mbar_wait(&bars->e_empty[s], ((ie / SE) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&bars->e_full[s], (uint32_t)kImgBytes);
+          const uint32_t dst = smem_u32(smem + Lay::kE + s * kImgBytes);
+          tma_load_2d(dst, &tm_e, &bars->e_full[s], 0, tile * 128);
+          tma_load_2d(dst + kSlabBytes, &tm_e, &bars->e_full[s], 64, tile * 128);
+          ++ie;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(false, B_MN);
+      mbar_wait(&bars->w_full, 0u);
+      tcgen05_fence_after();
+      uint32_t ia = 0, item = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, item += NC) {
+        for (int kc = 0; kc < KC; ++kc, ++ia) {
+          const int s = ia % SA;
+          mbar_wait(&bars->a_full[s], (ia / SA) & 1u);
+          tcgen05_fence_after();
+          const uint32_t a_img = smem_u32(smem + Lay::kA + s * kImgBytes);
+          for (int n = 0; n < NC; ++n) {
+            const uint32_t it = item + n, slot = it % kAccSlots;
+            if (kc == 0) {
+              mbar_wait(&bars->acc_empty[slot], ((it / kAccSlots) & 1u) ^ 1u);
+              tcgen05_fence_after();
+            }
+            const uint32_t b_img = smem_u32(smem + Lay::kW + (kc * NC + n) * kImgBytes);
+            mma_128x128x128(tmem_base + slot * 128u, a_img, false, b_img, B_MN, idesc, kc > 0);
+            if (kc == KC - 1) umma_commit(&bars->acc_full[slot]);
+          }
+          umma_commit(&bars->a_empty[s]);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue groups =====================
+    const int eg = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                   // tile row == TMEM lane
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    const uint32_t bar_id = 1u + (uint32_t)eg;
+    unsigned char* stg0 = smem + Lay::kStg + (eg * kNOut) * kImgBytes;
+    unsigned char* stg1 = stg0 + kImgBytes;  // only when kNOut == 2
+    const float ks = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+    uint32_t item = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, item += NC) {
+      for (int n = 0; n < NC; ++n) {
+        const uint32_t it = item + n;
+        if ((int)(it % NG) != eg) continue;
+        const uint32_t slot = it % kAccSlots;
+        mbar_wait(&bars->acc_full[slot], (it / kAccSlots) & 1u);
+        tcgen05_fence_after();
+        unsigned char* eimg = nullptr;
+        int se = 0;
+        if (kHasE) {
+          se = it % SE;
+          mbar_wait(&bars->e_full[se], (it / SE) & 1u);
+          eimg = smem + Lay::kE + se * kImgBytes;
+        }
+        // the previous TMA store of this group must have finished reading the staging images
+        named_bar_sync(bar_id, 128);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 128u;
+        const long long tok = (long long)tile * 128 + r;
+        float zsum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld_x32(taddr + (uint32_t)c0, acc);
+          tmem_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c8 = (c0 >> 3) + g;
+            const int col = n * 128 + c0 + g * 8;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+            if (EPI == LT_BIAS || EPI == LT_GELU || EPI == LT_RES_LN) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (EPI == LT_GELU) {
+              uint4 pre;
+              pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
+              pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(stg0 + img_off(r, c8)) = pre;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(stg1 + img_off(r, c8)) = o;
+            } else if (EPI == LT_GELU_BWD) {
+              const uint4 pre = *reinterpret_cast<const uint4*>(eimg + img_off(r, c8));
+              float x[8];
+              unpack_bf16x2(pre.x, x[0], x[1]); unpack_bf16x2(pre.y, x[2], x[3]);
+              unpack_bf16x2(pre.z, x[4], x[5]); unpack_bf16x2(pre.w, x[6], x[7]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(x[j]);
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(stg0 + img_off(r, c8)) = o;
+            } else if (EPI == LT_RES_LN) {
+              if (p.dropout_p > 0.f) {
+                const uint64_t idx = (uint64_t)tok * 128u + (uint64_t)(c0 + g * 8);
+                const uint32_t k0 = dropout_keep4(p.seed, p.site, idx, p.dropout_p);
+                const uint32_t k1 = dropout_keep4(p.seed, p.site, idx + 4, p.dropout_p);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  v[j] = (k0 >> j) & 1u ? v[j] * ks : 0.f;
+                  v[4 + j] = (k1 >> j) & 1u ? v[4 + j] * ks : 0.f;
+                }
+              }
+              uint4* zp = reinterpret_cast<uint4*>(eimg + img_off(r, c8));
+              const uint4 rs = *zp;
+              float x[8];
+              unpack_bf16x2(rs.x, x[0], x[1]); unpack_bf16x2(rs.y, x[2], x[3]);
+              unpack_bf16x2(rs.z, x[4], x[5]); unpack_bf16x2(rs.w, x[6], x[7]);
+              uint4 z;
+              z.x = pack_bf16x2(v[0] + x[0], v[1] + x[1]); z.y = pack_bf16x2(v[2] + x[2], v[3] + x[3]);
+              z.z = pack_bf16x2(v[4] + x[4], v[5] + x[5]); z.w = pack_bf16x2(v[6] + x[6], v[7] + x[7]);
+              *zp = z;  // z replaces the residual in place (the row is private to this thread)
+              float zf[8];
+              unpack_bf16x2(z.x, zf[0], zf[1]); unpack_bf16x2(z.y, zf[2], zf[3]);
+              unpack_bf16x2(z.z, zf[4], zf[5]); unpack_bf16x2(z.w, zf[6], zf[7]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) zsum += zf[j];
+            } else {  // LT_BIAS, LT_PLAIN
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(stg0 + img_off(r, c8)) = o;
+            }
+          }
+        }
+        // accumulator slot drained
+        tcgen05_fence_before();
+        mbar_arrive(&bars->acc_empty[slot]);
+        if (EPI == LT_RES_LN) {
+          // LayerNorm over the bf16-rounded z (exactly what the backward pass re-reads)
+          const float mean = zsum * (1.f / 128.f);
+          float q = 0.f;
+#pragma unroll
+          for (int c8 = 0; c8 < 16; ++c8) {
+            const uint4 z = *reinterpret_cast<const uint4*>(eimg + img_off(r, c8));
+            float zf[8];
+            unpack_bf16x2(z.x, zf[0], zf[1]); unpack_bf16x2(z.y, zf[2], zf[3]);
+            unpack_bf16x2(z.z, zf[4], zf[5]); unpack_bf16x2(z.w, zf[6], zf[7]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = zf[j] - mean; q = fmaf(d, d, q); }
+          }
+          const float rstd = rsqrtf(q * (1.f / 128.f) + p.ln_eps);
+          const bool f32_ok = p.out_f32 != nullptr && tok < p.T;
+#pragma unroll
+          for (int c8 = 0; c8 < 16; ++c8) {
+            const uint4 z = *reinterpret_cast<const uint4*>(eimg + img_off(r, c8));
+            float zf[8];
+            unpack_bf16x2(z.x, zf[0], zf[1]); unpack_bf16x2(z.y, zf[2], zf[3]);
+            unpack_bf16x2(z.z, zf[4], zf[5]); unpack_bf16x2(z.w, zf[6], zf[7]);
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c8 * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c8 * 8 + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c8 * 8 + 4));
+            float y[8];
+            y[0] = (zf[0] - mean) * rstd * g0.x + b0.x; y[1] = (zf[1] - mean) * rstd * g0.y + b0.y;
+            y[2] = (zf[2] - mean) * rstd * g0.z + b0.z; y[3] = (zf[3] - mean) * rstd * g0.w + b0.w;
+            y[4] = (zf[4] - mean) * rstd * g1.x + b1.x; y[5] = (zf[5] - mean) * rstd * g1.y + b1.y;
+            y[6] = (zf[6] - mean) * rstd * g1.z + b1.z; y[7] = (zf[7] - mean) * rstd * g1.w + b1.w;
+            uint4 o;
+            o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
+            o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+            *reinterpret_cast<uint4*>(stg0 + img_off(r, c8)) = o;
+            if (f32_ok) {
+              float* o32 = p.out_f32 + tok * 128 + c8 * 8;
+              *reinterpret_cast<float4*>(o32) = make_float4(y[0], y[1], y[2], y[3]);
+              *reinterpret_cast<float4*>(o32 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            }
+          }
+        }
+        // hand the staged images to the TMA store engine
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (leader) {
+          const int col = n * 128, row = tile * 128;
+          if (EPI == LT_GELU) {
+            tma_store_2d(&tm_aux, smem_u32(stg0), col, row);
+            tma_store_2d(&tm_aux, smem_u32(stg0) + kSlabBytes, col + 64, row);
+            tma_store_2d(&tm_out, smem_u32(stg1), col, row);
+            tma_store_2d(&tm_out, smem_u32(stg1) + kSlabBytes, col + 64, row);
+          } else {
+            tma_store_2d(&tm_out, smem_u32(stg0), col, row);
+            tma_store_2d(&tm_out, smem_u32(stg0) + kSlabBytes, col + 64, row);
+            if (EPI == LT_RES_LN) {
+              tma_store_2d(&tm_aux, smem_u32(eimg), col, row);
+              tma_store_2d(&tm_aux, smem_u32(eimg) + kSlabBytes, col + 64, row);
+            }
+          }
+          tma_store_commit();
+          tma_store_wait_read0();
+          if (kHasE) mbar_arrive(&bars->e_empty[se]);
+        }
+      }
+    }
+    if (leader) tma_store_wait_all0();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dW / dbias
+// ---------------------------------------------------------------------------------------------------
+struct DwBars {
+  uint64_t x_full[4], x_empty[4];
+  uint64_t dy_full[8], dy_empty[8];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+struct DwParams {
+  int T, num_tiles;
+  float* dw;
+  long long ld_dw;
+  float* dbias;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int NC, int SX, int SD>
+__global__ void __launch_bounds__(192, 1)
+dw_tile_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x, const DwParams p) {
+  constexpr int kX = 0;
+  constexpr int kDY = SX * kImgBytes;
+  constexpr int kRed = kDY + SD * kImgBytes;       // [8][128] floats for the column-sum reduction
+  constexpr int kBar = kRed + 8 * 128 * 4;
+  constexpr uint32_t kCols = NC * 128 <= 128 ? 128u : (NC * 128 <= 256 ? 256u : 512u);
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  DwBars* bars = reinterpret_cast<DwBars*>(smem + kBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&bars->x_full[s], 1);
+      mbar_init(&bars->x_empty[s], 1);
+    }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&bars->dy_full[s], 1);
+      mbar_init(&bars->dy_empty[s], 1 + 4);  // MMA commit + one arrival per column-sum warp
+    }
+    mbar_init(&bars->done, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tm_dy);
+    prefetch_tmap(&tm_x);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"(kCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const bool has_tiles = (int)blockIdx.x < p.num_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t ix = 0, id = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ix) {
+        {
+          const int s = ix % SX;
+          mbar_wait(&bars->x_empty[s], ((ix / SX) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&bars->x_full[s], (uint32_t)kImgBytes);
+          const uint32_t dst = smem_u32(smem + kX + s * kImgBytes);
+          tma_load_2d(dst, &tm_x, &bars->x_full[s], 0, tile * 128);
+          tma_load_2d(dst + kSlabBytes, &tm_x, &bars->x_full[s], 64, tile * 128);
+        }
+        for (int n = 0; n < NC; ++n, ++id) {
+          const int s = id % SD;
+          mbar_wait(&bars->dy_empty[s], ((id / SD) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&bars->dy_full[s], (uint32_t)kImgBytes);
+          const uint32_t dst = smem_u32(smem + kDY + s * kImgBytes);
+          tma_load_2d(dst, &tm_dy, &bars->dy_full[s], n * 128, tile * 128);
+          tma_load_2d(dst + kSlabBytes, &tm_dy, &bars->dy_full[s], n * 128 + 64, tile * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(true, true);
+      uint32_t ix = 0, id = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ix) {
+        const int sx = ix % SX;
+        mbar_wait(&bars->x_full[sx], (ix / SX) & 1u);
+        const uint32_t x_img = smem_u32(smem + kX + sx * kImgBytes);
+        for (int n = 0; n < NC; ++n, ++id) {
+          const int s = id % SD;
+          mbar_wait(&bars->dy_full[s], (id / SD) & 1u);
+          tcgen05_fence_after();
+          const uint32_t dy_img = smem_u32(smem + kDY + s * kImgBytes);
+          // dW_n[128 x 128] += dY_n^T (M = dY columns, K = tokens) * X (K = tokens, N = X columns)
+          mma_128x128x128(tmem_base + (uint32_t)n * 128u, dy_img, true, x_img, true, idesc, !first);
+          umma_commit(&bars->dy_empty[s]);
+        }
+        umma_commit(&bars->x_empty[sx]);
+        first = false;
+      }
+      umma_commit(&bars->done);
+    }
+  } else {
+    // ===================== column sums of dY, then the TMEM flush =====================
+    const int t = threadIdx.x - 64;        // 0..127
+    const int cg = t & 15, rg = t >> 4;    // 8 columns x 16 rows per thread
+    float cs[NC][8];
+#pragma unroll
+    for (int n = 0; n < NC; ++n)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[n][j] = 0.f;
+    uint32_t id = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+#pragma unroll
+      for (int n = 0; n < NC; ++n, ++id) {
+        const int s = id % SD;
+        mbar_wait(&bars->dy_full[s], (id / SD) & 1u);
+        if (p.dbias) {
+          const unsigned char* img = smem + kDY + s * kImgBytes;
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const uint4 u = *reinterpret_cast<const uint4*>(img + img_off(rg * 16 + i, cg));
+            float f[8];
+            unpack_bf16x2(u.x, f[0], f[1]); unpack_bf16x2(u.y, f[2], f[3]);
+            unpack_bf16x2(u.z, f[4], f[5]); unpack_bf16x2(u.w, f[6], f[7]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cs[n][j] += f[j];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->dy_empty[s]);
+      }
+    }
+    if (p.dbias && has_tiles) {
+      float* red = reinterpret_cast<float*>(smem + kRed);
+#pragma unroll
+      for (int n = 0; n < NC; ++n) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[rg * 128 + cg * 8 + j] = cs[n][j];
+        named_bar_sync(1, 128);
+        float v = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) v += red[g * 128 + t];
+        if (v != 0.f) atomicAdd(p.dbias + n * 128 + t, v);
+        named_bar_sync(1, 128);
+      }
+    }
+    if (has_tiles) {
+      mbar_wait(&bars->done, 0u);
+      tcgen05_fence_after();
+      const int quarter = warp & 3;
+      const int r = quarter * 32 + lane;
+#pragma unroll 1
+      for (int n = 0; n < NC; ++n) {
+        float* dst = p.dw + (long long)(n * 128 + r) * p.ld_dw;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(n * 128 + c0), acc);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(dst + c0 + j, __uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                       __uint_as_float(acc[j + 3]));
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+template <int NC, int KC, bool B_MN, int EPI, int NG, int SA, int SE>
+static int launch_lt(const pmgt_linear_tile_args* a, cudaStream_t st) {
+  using Lay = LtLayout<NC, KC, EPI, NG, SA, SE>;
+  static_assert(Lay::kTotal <= 232448, "shared memory budget (227 KiB)");
+  auto kern = linear_tile_kernel<NC, KC, B_MN, EPI, NG, SA, SE>;
+  static bool configured = false;
+  if (!configured) {
+    PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay::kTotal));
+    configured = true;
+  }
+  CUtensorMap tx, tw, te, to, ta;
+  memset(&te, 0, sizeof(te));
+  memset(&ta, 0, sizeof(ta));
+  int rc;
+  if ((rc = make_tmap(&tx, a->x, a->K, a->T, a->ldx, 64, 128))) return rc;
+  // weights: w_mn = 0 -> [N][K]; w_mn = 1 -> [K][N]  (rows x inner)
+  if ((rc = B_MN ? make_tmap(&tw, a->w, a->N, a->K, a->ldw, 64, 128) : make_tmap(&tw, a->w, a->K, a->N, a->ldw, 64, 128)))
+    return rc;
+  if ((rc = make_tmap(&to, a->out, a->N, a->T, a->ldo, 64, 128))) return rc;
+  if (Lay::kHasE && (rc = make_tmap(&te, a->e_in, a->N, a->T, a->ld_e, 64, 128))) return rc;
+  if ((EPI == LT_GELU || EPI == LT_RES_LN) && (rc = make_tmap(&ta, a->aux_out, a->N, a->T, a->ld_aux_out, 64, 128)))
+    return rc;
+  LtParams p;
+  p.T = (int)a->T;
+  p.num_tiles = (int)((a->T + 127) / 128);
+  p.N = a->N;
+  p.bias = a->bias; p.ln_g = a->ln_g; p.ln_b = a->ln_b; p.ln_eps = a->ln_eps;
+  p.dropout_p = a->dropout_p; p.seed = a->dropout_seed; p.site = a->dropout_site;
+  p.out_f32 = a->out_f32;
+  int grid = num_sms();
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  kern<<<grid, 64 + 128 * NG, Lay::kTotal, st>>>(tx, tw, te, to, ta, p);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+template <int NC, int SX, int SD>
+static int launch_dw(const pmgt_dw_tile_args* a, cudaStream_t st) {
+  constexpr int smem = (SX + SD) * kImgBytes + 8 * 128 * 4 + 256 + 1024;
+  static_assert(smem <= 232448, "shared memory budget (227 KiB)");
+  auto kern = dw_tile_kernel<NC, SX, SD>;
+  static bool configured = false;
+  if (!configured) {
+    PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  CUtensorMap tdy, tx;
+  int rc;
+  if ((rc = make_tmap(&tdy, a->dy, a->N, a->T, a->ld_dy, 64, 128))) return rc;
+  if ((rc = make_tmap(&tx, a->x, a->K, a->T, a->ldx, 64, 128))) return rc;
+  DwParams p;
+  p.T = (int)a->T;
+  p.num_tiles = (int)((a->T + 127) / 128);
+  p.dw = a->dw; p.ld_dw = a->ld_dw; p.dbias = a->dbias;
+  int grid = num_sms();
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  kern<<<grid, 192, smem, st>>>(tdy, tx, p);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+}  // namespace pmgt
+
+using namespace pmgt;
+
+extern "C" {
+
+int pmgt_linear_tile_supported(int64_t K, int64_t N, int w_mn, int epi) {
+  if (K % 128 != 0 || N % 128 != 0 || K <= 0 || N <= 0) return 0;
+  const int kc = (int)(K / 128), nc = (int)(N / 128);
+  if (epi == PMGT_LT_BIAS && !w_mn) return (kc == 1 && (nc == 1 || nc == 4)) ? 1 : 0;
+  if (epi == PMGT_LT_GELU && !w_mn) return (kc == 1 && nc == 1) ? 1 : 0;
+  if (epi == PMGT_LT_RES_LN && !w_mn) return (kc == 1 && nc == 1) ? 1 : 0;
+  if (epi == PMGT_LT_PLAIN && w_mn) return (nc == 1 && (kc == 1 || kc == 4)) ? 1 : 0;
+  if (epi == PMGT_LT_GELU_BWD && w_mn) return (kc == 1 && nc == 1) ? 1 : 0;
+  return 0;
+}
+
+int pmgt_linear_tile(const pmgt_linear_tile_args* a, void* stream) {
+  PMGT_REQUIRE(a && a->x && a->w && a->out, "pmgt_linear_tile: null argument");
+  PMGT_REQUIRE(a->T >= 0 && a->T < (1ll << 31) - 128, "pmgt_linear_tile: bad T");
+  if (a->T == 0) return PMGT_OK;
+  PMGT_REQUIRE(pmgt_linear_tile_supported(a->K, a->N, a->w_mn, a->epi),
+               "pmgt_linear_tile: unsupported shape K=%d N=%d w_mn=%d epi=%d (use pmgt_gemm_bf16)", a->K, a->N, a->w_mn,
+               a->epi);
+  PMGT_REQUIRE(a->ldx % 8 == 0 && a->ldw % 8 == 0 && a->ldo % 8 == 0, "pmgt_linear_tile: row pitches must be multiples of 8");
+  PMGT_REQUIRE((((uintptr_t)a->x | (uintptr_t)a->w | (uintptr_t)a->out) & 15) == 0, "pmgt_linear_tile: 16-byte alignment");
+  const int kc = a->K / 128, nc = a->N / 128;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->epi) {
+    case PMGT_LT_BIAS:
+      PMGT_REQUIRE(a->bias, "pmgt_linear_tile: bias required");
+      if (nc == 4) return launch_lt<4, 1, false, LT_BIAS, 1, 2, 1>(a, st);
+      return launch_lt<1, 1, false, LT_BIAS, 2, 3, 1>(a, st);
+    case PMGT_LT_GELU:
+      PMGT_REQUIRE(a->bias && a->aux_out && a->ld_aux_out % 8 == 0, "pmgt_linear_tile: GELU needs bias and aux_out");
+      return launch_lt<1, 1, false, LT_GELU, 2, 2, 1>(a, st);
+    case PMGT_LT_RES_LN:
+      PMGT_REQUIRE(a->bias && a->aux_out && a->e_in && a->ln_g && a->ln_b && a->ld_aux_out % 8 == 0 && a->ld_e % 8 == 0,
+                   "pmgt_linear_tile: RES_LN needs bias, residual (e_in), z out (aux_out), ln_g, ln_b");
+      PMGT_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "pmgt_linear_tile: bad dropout_p");
+      return launch_lt<1, 1, false, LT_RES_LN, 2, 2, 2>(a, st);
+    case PMGT_LT_PLAIN:
+      if (kc == 4) return launch_lt<1, 4, true, LT_PLAIN, 1, 2, 1>(a, st);
+      return launch_lt<1, 1, true, LT_PLAIN, 2, 3, 1>(a, st);
+    case PMGT_LT_GELU_BWD:
+      PMGT_REQUIRE(a->e_in && a->ld_e % 8 == 0, "pmgt_linear_tile: GELU_BWD needs the pre-activation (e_in)");
+      return launch_lt<1, 1, true, LT_GELU_BWD, 2, 2, 2>(a, st);
+  }
+  set_error("pmgt_linear_tile: unknown epilogue %d", a->epi);
+  return PMGT_ERR_INVALID;
+}
+
+int pmgt_dw_tile_supported(int64_t N, int64_t K) { return (K == 128 && (N == 128 || N == 512)) ? 1 : 0; }
+
+int pmgt_dw_tile(const pmgt_dw_tile_args* a, void* stream) {
+  PMGT_REQUIRE(a && a->dy && a->x && a->dw, "pmgt_dw_tile: null argument");
+  PMGT_REQUIRE(a->T >= 0 && a->T < (1ll << 31) - 128, "pmgt_dw_tile: bad T");
+  if (a->T == 0) return PMGT_OK;
+  PMGT_REQUIRE(pmgt_dw_tile_supported(a->N, a->K), "pmgt_dw_tile: unsupported shape N=%d K=%d (use pmgt_gemm_bf16)", a->N,
+               a->K);
+  PMGT_REQUIRE(a->ld_dy % 8 == 0 && a->ldx % 8 == 0 && a->ld_dw % 4 == 0, "pmgt_dw_tile: row pitch alignment");
+  PMGT_REQUIRE((((uintptr_t)a->dy | (uintptr_t)a->x | (uintptr_t)a->dw) & 15) == 0, "pmgt_dw_tile: 16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->N == 512) return launch_dw<4, 2, 4>(a, st);
+  return launch_dw<1, 3, 3>(a, st);
+}
+
+}  // extern "C"

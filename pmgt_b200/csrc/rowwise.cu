@@ -454,6 +454,131 @@ __global__ void __launch_bounds__(kRowThreads) res_ln_bwd_kernel(const pmgt_resl
 }
 
 // ---------------------------------------------------------------------------
+// LayerNorm backward from the saved pre-LayerNorm input z, H = 128.
+// A half-warp owns a row (8 columns = one 16-byte load per lane), two rows per half-warp in flight;
+// the column sums d_g / d_b stay in registers over all rows of the thread and are reduced once per CTA.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8_row(const uint4& u, float* f) {
+  unpack_bf16x2(u.x, f[0], f[1]); unpack_bf16x2(u.y, f[2], f[3]);
+  unpack_bf16x2(u.z, f[4], f[5]); unpack_bf16x2(u.w, f[6], f[7]);
+}
+__device__ __forceinline__ uint4 pack8_row(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+__global__ void __launch_bounds__(256) ln_bwd128_kernel(const pmgt_lnbwd_args a) {
+  constexpr int H = 128, U = 2;
+  __shared__ float red[16][2][H];
+  const int lane = threadIdx.x & 31, hw = threadIdx.x >> 4;  // 16 half-warps per CTA
+  const int c = (lane & 15) * 8;
+  const long long hw0 = (long long)blockIdx.x * 16 + hw;
+  const long long nhw = (long long)gridDim.x * 16;
+  const float ks = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
+  const bool sep_do = a.d_o != nullptr && a.d_o != a.dz;
+  float gam[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(a.ln_g + c), g1 = *reinterpret_cast<const float4*>(a.ln_g + c + 4);
+    gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+  }
+  float dgam[8], dbet[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dgam[j] = dbet[j] = 0.f;
+  // all lanes of a warp run the same number of iterations (shuffles need full participation)
+  const long long iters = (a.T + nhw * U - 1) / (nhw * U);
+  for (long long itn = 0; itn < iters; ++itn) {
+    uint4 zu[U], da[U], db[U];
+    float4 df0[U], df1[U];
+    bool ok[U];
+    long long tok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      tok[u] = (itn * U + u) * nhw + hw0;
+      ok[u] = tok[u] < a.T;
+      const long long o = (ok[u] ? tok[u] : 0) * H + c;
+      zu[u] = *reinterpret_cast<const uint4*>(a.z + o);
+      da[u] = a.dy_a ? *reinterpret_cast<const uint4*>(a.dy_a + o) : make_uint4(0, 0, 0, 0);
+      db[u] = a.dy_b ? *reinterpret_cast<const uint4*>(a.dy_b + o) : make_uint4(0, 0, 0, 0);
+      if (a.dy_f32) {
+        df0[u] = *reinterpret_cast<const float4*>(a.dy_f32 + o);
+        df1[u] = *reinterpret_cast<const float4*>(a.dy_f32 + o + 4);
+      } else {
+        df0[u] = df1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float z[8], dy[8], t[8];
+      unpack8_row(zu[u], z);
+      unpack8_row(da[u], dy);
+      unpack8_row(db[u], t);
+      dy[0] += t[0] + df0[u].x; dy[1] += t[1] + df0[u].y; dy[2] += t[2] + df0[u].z; dy[3] += t[3] + df0[u].w;
+      dy[4] += t[4] + df1[u].x; dy[5] += t[5] + df1[u].y; dy[6] += t[6] + df1[u].z; dy[7] += t[7] + df1[u].w;
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += z[j];
+      const float mean = half_warp_sum(s) * (1.f / H);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { z[j] -= mean; q = fmaf(z[j], z[j], q); }
+      const float rstd = rsqrtf(half_warp_sum(q) * (1.f / H) + a.ln_eps);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        z[j] *= rstd;  // xhat
+        if (ok[u]) { dgam[j] = fmaf(dy[j], z[j], dgam[j]); dbet[j] += dy[j]; }
+        dy[j] *= gam[j];
+        s1 += dy[j];
+        s2 = fmaf(dy[j], z[j], s2);
+      }
+      s1 = half_warp_sum(s1) * (1.f / H);
+      s2 = half_warp_sum(s2) * (1.f / H);
+      float dz[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dz[j] = rstd * (dy[j] - s1 - z[j] * s2);
+      if (ok[u]) {
+        *reinterpret_cast<uint4*>(a.dz + tok[u] * H + c) = pack8_row(dz);
+        if (sep_do) {
+          if (a.dropout_p > 0.f) {
+            const uint64_t idx = (uint64_t)tok[u] * H + c;
+            const uint32_t k0 = dropout_keep4(a.dropout_seed, a.dropout_site, idx, a.dropout_p);
+            const uint32_t k1 = dropout_keep4(a.dropout_seed, a.dropout_site, idx + 4, a.dropout_p);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              dz[j] = (k0 >> j) & 1u ? dz[j] * ks : 0.f;
+              dz[4 + j] = (k1 >> j) & 1u ? dz[4 + j] * ks : 0.f;
+            }
+          }
+          *reinterpret_cast<uint4*>(a.d_o + tok[u] * H + c) = pack8_row(dz);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[hw][0][c + j] = dgam[j];
+    red[hw][1][c + j] = dbet[j];
+  }
+  __syncthreads();
+  {
+    const int which = threadIdx.x >> 7, col = threadIdx.x & 127;
+    float v = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) v += red[g][which][col];
+    float* dst = which == 0 ? a.d_g : a.d_b;
+    if (dst && v != 0.f) atomicAdd(dst + col, v);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // column sums of a bf16 matrix: out[n] += sum_t x[t][n]
 // ---------------------------------------------------------------------------
 // 256 threads = (N / 8) column threads x `groups` row groups; every thread keeps 8 column sums of the rows
@@ -664,6 +789,20 @@ int pmgt_res_ln_bwd(const pmgt_resln_args* a, void* stream) {
     }
     res_ln_bwd_kernel<8><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(*a);
   }
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+int pmgt_ln_bwd(const pmgt_lnbwd_args* a, void* stream) {
+  PMGT_REQUIRE(a && a->z && a->ln_g && a->dz && (a->dy_a || a->dy_b || a->dy_f32), "pmgt_ln_bwd: null argument");
+  PMGT_REQUIRE(a->H == 128, "pmgt_ln_bwd: H must be 128 (other sizes: pmgt_res_ln_bwd)");
+  PMGT_REQUIRE(a->dropout_p == 0.f || (a->d_o && a->d_o != a->dz), "pmgt_ln_bwd: dropout needs a separate d_o buffer");
+  PMGT_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "pmgt_ln_bwd: bad dropout_p");
+  if (a->T == 0) return PMGT_OK;
+  long long ctas = (a->T + 31) / 32;
+  const long long cap = (long long)num_sms() * 8;
+  if (ctas > cap) ctas = cap;
+  ln_bwd128_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(*a);
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
 }

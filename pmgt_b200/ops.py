@@ -9,7 +9,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import AttnArgs, EmbedArgs, GemmArgs, GsrArgs, NfrArgs, ResLnArgs, check, cur_stream, ptr
+from ._lib import (AttnArgs, DwTileArgs, EmbedArgs, GemmArgs, GsrArgs, LinearTileArgs, LnBwdArgs, NfrArgs, ResLnArgs, check,
+                   cur_stream, ptr)
 
 EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_ADDEND, EPI_OUT_F32, EPI_ATOMIC = 1, 2, 4, 8, 16, 32
 BF16 = torch.bfloat16
@@ -111,6 +112,71 @@ def linear_dw(dy, x, dw_f32, *, rows=None, src_rows=0, x_cols=None, tag=None):
     gemm(dy, x, dw_f32, M=N, N=K, K=T, lda=dy.stride(0), ldb=x.stride(0), ldo=dw_f32.stride(0), a_mn=True, b_mn=True,
          b_rows=rows, b_src_rows=src_rows, epi=EPI_ATOMIC, split_k=split,
          tag=tag or ("gemm_dw_gather" if rows is not None else "gemm_dw"))
+
+
+# -- persistent token-tile kernels (fast path for H = I = 128) ------------------------------------
+LT_BIAS, LT_GELU, LT_RES_LN, LT_PLAIN, LT_GELU_BWD = 0, 1, 2, 3, 4
+
+
+def linear_tile_supported(K, N, w_mn, epi) -> bool:
+    return bool(_lib.lib().pmgt_linear_tile_supported(K, N, int(w_mn), epi))
+
+
+def dw_tile_supported(N, K) -> bool:
+    return bool(_lib.lib().pmgt_dw_tile_supported(N, K))
+
+
+def linear_tile(x, w, out, epi, *, w_mn=False, bias=None, aux_out=None, e_in=None, ln_g=None, ln_b=None, ln_eps=0.0,
+                p=0.0, seed=0, site=0, out_f32=None, tag=None):
+    """``pmgt_linear_tile``: out[T,N] = epi(x[T,K] @ w^T) (w_mn=False, w [N,K]) or epi(x[T,K] @ w) (w_mn=True, w [K,N])."""
+    _require_cuda(x, "x")
+    T, K = x.shape
+    N = out.shape[1]
+    a = LinearTileArgs()
+    a.T, a.K, a.N = T, K, N
+    a.x, a.ldx = ptr(x), x.stride(0)
+    a.w, a.ldw, a.w_mn = ptr(w), w.stride(0), int(w_mn)
+    a.epi = epi
+    a.bias = ptr(bias)
+    a.out, a.ldo = ptr(out), out.stride(0)
+    a.aux_out, a.ld_aux_out = ptr(aux_out), (aux_out.stride(0) if aux_out is not None else 0)
+    a.e_in, a.ld_e = ptr(e_in), (e_in.stride(0) if e_in is not None else 0)
+    a.ln_g, a.ln_b, a.ln_eps = ptr(ln_g), ptr(ln_b), ln_eps
+    a.dropout_p, a.dropout_seed, a.dropout_site = p, seed, site
+    a.out_f32 = ptr(out_f32)
+    nbytes = 2 * T * K + 2 * K * N + 2 * T * N
+    if aux_out is not None:
+        nbytes += 2 * T * N
+    if e_in is not None:
+        nbytes += 2 * T * N
+    if out_f32 is not None:
+        nbytes += 4 * T * N
+    _run(tag or "linear_tile", _lib.lib().pmgt_linear_tile, (C.byref(a), cur_stream()), 1, nbytes, 2 * T * N * K)
+
+
+def dw_tile(dy, x, dw_f32, dbias=None, tag="dw_tile"):
+    """``pmgt_dw_tile``: dw[N,K] += dy[T,N]^T @ x[T,K]; dbias[N] += dy.sum(0)."""
+    T, N = dy.shape
+    K = x.shape[1]
+    a = DwTileArgs()
+    a.T, a.N, a.K = T, N, K
+    a.dy, a.ld_dy = ptr(dy), dy.stride(0)
+    a.x, a.ldx = ptr(x), x.stride(0)
+    a.dw, a.ld_dw = ptr(dw_f32), dw_f32.stride(0)
+    a.dbias = ptr(dbias)
+    _run(tag, _lib.lib().pmgt_dw_tile, (C.byref(a), cur_stream()), 1, 2 * T * (N + K) + 4 * N * K, 2 * T * N * K)
+
+
+def ln_bwd(T, H, z, ln_g, eps, p, seed, site, dz, d_o, d_g, d_b, dy_a=None, dy_b=None, dy_f32=None):
+    a = LnBwdArgs()
+    a.T, a.H = T, H
+    a.z, a.dy_a, a.dy_b, a.dy_f32 = ptr(z), ptr(dy_a), ptr(dy_b), ptr(dy_f32)
+    a.ln_g, a.ln_eps = ptr(ln_g), eps
+    a.dropout_p, a.dropout_seed, a.dropout_site = p, seed, site
+    a.dz, a.d_o, a.d_g, a.d_b = ptr(dz), ptr(d_o), ptr(d_g), ptr(d_b)
+    n_in = 1 + (dy_a is not None) + (dy_b is not None) + 2 * (dy_f32 is not None)
+    n_out = 1 + (d_o is not None and d_o is not dz)
+    _run("ln_bwd", _lib.lib().pmgt_ln_bwd, (C.byref(a), cur_stream()), 1, 2 * T * H * (n_in + n_out))
 
 
 def embed_args(rows, L, H, ev, et, w_att, b_att, pos, role, ln_g, ln_b, eps, p, seed, site, **kw):

@@ -1,0 +1,148 @@
+"""Parity of the persistent tcgen05 token-tile kernels (pmgt_linear_tile / pmgt_dw_tile / pmgt_ln_bwd) against fp32
+torch on identical bf16-rounded inputs.  Sizes cover a ragged last tile, fewer tiles than SMs and more tiles than SMs
+(persistent loop wrap-around, ring / TMEM-slot phase flips)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+SIZES = [200, 128 * 5, 40000 + 37]
+
+
+def _ops():
+    from pmgt_b200 import ops
+    return ops
+
+
+def _r(*shape, s=1.0):
+    return (torch.randn(*shape, device="cuda") * s).to(BF16)
+
+
+def _close(got, want, tol=1e-2, name=""):
+    scale = want.abs().max().clamp_min(1e-6)
+    assert torch.isfinite(got.float()).all(), f"{name}: non-finite"
+    err = float((got.float() - want).abs().max() / scale)
+    assert err < tol, f"{name}: max scaled error {err:.4g} >= {tol}"
+
+
+@pytest.mark.parametrize("T", SIZES)
+@pytest.mark.parametrize("N", [128, 512])
+def test_bias(T, N):
+    ops = _ops()
+    x, w = _r(T, 128), _r(N, 128, s=0.1)
+    b = torch.randn(N, device="cuda")
+    out = torch.full((T, N), 7.0, device="cuda", dtype=BF16)
+    ops.linear_tile(x, w, out, ops.LT_BIAS, bias=b)
+    _close(out, F.linear(x.float(), w.float(), b), name="bias")
+
+
+@pytest.mark.parametrize("T", SIZES)
+def test_gelu(T):
+    ops = _ops()
+    x, w = _r(T, 128), _r(128, 128, s=0.1)
+    b = torch.randn(128, device="cuda") * 0.3
+    out = torch.empty(T, 128, device="cuda", dtype=BF16)
+    pre = torch.empty_like(out)
+    ops.linear_tile(x, w, out, ops.LT_GELU, bias=b, aux_out=pre)
+    want_pre = F.linear(x.float(), w.float(), b)
+    _close(pre, want_pre, name="pre")
+    _close(out, F.gelu(want_pre), name="gelu")
+
+
+@pytest.mark.parametrize("T", SIZES)
+@pytest.mark.parametrize("f32", [False, True])
+def test_res_ln(T, f32):
+    ops = _ops()
+    x, w, res = _r(T, 128), _r(128, 128, s=0.1), _r(T, 128)
+    b = torch.randn(128, device="cuda") * 0.3
+    g = 1 + 0.1 * torch.randn(128, device="cuda")
+    be = 0.1 * torch.randn(128, device="cuda")
+    out = torch.empty(T, 128, device="cuda", dtype=BF16)
+    z = torch.empty_like(out)
+    o32 = torch.empty(T, 128, device="cuda") if f32 else None
+    ops.linear_tile(x, w, out, ops.LT_RES_LN, bias=b, aux_out=z, e_in=res, ln_g=g, ln_b=be, ln_eps=1e-12, out_f32=o32)
+    want_z = F.linear(x.float(), w.float(), b) + res.float()
+    _close(z, want_z, name="z")
+    want = F.layer_norm(want_z, (128,), g, be, 1e-12)
+    _close(out, want, 1.5e-2, name="y")
+    if f32:
+        _close(o32, want, 1.5e-2, name="y_f32")
+        assert torch.equal(o32.to(BF16), out)
+
+
+@pytest.mark.parametrize("T", SIZES)
+@pytest.mark.parametrize("K", [128, 512])
+def test_plain_dx(T, K):
+    ops = _ops()
+    dy, w = _r(T, K), _r(K, 128, s=0.1)  # w is the nn.Linear weight [N_w = K][K_w = 128]
+    out = torch.empty(T, 128, device="cuda", dtype=BF16)
+    ops.linear_tile(dy, w, out, ops.LT_PLAIN, w_mn=True)
+    _close(out, dy.float() @ w.float(), name="dx")
+
+
+@pytest.mark.parametrize("T", SIZES)
+def test_gelu_bwd(T):
+    ops = _ops()
+    dy, w, pre = _r(T, 128), _r(128, 128, s=0.1), _r(T, 128)
+    out = torch.empty(T, 128, device="cuda", dtype=BF16)
+    ops.linear_tile(dy, w, out, ops.LT_GELU_BWD, w_mn=True, e_in=pre)
+    p32 = pre.float().requires_grad_(True)
+    F.gelu(p32).backward(dy.float() @ w.float())
+    _close(out, p32.grad, name="dh_pre")
+
+
+@pytest.mark.parametrize("T", SIZES)
+@pytest.mark.parametrize("N", [128, 512])
+def test_dw(T, N):
+    ops = _ops()
+    dy, x = _r(T, N), _r(T, 128)
+    dw = torch.ones(N, 128, device="cuda")
+    db = torch.ones(N, device="cuda")
+    ops.dw_tile(dy, x, dw, db)
+    _close(dw, dy.float().t() @ x.float() + 1, 2e-3, name="dw")
+    _close(db, dy.float().sum(0) + 1, 2e-3, name="db")
+    dw2 = torch.zeros(N, 128, device="cuda")
+    ops.dw_tile(dy, x, dw2, None)
+    _close(dw2, dy.float().t() @ x.float(), 2e-3, name="dw (no bias)")
+
+
+@pytest.mark.parametrize("T", [77, 5000])
+def test_ln_bwd(T):
+    ops = _ops()
+    z, dya, dyb = _r(T, 128), _r(T, 128), _r(T, 128)
+    dy32 = torch.randn(T, 128, device="cuda")
+    g = 1 + 0.1 * torch.randn(128, device="cuda")
+    zf = z.float().requires_grad_(True)
+    gg = g.clone().requires_grad_(True)
+    bb = torch.zeros(128, device="cuda", requires_grad=True)
+    F.layer_norm(zf, (128,), gg, bb, 1e-12).backward(dya.float() + dyb.float() + dy32)
+    dz = torch.empty_like(z)
+    dg, db = torch.zeros(128, device="cuda"), torch.zeros(128, device="cuda")
+    ops.ln_bwd(T, 128, z, g, 1e-12, 0.0, 0, 0, dz, dz, dg, db, dy_a=dya, dy_b=dyb, dy_f32=dy32)
+    _close(dz, zf.grad, name="dz")
+    _close(dg, gg.grad, 5e-3, "d_g")
+    _close(db, bb.grad, 5e-3, "d_b")
+
+
+def test_res_ln_dropout_matches_ln_bwd_mask():
+    """The RES_LN epilogue and pmgt_ln_bwd must regenerate the same Philox mask: with x = 0 and bias = 1 the
+    dense output is 1 everywhere, so z - res is 0 exactly where the forward dropped."""
+    ops = _ops()
+    T, p = 1000, 0.25
+    x, w = torch.zeros(T, 128, device="cuda", dtype=BF16), _r(128, 128)
+    b = torch.ones(128, device="cuda")
+    res = torch.zeros(T, 128, device="cuda", dtype=BF16)
+    g, be = torch.ones(128, device="cuda"), torch.zeros(128, device="cuda")
+    out, z = torch.empty(T, 128, device="cuda", dtype=BF16), torch.empty(T, 128, device="cuda", dtype=BF16)
+    ops.linear_tile(x, w, out, ops.LT_RES_LN, bias=b, aux_out=z, e_in=res, ln_g=g, ln_b=be, ln_eps=1e-12, p=p, seed=99, site=3)
+    dropped = z.float() == 0
+    rate = float(dropped.float().mean())
+    assert abs(rate - p) < 0.01, rate
+    assert torch.allclose(z.float()[~dropped], torch.tensor(1 / (1 - p), device="cuda"), rtol=1e-2)
+    dy = _r(T, 128)
+    dz, d_o = torch.empty_like(z), torch.empty_like(z)
+    ops.ln_bwd(T, 128, z, g, 1e-12, p, 99, 3, dz, d_o, torch.zeros(128, device="cuda"), torch.zeros(128, device="cuda"),
+               dy_a=dy)
+    assert bool((d_o.float()[dropped] == 0).all())
+    assert torch.allclose(d_o.float()[~dropped], (dz.float() / (1 - p))[~dropped], rtol=2e-2, atol=1e-3)

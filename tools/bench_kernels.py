@@ -93,7 +93,36 @@ def bench_gemm():
     timeit(lambda: ops.linear_dw(out, x, dw), T * H * 2 * 5, "gemm dw [512,T]x[T,128]")
 
 
-ALL = {"attn": bench_attn, "resln": bench_resln, "gemm": bench_gemm}
+def bench_tile(p=0.1):
+    x = r(T, H)
+    w4 = r(4 * H, H, s=0.05)
+    w = r(H, H, s=0.05)
+    b4 = torch.zeros(4 * H, device="cuda")
+    g = 1 + 0.1 * torch.randn(H, device="cuda")
+    be = 0.1 * torch.randn(H, device="cuda")
+    o4 = torch.empty(T, 4 * H, device="cuda", dtype=BF16)
+    o, o2, res = torch.empty(T, H, device="cuda", dtype=BF16), torch.empty(T, H, device="cuda", dtype=BF16), r(T, H)
+    B = T * H * 2
+    timeit(lambda: ops.linear_tile(x, w4, o4, ops.LT_BIAS, bias=b4), 5 * B, "tile qkvc fwd (BIAS N=512)")
+    timeit(lambda: ops.linear_tile(x, w, o, ops.LT_BIAS, bias=b4[:H]), 2 * B, "tile BIAS N=128")
+    timeit(lambda: ops.linear_tile(x, w, o, ops.LT_GELU, bias=b4[:H], aux_out=o2), 3 * B, "tile GELU")
+    timeit(lambda: ops.linear_tile(x, w, o, ops.LT_RES_LN, bias=b4[:H], aux_out=o2, e_in=res, ln_g=g, ln_b=be,
+                                   ln_eps=1e-12, p=p, seed=1, site=3), 4 * B, f"tile RES_LN p={p}")
+    timeit(lambda: ops.linear_tile(x, w, o, ops.LT_RES_LN, bias=b4[:H], aux_out=o2, e_in=res, ln_g=g, ln_b=be,
+                                   ln_eps=1e-12, p=0.0, seed=1, site=3), 4 * B, "tile RES_LN p=0")
+    timeit(lambda: ops.linear_tile(x, w, o, ops.LT_PLAIN, w_mn=True), 2 * B, "tile dX K=128")
+    timeit(lambda: ops.linear_tile(o4, w4, o, ops.LT_PLAIN, w_mn=True), 5 * B, "tile dX K=512")
+    timeit(lambda: ops.linear_tile(x, w, o, ops.LT_GELU_BWD, w_mn=True, e_in=res), 3 * B, "tile GELU_BWD")
+    dw4, db4 = torch.zeros(4 * H, H, device="cuda"), torch.zeros(4 * H, device="cuda")
+    timeit(lambda: ops.dw_tile(o4, x, dw4, db4), 5 * B, "tile dW N=512 + dbias")
+    timeit(lambda: ops.dw_tile(res, x, dw4[:H], db4[:H]), 2 * B, "tile dW N=128 + dbias")
+    dz, do = torch.empty_like(o), torch.empty_like(o)
+    dg, db = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
+    timeit(lambda: ops.ln_bwd(T, H, res, g, 1e-12, p, 1, 3, dz, do, dg, db, dy_a=x, dy_b=o), 5 * B, f"ln_bwd p={p} (2 dy)")
+    timeit(lambda: ops.ln_bwd(T, H, res, g, 1e-12, 0.0, 1, 3, dz, dz, dg, db, dy_a=x), 3 * B, "ln_bwd p=0 (1 dy)")
+
+
+ALL = {"tile": bench_tile, "attn": bench_attn, "resln": bench_resln, "gemm": bench_gemm}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(ALL)
