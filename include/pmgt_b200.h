@@ -39,7 +39,7 @@ typedef enum pmgt_status {
 } pmgt_status;
 
 /* ABI version of this header; bumped on any signature change. */
-#define PMGT_B200_ABI_VERSION 1
+#define PMGT_B200_ABI_VERSION 2
 int pmgt_abi_version(void);
 const char* pmgt_last_error(void);
 
@@ -196,6 +196,7 @@ typedef struct pmgt_embed_args {
   uint16_t* dev; uint16_t* det;
   float* d_w_att; float* d_b_att; float* d_pos; float* d_role; float* d_ln_g; float* d_ln_b;
   float* d_bias_v; float* d_bias_t;
+  const uint16_t* dx_b;       /* bwd, optional: second gradient term, summed with dx */
 } pmgt_embed_args;
 
 int pmgt_embed_fuse_fwd(const pmgt_embed_args* a, void* stream);

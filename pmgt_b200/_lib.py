@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmgt_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 
@@ -55,6 +55,7 @@ class EmbedArgs(C.Structure):
         ("d_w_att", c_vp), ("d_b_att", c_vp), ("d_pos", c_vp), ("d_role", c_vp),
         ("d_ln_g", c_vp), ("d_ln_b", c_vp),
         ("d_bias_v", c_vp), ("d_bias_t", c_vp),
+        ("dx_b", c_vp),
     ]
 
 

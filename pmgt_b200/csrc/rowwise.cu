@@ -206,6 +206,14 @@ __global__ void __launch_bounds__(kRowThreads) embed_fuse_bwd_kernel(const pmgt_
       float a0, a1, mean, rstd;
       embed_forward_row<G>(a, tok, l, lane, ev, et, tv, tt, z, a0, a1, mean, rstd);
       load_row_bf16<G>(a.dx + tok * H, H, lane, dy);
+      if (a.dx_b) {
+        RowRegs<G> e;
+        load_row_bf16<G>(a.dx_b + tok * H, H, lane, e);
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dy.v[i][j] += e.v[i][j];
+      }
       // LayerNorm backward
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll

@@ -301,7 +301,16 @@ def encoder_param_order(bert: "PMGTModel", prefix: str = "") -> List[Tuple[str, 
 class _EncoderRun:
     """Activations of one encoder pass kept for the backward pass."""
     __slots__ = ("R", "L", "T", "mask", "rows_idx", "src", "src_rows", "ev", "et", "x0", "layers", "seed", "p_hid",
-                 "p_att", "hidden_f32")
+                 "p_att", "hidden_f32", "tile")
+
+
+def _tile_path(H: int, I: int) -> bool:
+    """The persistent token-tile kernels cover the default encoder (H = I = 128); other sizes use pmgt_gemm_bf16."""
+    return (ops.linear_tile_supported(H, 4 * H, False, ops.LT_BIAS) and ops.linear_tile_supported(H, H, False, ops.LT_RES_LN)
+            and ops.linear_tile_supported(H, I, False, ops.LT_GELU) and ops.linear_tile_supported(I, H, False, ops.LT_RES_LN)
+            and ops.linear_tile_supported(4 * H, H, True, ops.LT_PLAIN) and ops.linear_tile_supported(I, H, True, ops.LT_PLAIN)
+            and ops.linear_tile_supported(H, I, True, ops.LT_GELU_BWD) and ops.dw_tile_supported(4 * H, H)
+            and ops.dw_tile_supported(H, I) and ops.dw_tile_supported(I, H) and H == 128)
 
 
 def _encode_forward(fp: FlatParams, pre: str, cfg: PMGTConfig, src: List[torch.Tensor], rows_idx, R: int, L: int,
@@ -346,7 +355,36 @@ def _encode_forward(fp: FlatParams, pre: str, cfg: PMGTConfig, src: List[torch.T
 
     n_layers = cfg.num_hidden_layers
     hidden_f32 = new(T, H, dtype=torch.float32)
-    for i in range(n_layers):
+    tile = _tile_path(H, I)
+    if keep:
+        run.tile = tile
+    for i in range(n_layers if tile else 0):
+        # ---- fast path: persistent tcgen05 token-tile kernels, element-wise work fused into the epilogues
+        P = f"{pre}encoder.layer.{i}."
+        site = 10 * (i + 1)
+        last = i == n_layers - 1
+        qkvc = new(T, 4 * H)
+        ops.linear_tile(x, fp.bf16(P + "attention.self.query.weight", 4), qkvc, ops.LT_BIAS,
+                        bias=fp.f32(P + "attention.self.query.bias", 4), tag="lt_qkvc_fwd")
+        ctx = new(T, H)
+        ops.attn_core_fwd(ops.attn_args(R, L, H, heads, float(cfg.beta), qkvc, mask, p_att, seed, site, ctx=ctx))
+        a, z1 = new(T, H), new(T, H)
+        ops.linear_tile(ctx, fp.bf16(P + "attention.output.dense.weight"), a, ops.LT_RES_LN,
+                        bias=fp.f32(P + "attention.output.dense.bias"), aux_out=z1, e_in=x,
+                        ln_g=fp.f32(P + "attention.output.LayerNorm.weight"), ln_b=fp.f32(P + "attention.output.LayerNorm.bias"),
+                        ln_eps=cfg.layer_norm_eps, p=p_hid, seed=seed, site=site + 3, tag="lt_res_ln_fwd")
+        h_pre, h = new(T, I), new(T, I)
+        ops.linear_tile(a, fp.bf16(P + "intermediate.dense.weight"), h, ops.LT_GELU,
+                        bias=fp.f32(P + "intermediate.dense.bias"), aux_out=h_pre, tag="lt_gelu_fwd")
+        y, z2 = new(T, H), new(T, H)
+        ops.linear_tile(h, fp.bf16(P + "output.dense.weight"), y, ops.LT_RES_LN, bias=fp.f32(P + "output.dense.bias"),
+                        aux_out=z2, e_in=a, ln_g=fp.f32(P + "output.LayerNorm.weight"),
+                        ln_b=fp.f32(P + "output.LayerNorm.bias"), ln_eps=cfg.layer_norm_eps, p=p_hid, seed=seed,
+                        site=site + 4, out_f32=(hidden_f32 if last else None), tag="lt_res_ln_fwd")
+        if keep:
+            run.layers.append((x, qkvc, ctx, z1, a, h_pre, h, z2))
+        x = y
+    for i in range(0 if tile else n_layers):
         P = f"{pre}encoder.layer.{i}."
         site = 10 * (i + 1)
         qkvc = new(T, 4 * H)
@@ -392,7 +430,43 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
     G = arena.view
     dy_f32 = d_hidden.contiguous().view(T, H)
     dy = None
-    for i in reversed(range(cfg.num_hidden_layers)):
+    dy_b = None  # second gradient term of the layer input (the LayerNorm residual branch), tile path only
+    for i in reversed(range(cfg.num_hidden_layers if run.tile else 0)):
+        P = f"{pre}encoder.layer.{i}."
+        site = 10 * (i + 1)
+        x, qkvc, ctx, z1, a, h_pre, h, z2 = run.layers[i]
+        # ---- BertOutput: LayerNorm(dropout(dense(h)) + a)
+        dz2 = new(T, H)
+        do2 = new(T, H) if p_hid > 0 else dz2
+        ops.ln_bwd(T, H, z2, fp.f32(P + "output.LayerNorm.weight"), cfg.layer_norm_eps, p_hid, seed, site + 4, dz2, do2,
+                   G(P + "output.LayerNorm.weight"), G(P + "output.LayerNorm.bias"), dy_a=dy, dy_b=dy_b, dy_f32=dy_f32)
+        dy_f32 = None
+        ops.dw_tile(do2, h, G(P + "output.dense.weight"), G(P + "output.dense.bias"))
+        dh_pre = new(T, I)
+        ops.linear_tile(do2, fp.bf16(P + "output.dense.weight"), dh_pre, ops.LT_GELU_BWD, w_mn=True, e_in=h_pre,
+                        tag="lt_dx_gelu")
+        # ---- BertIntermediate
+        ops.dw_tile(dh_pre, a, G(P + "intermediate.dense.weight"), G(P + "intermediate.dense.bias"))
+        da = new(T, H)
+        ops.linear_tile(dh_pre, fp.bf16(P + "intermediate.dense.weight"), da, ops.LT_PLAIN, w_mn=True, tag="lt_dx")
+        # ---- BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x); d a = da (FFN branch) + dz2 (residual branch)
+        dz1 = new(T, H)
+        do1 = new(T, H) if p_hid > 0 else dz1
+        ops.ln_bwd(T, H, z1, fp.f32(P + "attention.output.LayerNorm.weight"), cfg.layer_norm_eps, p_hid, seed, site + 3,
+                   dz1, do1, G(P + "attention.output.LayerNorm.weight"), G(P + "attention.output.LayerNorm.bias"),
+                   dy_a=da, dy_b=dz2)
+        ops.dw_tile(do1, ctx, G(P + "attention.output.dense.weight"), G(P + "attention.output.dense.bias"))
+        dctx = new(T, H)
+        ops.linear_tile(do1, fp.bf16(P + "attention.output.dense.weight"), dctx, ops.LT_PLAIN, w_mn=True, tag="lt_dx")
+        # ---- dual-softmax attention core, then the fused Q/K/V/C projection
+        dqkvc = new(T, 4 * H)
+        ops.attn_core_bwd(ops.attn_args(R, L, H, heads, float(cfg.beta), qkvc, run.mask, p_att, seed, site, dctx=dctx,
+                                        dqkvc=dqkvc))
+        ops.dw_tile(dqkvc, x, G(P + "attention.self.query.weight", 4), G(P + "attention.self.query.bias", 4))
+        dx = new(T, H)
+        ops.linear_tile(dqkvc, fp.bf16(P + "attention.self.query.weight", 4), dx, ops.LT_PLAIN, w_mn=True, tag="lt_dx_qkvc")
+        dy, dy_b = dx, dz1  # d x = dx (projection branch) + dz1 (residual branch): summed by the consumer
+    for i in reversed(range(0 if run.tile else cfg.num_hidden_layers)):
         P = f"{pre}encoder.layer.{i}."
         site = 10 * (i + 1)
         x, qkvc, ctx, o1, a, h_pre, h, o2 = run.layers[i]
@@ -433,13 +507,14 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
         dy = dx
     if dy is None:  # zero layers
         dy = dy_f32.to(BF16)
+        dy_b = None
     # ---- embeddings
     E = pre + "embeddings."
     dev_, det_ = new(T, H), new(T, H)
     ea = ops.embed_args(R, L, H, run.ev, run.et, fp.f32(E + "attention.1.weight"), fp.f32(E + "attention.1.bias"),
                         fp.f32(E + "position_embeddings.weight"), fp.f32(E + "role_embeddings.weight"),
                         fp.f32(E + "LayerNorm.weight"), fp.f32(E + "LayerNorm.bias"), cfg.layer_norm_eps, p_hid, seed, 0,
-                        dx=dy, dev=dev_, det=det_, d_w_att=G(E + "attention.1.weight"), d_b_att=G(E + "attention.1.bias"),
+                        dx=dy, dx_b=dy_b, dev=dev_, det=det_, d_w_att=G(E + "attention.1.weight"), d_b_att=G(E + "attention.1.bias"),
                         d_pos=G(E + "position_embeddings.weight"), d_role=G(E + "role_embeddings.weight"),
                         d_ln_g=G(E + "LayerNorm.weight"), d_ln_b=G(E + "LayerNorm.bias"),
                         d_bias_v=G(E + "feat_linear.0.bias"), d_bias_t=G(E + "feat_linear.1.bias"))
