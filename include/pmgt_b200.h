@@ -197,6 +197,11 @@ typedef struct pmgt_embed_args {
   float* d_w_att; float* d_b_att; float* d_pos; float* d_role; float* d_ln_g; float* d_ln_b;
   float* d_bias_v; float* d_bias_t;
   const uint16_t* dx_b;       /* bwd, optional: second gradient term, summed with dx */
+  /* Projected-table mode (small graphs: project every table row once, gather the PROJECTED rows): when
+   * `row_idx` != NULL, ev / et are [table_rows][H] and token t reads row row_idx[t]; backward then accumulates the
+   * per-row gradients into dev_acc / det_acc ([table_rows][H] fp32, red.add) instead of writing dev / det.
+   * skip_row0: row 0 (<pad>) of the feature tables is all zero, so its gradient rows are never used. */
+  const int64_t* row_idx; float* dev_acc; float* det_acc; int skip_row0;
 } pmgt_embed_args;
 
 int pmgt_embed_fuse_fwd(const pmgt_embed_args* a, void* stream);

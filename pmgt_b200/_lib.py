@@ -56,6 +56,7 @@ class EmbedArgs(C.Structure):
         ("d_ln_g", c_vp), ("d_ln_b", c_vp),
         ("d_bias_v", c_vp), ("d_bias_t", c_vp),
         ("dx_b", c_vp),
+        ("row_idx", c_vp), ("dev_acc", c_vp), ("det_acc", c_vp), ("skip_row0", C.c_int),
     ]
 
 

@@ -103,8 +103,9 @@ __device__ __forceinline__ void embed_forward_row(const pmgt_embed_args& a, long
                                                   RowRegs<G>& ev, RowRegs<G>& et, RowRegs<G>& tv, RowRegs<G>& tt,
                                                   RowRegs<G>& z, float& a0, float& a1, float& mean, float& rstd) {
   const int H = a.H;
-  load_row_bf16<G>(a.ev + tok * H, H, lane, ev);
-  load_row_bf16<G>(a.et + tok * H, H, lane, et);
+  const long long er = a.row_idx ? a.row_idx[tok] : tok;
+  load_row_bf16<G>(a.ev + er * H, H, lane, ev);
+  load_row_bf16<G>(a.et + er * H, H, lane, et);
   float s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int i = 0; i < G; ++i) {
@@ -294,8 +295,24 @@ __global__ void __launch_bounds__(kRowThreads) embed_fuse_bwd_kernel(const pmgt_
           det.v[i][0] = det.v[i][1] = det.v[i][2] = det.v[i][3] = 0.f;
         }
       }
-      store_row_bf16<G>(a.dev + tok * H, H, lane, dev);
-      store_row_bf16<G>(a.det + tok * H, H, lane, det);
+      if (a.row_idx) {
+        const long long er = a.row_idx[tok];
+        if (!(a.skip_row0 && er == 0)) {
+#pragma unroll
+          for (int i = 0; i < G; ++i) {
+            const int h = (lane + 32 * i) * 4;
+            if (h < H) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.dev_acc + er * H + h), "f"(dev.v[i][0]),
+                           "f"(dev.v[i][1]), "f"(dev.v[i][2]), "f"(dev.v[i][3]) : "memory");
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.det_acc + er * H + h), "f"(det.v[i][0]),
+                           "f"(det.v[i][1]), "f"(det.v[i][2]), "f"(det.v[i][3]) : "memory");
+            }
+          }
+        }
+      } else {
+        store_row_bf16<G>(a.dev + tok * H, H, lane, dev);
+        store_row_bf16<G>(a.det + tok * H, H, lane, det);
+      }
     }
     // flush position / role gradient of this l
     __syncwarp();
@@ -747,7 +764,7 @@ int pmgt_embed_fuse_fwd(const pmgt_embed_args* a, void* stream) {
 
 int pmgt_embed_fuse_bwd(const pmgt_embed_args* a, void* stream) {
   PMGT_REQUIRE(a && a->ev && a->et && a->w_att && a->b_att && a->pos && a->role && a->ln_g && a->ln_b && a->dx &&
-                   a->dev && a->det && a->d_w_att && a->d_b_att && a->d_pos && a->d_role && a->d_ln_g && a->d_ln_b &&
+                   (a->row_idx ? (a->dev_acc && a->det_acc) : (a->dev && a->det)) && a->d_w_att && a->d_b_att && a->d_pos && a->d_role && a->d_ln_g && a->d_ln_b &&
                    a->d_bias_v && a->d_bias_t,
                "pmgt_embed_fuse_bwd: null argument");
   PMGT_REQUIRE(a->H % 4 == 0 && a->H >= 4 && a->H <= 1024, "pmgt_embed_fuse_bwd: H must be a multiple of 4 in [4,1024]");

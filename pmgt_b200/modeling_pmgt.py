@@ -301,7 +301,11 @@ def encoder_param_order(bert: "PMGTModel", prefix: str = "") -> List[Tuple[str, 
 class _EncoderRun:
     """Activations of one encoder pass kept for the backward pass."""
     __slots__ = ("R", "L", "T", "mask", "rows_idx", "src", "src_rows", "ev", "et", "x0", "layers", "seed", "p_hid",
-                 "p_att", "hidden_f32", "tile")
+                 "p_att", "hidden_f32", "tile", "dense_tables")
+
+
+# "auto": projected tables when 4 * table rows <= tokens, else the gather-fused GEMM; "table" / "gather" force a mode
+PROJECTION_MODE = "auto"
 
 
 def _tile_path(H: int, I: int) -> bool:
@@ -331,18 +335,29 @@ def _encode_forward(fp: FlatParams, pre: str, cfg: PMGTConfig, src: List[torch.T
     def new(*shape, dtype=BF16):
         return torch.empty(shape, dtype=dtype, device=dev)
 
-    # K2: (gathered) per-modality projections on tensor cores, then the fusion kernel
+    # K2: per-modality projections on tensor cores, then the fusion kernel.  Two modes:
+    #  * gather-fused GEMM: rows of the feature tables are fetched inside the GEMM, one projection per TOKEN
+    #    (large graphs: most table rows are never touched in a step);
+    #  * projected tables: when the tables are small next to the token count (VG / TG: ~10^4 rows vs 3*10^5
+    #    tokens) every table row is projected ONCE and tokens gather the projected H-vectors instead.
+    dense_tables = rows_idx is not None and (PROJECTION_MODE == "table" or
+                                             (PROJECTION_MODE == "auto" and 4 * src[0].shape[0] <= T))
     proj = []
     for m in range(2):
-        out = new(T, H)
-        ops.linear_fwd(src[m], fp.bf16(f"{E}feat_linear.{m}.weight"), fp.f32(f"{E}feat_linear.{m}.bias"), out,
-                       rows=rows_idx, src_rows=(src[m].shape[0] if rows_idx is not None else 0))
+        if dense_tables:
+            out = new(src[m].shape[0], H)
+            ops.linear_fwd(src[m], fp.bf16(f"{E}feat_linear.{m}.weight"), fp.f32(f"{E}feat_linear.{m}.bias"), out,
+                           tag="gemm_fwd_table")
+        else:
+            out = new(T, H)
+            ops.linear_fwd(src[m], fp.bf16(f"{E}feat_linear.{m}.weight"), fp.f32(f"{E}feat_linear.{m}.bias"), out,
+                           rows=rows_idx, src_rows=(src[m].shape[0] if rows_idx is not None else 0))
         proj.append(out)
     x = new(T, H)
     ea = ops.embed_args(R, L, H, proj[0], proj[1], fp.f32(E + "attention.1.weight"), fp.f32(E + "attention.1.bias"),
                         fp.f32(E + "position_embeddings.weight"), fp.f32(E + "role_embeddings.weight"),
                         fp.f32(E + "LayerNorm.weight"), fp.f32(E + "LayerNorm.bias"), cfg.layer_norm_eps, p_hid, seed, 0,
-                        x_out=x)
+                        x_out=x, row_idx=(rows_idx if dense_tables else None))
     ops.embed_fuse_fwd(ea)
 
     run = None
@@ -352,6 +367,7 @@ def _encode_forward(fp: FlatParams, pre: str, cfg: PMGTConfig, src: List[torch.T
         run.src, run.src_rows = src, [s.shape[0] for s in src]
         run.ev, run.et, run.x0, run.layers = proj[0], proj[1], x, []
         run.seed, run.p_hid, run.p_att = seed, p_hid, p_att
+        run.dense_tables = dense_tables
 
     n_layers = cfg.num_hidden_layers
     hidden_f32 = new(T, H, dtype=torch.float32)
@@ -510,18 +526,29 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
         dy_b = None
     # ---- embeddings
     E = pre + "embeddings."
-    dev_, det_ = new(T, H), new(T, H)
-    ea = ops.embed_args(R, L, H, run.ev, run.et, fp.f32(E + "attention.1.weight"), fp.f32(E + "attention.1.bias"),
-                        fp.f32(E + "position_embeddings.weight"), fp.f32(E + "role_embeddings.weight"),
-                        fp.f32(E + "LayerNorm.weight"), fp.f32(E + "LayerNorm.bias"), cfg.layer_norm_eps, p_hid, seed, 0,
-                        dx=dy, dx_b=dy_b, dev=dev_, det=det_, d_w_att=G(E + "attention.1.weight"), d_b_att=G(E + "attention.1.bias"),
-                        d_pos=G(E + "position_embeddings.weight"), d_role=G(E + "role_embeddings.weight"),
-                        d_ln_g=G(E + "LayerNorm.weight"), d_ln_b=G(E + "LayerNorm.bias"),
-                        d_bias_v=G(E + "feat_linear.0.bias"), d_bias_t=G(E + "feat_linear.1.bias"))
-    ops.embed_fuse_bwd(ea)
-    for m, d in enumerate((dev_, det_)):
-        ops.linear_dw(d, run.src[m], G(f"{E}feat_linear.{m}.weight"), rows=run.rows_idx,
-                      src_rows=(run.src_rows[m] if run.rows_idx is not None else 0), x_cols=run.src[m].shape[1])
+    common = dict(dx=dy, dx_b=dy_b, d_w_att=G(E + "attention.1.weight"), d_b_att=G(E + "attention.1.bias"),
+                  d_pos=G(E + "position_embeddings.weight"), d_role=G(E + "role_embeddings.weight"),
+                  d_ln_g=G(E + "LayerNorm.weight"), d_ln_b=G(E + "LayerNorm.bias"),
+                  d_bias_v=G(E + "feat_linear.0.bias"), d_bias_t=G(E + "feat_linear.1.bias"))
+    eargs = (R, L, H, run.ev, run.et, fp.f32(E + "attention.1.weight"), fp.f32(E + "attention.1.bias"),
+             fp.f32(E + "position_embeddings.weight"), fp.f32(E + "role_embeddings.weight"),
+             fp.f32(E + "LayerNorm.weight"), fp.f32(E + "LayerNorm.bias"), cfg.layer_norm_eps, p_hid, seed, 0)
+    if run.dense_tables:
+        # per-table-row gradient of the projected rows (fp32 red.add), then ONE dense dW GEMM per modality
+        accs = [torch.zeros(n, H, dtype=torch.float32, device=dev) for n in run.src_rows]
+        skip0 = int(all(getattr(t, "_pmgt_row0_zero", False) for t in run.src))
+        ops.embed_fuse_bwd(ops.embed_args(*eargs, row_idx=run.rows_idx, dev_acc=accs[0], det_acc=accs[1], skip_row0=skip0,
+                                          **common))
+        for m in range(2):
+            d16 = new(run.src_rows[m], H)
+            ops.cast_f32_bf16(accs[m].view(-1), d16.view(-1))
+            ops.linear_dw(d16, run.src[m], G(f"{E}feat_linear.{m}.weight"), tag="gemm_dw_table")
+    else:
+        dev_, det_ = new(T, H), new(T, H)
+        ops.embed_fuse_bwd(ops.embed_args(*eargs, dev=dev_, det=det_, **common))
+        for m, d in enumerate((dev_, det_)):
+            ops.linear_dw(d, run.src[m], G(f"{E}feat_linear.{m}.weight"), rows=run.rows_idx,
+                          src_rows=(run.src_rows[m] if run.rows_idx is not None else 0), x_cols=run.src[m].shape[1])
 
 
 class _EncodeFn(torch.autograd.Function):

@@ -119,7 +119,10 @@ class PMGT(PMGTPretrainedModel):
                 w = e.weight.data
                 if not w.is_cuda:
                     raise PMGTError("PMGT must be moved to a CUDA device before forward (no CPU fallback)")
-                out.append(w if w.dtype == BF16 else w.to(BF16).contiguous())
+                t = w if w.dtype == BF16 else w.to(BF16).contiguous()
+                # <pad> row all zero (the reference's tables, notebook cell 30): its gradient rows are never needed
+                t._pmgt_row0_zero = bool((t[0] == 0).all())
+                out.append(t)
             self._tables_bf16, self._tables_key = out, key
         return self._tables_bf16
 

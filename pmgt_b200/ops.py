@@ -186,7 +186,7 @@ def embed_args(rows, L, H, ev, et, w_att, b_att, pos, role, ln_g, ln_b, eps, p, 
     a.w_att, a.b_att, a.pos, a.role, a.ln_g, a.ln_b = ptr(w_att), ptr(b_att), ptr(pos), ptr(role), ptr(ln_g), ptr(ln_b)
     a.ln_eps, a.dropout_p, a.dropout_seed, a.dropout_site = eps, p, seed, site
     for k, v in kw.items():
-        setattr(a, k, ptr(v))
+        setattr(a, k, v if isinstance(v, (int, bool)) else ptr(v))
     return a
 
 

@@ -104,7 +104,10 @@ def test_pretrain_step_matches_reference_golden(golden_dir, name):
     (dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
           feat_hidden_sizes=[256, 128], mask_node_ratio=0.3), 8, 4, 33, 120),                     # wide-style: L = 33
 ])
-def test_pretrain_step_matches_oracle_on_device(over, B, P, L, node_size):
+@pytest.mark.parametrize("projection", ["gather", "table"])
+def test_pretrain_step_matches_oracle_on_device(over, B, P, L, node_size, projection, monkeypatch):
+    from pmgt_b200 import modeling_pmgt
+    monkeypatch.setattr(modeling_pmgt, "PROJECTION_MODE", projection)
     cfg = model_ref.default_cfg(**over)
     sd = model_ref.init_state_dict(cfg, node_size, seed=21, perturb=0.05)
     net = _build(cfg, node_size, sd)
