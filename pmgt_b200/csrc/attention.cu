@@ -304,6 +304,8 @@ static int attn_launch_cfg(const pmgt_attn_args* a, bool bwd, AttnSmemLayout& la
 
 int attn_small_fwd(const pmgt_attn_args* a, cudaStream_t st);  // attention_small.cu
 int attn_small_bwd(const pmgt_attn_args* a, cudaStream_t st);
+int attn_mma_fwd(const pmgt_attn_args* a, cudaStream_t st);    // attention_mma.cu
+int attn_mma_bwd(const pmgt_attn_args* a, cudaStream_t st);
 
 }  // namespace pmgt
 
@@ -316,7 +318,8 @@ int pmgt_attn_core_fwd(const pmgt_attn_args* a, void* stream) {
   if (a->rows == 0) return PMGT_OK;
   PMGT_REQUIRE(a->heads >= 1 && a->H % a->heads == 0, "attention: H must be divisible by heads");
   {  // register-resident kernel for the short-sequence shapes (default PMGT: L = 6, dh = 128)
-    const int r = attn_small_fwd(a, (cudaStream_t)stream);
+    int r = attn_mma_fwd(a, (cudaStream_t)stream);
+    if (r == 0) r = attn_small_fwd(a, (cudaStream_t)stream);
     if (r < 0) return r;
     if (r > 0) return PMGT_OK;
   }
@@ -338,7 +341,8 @@ int pmgt_attn_core_bwd(const pmgt_attn_args* a, void* stream) {
   PMGT_REQUIRE(a && a->qkvc && a->mask && a->dctx && a->dqkvc, "pmgt_attn_core_bwd: null argument");
   if (a->rows == 0) return PMGT_OK;
   PMGT_REQUIRE(a->heads >= 1 && a->H % a->heads == 0, "attention: H must be divisible by heads");
-  int rc = attn_small_bwd(a, (cudaStream_t)stream);
+  int rc = attn_mma_bwd(a, (cudaStream_t)stream);
+  if (rc == 0) rc = attn_small_bwd(a, (cudaStream_t)stream);
   if (rc < 0) return rc;
   if (rc == 0) {
     AttnSmemLayout lay; int warps; size_t smem;

@@ -185,6 +185,9 @@ class PMGT(PMGTPretrainedModel):
                 m_ids, m_mask, target_idx = masked_inputs
                 ids.append(m_ids)
                 masks.append(t_mask)
+                # data-dependent shapes are resolved HERE, before the encoder is enqueued: nonzero() synchronises
+                # the stream, and a sync after the encoder launch would drain the whole launch pipeline
+                m_pos = m_mask.nonzero(as_tuple=False)  # (Mm, 2): row, position-1
         ids_all = ids[0] if len(ids) == 1 else torch.cat(ids, dim=0)
         mask_all = masks[0] if len(masks) == 1 else torch.cat(masks, dim=0)
         R = ids_all.shape[0]
@@ -200,8 +203,7 @@ class PMGT(PMGTPretrainedModel):
             # tokens the losses read: position 0 of targets and pairs, masked positions of the masked rows
             tok = [torch.arange(0, (B + SP) * L, L, device=dev)]
             if nfr_on:
-                pos = m_mask.nonzero(as_tuple=False)  # (Mm, 2): row, position-1
-                tok.append((B + SP + pos[:, 0]) * L + pos[:, 1] + 1)
+                tok.append((B + SP + m_pos[:, 0]) * L + m_pos[:, 1] + 1)
             rows = _TakeRows.apply(hidden.view(R * L, H), torch.cat(tok) if len(tok) > 1 else tok[0])
             pair_off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
             torch.cumsum(num_pairs.to(dev), 0, out=pair_off[1:])
