@@ -61,40 +61,35 @@ __device__ __forceinline__ float quad_max(float v) {
   return v;
 }
 
-// keep bits of elements base_idx .. base_idx + LL - 1 (LL <= 60) for dropout sites `site` (k1) and `site + 1` (k2):
-// lanes 0..NB-1 run the Philox blocks of the first site, lanes 16..16+NB-1 those of the second, then an OR
-// reduction within each half-warp (same stream as common.cuh:dropout_keep).
+// keep bits of elements base_idx .. base_idx + LL - 1 (LL <= 64) for dropout sites `site` (k1) and `site + 1`
+// (k2): lanes 0..NB-1 run the Philox blocks (8 elements each) of the first site, lanes 16..16+NB-1 those of the
+// second, then an OR reduction within each half-warp (stream of common.cuh).
 template <int LL>
 __device__ __forceinline__ void warp_dropout_bits2(uint64_t seed, uint32_t site, uint64_t base_idx, float p, int lane,
                                                    uint64_t& k1, uint64_t& k2) {
-  constexpr int NB = (LL + 3) / 4 + 1;
+  constexpr int NB = (LL + 7) / 8 + 1;
   static_assert(NB <= 16, "one Philox block per lane of a half-warp");
-  const uint64_t b0 = base_idx >> 2;
+  const uint64_t b0 = base_idx & ~(uint64_t)7;
   const int hl = lane & 15;
-  uint32_t lo = 0, hi = 0;
-  if (hl < NB) {
-    const uint64_t blk = b0 + (uint64_t)hl;
-    const Philox4 r = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), site + (uint32_t)(lane >> 4), 0x5eedu,
-                                    (uint32_t)seed, (uint32_t)(seed >> 32));
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const long long e = (long long)(blk * 4 + (uint64_t)w) - (long long)base_idx;
-      if (e >= 0 && e < LL) {
-        const float u = (float)(philox_word(r, w) >> 8) * (1.0f / 16777216.0f);
-        if (u >= p) {
-          if (e < 32) lo |= 1u << e;
-          else hi |= 1u << (e - 32);
-        }
-      }
-    }
+  uint64_t bits = 0;
+  const uint64_t i8 = b0 + 8ull * hl;
+  if (hl < NB && i8 < base_idx + LL) {
+    const uint64_t m = dropout_keep8(seed, site + (uint32_t)(lane >> 4), i8, p);
+    const long long sh = (long long)i8 - (long long)base_idx;
+    bits = sh >= 0 ? (m << sh) : (m >> (-sh));
   }
+  uint32_t lo = (uint32_t)bits, hi = (uint32_t)(bits >> 32);
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) {
     lo |= __shfl_xor_sync(0xffffffffu, lo, o);
     hi |= __shfl_xor_sync(0xffffffffu, hi, o);
   }
   const uint32_t lo2 = __shfl_xor_sync(0xffffffffu, lo, 16), hi2 = __shfl_xor_sync(0xffffffffu, hi, 16);
-  const uint64_t mine = ((uint64_t)hi << 32) | lo, other = ((uint64_t)hi2 << 32) | lo2;
+  uint64_t mine = ((uint64_t)hi << 32) | lo, other = ((uint64_t)hi2 << 32) | lo2;
+  if (LL < 64) {
+    mine &= (1ull << (LL & 63)) - 1ull;
+    other &= (1ull << (LL & 63)) - 1ull;
+  }
   k1 = (lane < 16) ? mine : other;
   k2 = (lane < 16) ? other : mine;
 }

@@ -71,35 +71,29 @@ __device__ __forceinline__ void store_row(uint16_t* __restrict__ dst, int t, con
   for (int m = 0; m < NCH; ++m) *reinterpret_cast<uint4*>(dst + (m * G + t) * 8) = pack8(&f[m * 8]);
 }
 
-// keep-bit e of `bits` = dropout_keep(seed, site, base_idx + e, p) for e < LL (<= 64); the Philox blocks
-// are spread over the G lanes of the group and OR-reduced (same stream as common.cuh:dropout_keep).
+// keep-bit e of the result = dropout_keep(seed, site, base_idx + e, p) for e < LL (<= 64); the Philox blocks
+// (8 elements each) are spread over the G lanes of the group and OR-reduced (stream of common.cuh).
 template <int LL, int G>
 __device__ __forceinline__ uint64_t dropout_bits(uint64_t seed, uint32_t site, uint64_t base_idx, float p, int t) {
-  constexpr int NB = (LL + 3) / 4 + 1;
-  const uint64_t b0 = base_idx >> 2;
-  uint32_t lo = 0, hi = 0;
+  constexpr int NB = (LL + 7) / 8 + 1;
+  const uint64_t b0 = base_idx & ~(uint64_t)7;
+  uint64_t bits = 0;
   for (int bb = t; bb < NB; bb += G) {
-    const uint64_t blk = b0 + (uint64_t)bb;
-    const Philox4 r = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), site, 0x5eedu, (uint32_t)seed,
-                                    (uint32_t)(seed >> 32));
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const long long e = (long long)(blk * 4 + (uint64_t)w) - (long long)base_idx;
-      if (e >= 0 && e < LL) {
-        const float u = (float)(philox_word(r, w) >> 8) * (1.0f / 16777216.0f);
-        if (u >= p) {
-          if (e < 32) lo |= 1u << e;
-          else hi |= 1u << (e - 32);
-        }
-      }
+    const uint64_t i8 = b0 + 8ull * bb;
+    if (i8 < base_idx + LL) {
+      const uint64_t m = dropout_keep8(seed, site, i8, p);
+      const long long sh = (long long)i8 - (long long)base_idx;
+      bits |= sh >= 0 ? (m << sh) : (m >> (-sh));
     }
   }
+  uint32_t lo = (uint32_t)bits, hi = (uint32_t)(bits >> 32);
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) {
     lo |= __shfl_xor_sync(0xffffffffu, lo, o);
     hi |= __shfl_xor_sync(0xffffffffu, hi, o);
   }
-  return ((uint64_t)hi << 32) | lo;
+  bits = ((uint64_t)hi << 32) | lo;
+  return LL >= 64 ? bits : (bits & ((1ull << (LL & 63)) - 1ull));
 }
 
 // From the reduced raw products: probabilities of both branches (in place: s2 -> P2, p1 out),

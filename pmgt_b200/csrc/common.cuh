@@ -79,27 +79,34 @@ __host__ __device__ __forceinline__ uint32_t philox_word(const Philox4& p, int i
   return i == 0 ? p.x : (i == 1 ? p.y : (i == 2 ? p.z : p.w));
 }
 
-// dropout keep decision for element `idx` of dropout site `site`.
-// keep with probability 1-p; the caller scales kept values by 1/(1-p).
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint64_t idx, float p) {
-  Philox4 r = philox4x32_10((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), site, 0x5eedu,
-                            (uint32_t)seed, (uint32_t)(seed >> 32));
-  uint32_t wsel = philox_word(r, (int)(idx & 3));
-  float u = (float)(wsel >> 8) * (1.0f / 16777216.0f);
-  return u >= p;
+// Dropout stream.  One Philox4x32-10 call covers the 8 consecutive elements of block idx >> 3: counter
+// (block_lo, block_hi, site, 0x5eed), key = seed; element j = idx & 7 uses the 16-bit field j of the 128-bit
+// output (word j >> 1, half j & 1) and is KEPT when field >= round(p * 65536).  The caller scales kept values
+// by 1 / (1 - p).  Every kernel (forward and the backward pass that regenerates the mask) goes through these
+// helpers, so the masks agree by construction.
+__device__ __forceinline__ uint32_t dropout_threshold(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+
+// keep bits of the 8 elements idx8 .. idx8 + 7 (idx8 a multiple of 8): bit j = keep element idx8 + j
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t site, uint64_t idx8, float p) {
+  const uint64_t blk = idx8 >> 3;
+  const Philox4 r = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), site, 0x5eedu, (uint32_t)seed,
+                                  (uint32_t)(seed >> 32));
+  const uint32_t thr = dropout_threshold(p);
+  uint32_t m = 0;
+  m |= ((r.x & 0xffffu) >= thr) ? 1u : 0u;
+  m |= ((r.x >> 16) >= thr) ? 2u : 0u;
+  m |= ((r.y & 0xffffu) >= thr) ? 4u : 0u;
+  m |= ((r.y >> 16) >= thr) ? 8u : 0u;
+  m |= ((r.z & 0xffffu) >= thr) ? 16u : 0u;
+  m |= ((r.z >> 16) >= thr) ? 32u : 0u;
+  m |= ((r.w & 0xffffu) >= thr) ? 64u : 0u;
+  m |= ((r.w >> 16) >= thr) ? 128u : 0u;
+  return m;
 }
 
-// keep bits of the 4 consecutive elements idx4 .. idx4+3 (idx4 a multiple of 4): ONE Philox call, same
-// stream as dropout_keep (bit j = keep element idx4 + j).
-__device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint32_t site, uint64_t idx4, float p) {
-  const Philox4 r = philox4x32_10((uint32_t)(idx4 >> 2), (uint32_t)(idx4 >> 34), site, 0x5eedu, (uint32_t)seed,
-                                  (uint32_t)(seed >> 32));
-  uint32_t m = 0;
-  m |= ((float)(r.x >> 8) * (1.0f / 16777216.0f) >= p) ? 1u : 0u;
-  m |= ((float)(r.y >> 8) * (1.0f / 16777216.0f) >= p) ? 2u : 0u;
-  m |= ((float)(r.z >> 8) * (1.0f / 16777216.0f) >= p) ? 4u : 0u;
-  m |= ((float)(r.w >> 8) * (1.0f / 16777216.0f) >= p) ? 8u : 0u;
-  return m;
+// single element (row-wise kernels call it for 4 consecutive elements of one block; the Philox call is shared)
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint64_t idx, float p) {
+  return (dropout_keep8(seed, site, idx & ~(uint64_t)7, p) >> (uint32_t)(idx & 7)) & 1u;
 }
 
 // ---------------------------------------------------------------------------

@@ -259,13 +259,9 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             } else if (EPI == LT_RES_LN) {
               if (p.dropout_p > 0.f) {
                 const uint64_t idx = (uint64_t)tok * 128u + (uint64_t)(c0 + g * 8);
-                const uint32_t k0 = dropout_keep4(p.seed, p.site, idx, p.dropout_p);
-                const uint32_t k1 = dropout_keep4(p.seed, p.site, idx + 4, p.dropout_p);
+                const uint32_t k8 = dropout_keep8(p.seed, p.site, idx, p.dropout_p);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  v[j] = (k0 >> j) & 1u ? v[j] * ks : 0.f;
-                  v[4 + j] = (k1 >> j) & 1u ? v[4 + j] * ks : 0.f;
-                }
+                for (int j = 0; j < 8; ++j) v[j] = (k8 >> j) & 1u ? v[j] * ks : 0.f;
               }
               uint4* zp = reinterpret_cast<uint4*>(eimg + img_off(r, c8));
               const uint4 rs = *zp;

@@ -574,13 +574,9 @@ __global__ void __launch_bounds__(256) ln_bwd128_kernel(const pmgt_lnbwd_args a)
         if (sep_do) {
           if (a.dropout_p > 0.f) {
             const uint64_t idx = (uint64_t)tok[u] * H + c;
-            const uint32_t k0 = dropout_keep4(a.dropout_seed, a.dropout_site, idx, a.dropout_p);
-            const uint32_t k1 = dropout_keep4(a.dropout_seed, a.dropout_site, idx + 4, a.dropout_p);
+            const uint32_t k8 = dropout_keep8(a.dropout_seed, a.dropout_site, idx, a.dropout_p);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              dz[j] = (k0 >> j) & 1u ? dz[j] * ks : 0.f;
-              dz[4 + j] = (k1 >> j) & 1u ? dz[4 + j] * ks : 0.f;
-            }
+            for (int j = 0; j < 8; ++j) dz[j] = (k8 >> j) & 1u ? dz[j] * ks : 0.f;
           }
           *reinterpret_cast<uint4*>(a.d_o + tok[u] * H + c) = pack8_row(dz);
         }
