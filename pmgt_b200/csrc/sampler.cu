@@ -57,17 +57,23 @@ __device__ __forceinline__ int upper_bound_cdf(const float* __restrict__ cdf, in
   return lo < n ? lo : n - 1;
 }
 
+// SPT > 0: table_cap == SPT * 128 and max_ctx <= 8 -- the top-k keeps every thread's slots in registers, each warp
+// extracts its own max_ctx best without block barriers, and warp 0 merges the 4 * max_ctx finalists (one barrier
+// instead of two table scans and two barriers per output position).  SPT == 0: any table size / max_ctx.
+template <int SPT>
 __global__ void __launch_bounds__(kSamplerThreads)
 sample_contexts_kernel(const SamplerParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* list_a = reinterpret_cast<int32_t*>(smem_raw);
   int32_t* list_b = list_a + p.list_cap;
-  int32_t* tkeys = list_b + p.list_cap;
+  int32_t* tkeys = list_a + ((2 * p.list_cap + 3) & ~3);  // 16-byte aligned (vector clear)
   uint32_t* tscore = reinterpret_cast<uint32_t*>(tkeys + p.table_cap);
-  uint32_t* tfirst = tscore + p.table_cap;
+  uint32_t* tfirst = tscore + p.table_cap;  // holds 0xffffffff - (first appearance), so an empty table is all zero
   __shared__ unsigned long long red[kSamplerThreads / 32];
   __shared__ unsigned long long best_sh;
   __shared__ unsigned long long deg_sh;
+  __shared__ unsigned long long cand_k[32];
+  __shared__ int32_t cand_n[32];
 
   const int tid = threadIdx.x;
   const int L = p.max_ctx + 1;
@@ -78,8 +84,9 @@ sample_contexts_kernel(const SamplerParams p) {
     const uint64_t key = (uint64_t)p.keys[ctx];
     const uint32_t key_lo = (uint32_t)key, key_hi = (uint32_t)(key >> 32);
 
-    for (int i = tid; i < p.table_cap; i += kSamplerThreads) {
-      tkeys[i] = 0; tscore[i] = 0u; tfirst[i] = 0xffffffffu;
+    {  // keys, scores and first-appearance words are contiguous: one 16-byte-vector clear
+      uint4* t4 = reinterpret_cast<uint4*>(tkeys);
+      for (int i = tid; i < p.table_cap * 3 / 4; i += kSamplerThreads) t4[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) deg_sh = 0ull;
     __syncthreads();
@@ -126,7 +133,7 @@ sample_contexts_kernel(const SamplerParams p) {
               slot = (slot + 1) & (uint32_t)(p.table_cap - 1);
             }
             atomicAdd(&tscore[slot], hop_w);
-            atomicMin(&tfirst[slot], gd);
+            atomicMax(&tfirst[slot], 0xffffffffu - gd);
           }
         }
       }
@@ -147,12 +154,60 @@ sample_contexts_kernel(const SamplerParams p) {
       p.out_ids[ctx * L] = root64;
       p.out_mask[ctx * L] = 1.0f;
     }
+    if constexpr (SPT > 0) {
+      unsigned long long mk[SPT];
+      int32_t mn[SPT];
+#pragma unroll
+      for (int s2 = 0; s2 < SPT; ++s2) {
+        const int i = tid + s2 * kSamplerThreads;
+        mn[s2] = tkeys[i];
+        mk[s2] = mn[s2] != 0 ? (((unsigned long long)tscore[i] << 32) | (unsigned long long)tfirst[i]) : 0ull;
+      }
+      const int lane = tid & 31, wrp = tid >> 5;
+      for (int r = 0; r < p.max_ctx; ++r) {
+        unsigned long long lb = 0ull;
+#pragma unroll
+        for (int s2 = 0; s2 < SPT; ++s2) lb = mk[s2] > lb ? mk[s2] : lb;
+        unsigned long long wb = lb;
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, wb, o);
+          wb = other > wb ? other : wb;
+        }
+        if (wb != 0ull && lb == wb) {  // keys are unique: exactly one lane of the warp
+#pragma unroll
+          for (int s2 = 0; s2 < SPT; ++s2)
+            if (mk[s2] == wb) { cand_k[wrp * 8 + r] = wb; cand_n[wrp * 8 + r] = mn[s2]; mk[s2] = 0ull; }
+        }
+        if (wb == 0ull && lane == 0) { cand_k[wrp * 8 + r] = 0ull; cand_n[wrp * 8 + r] = 0; }
+      }
+      __syncthreads();
+      if (wrp == 0) {
+        const int cw = lane >> 3, cr = lane & 7;
+        unsigned long long ck = cr < p.max_ctx ? cand_k[cw * 8 + cr] : 0ull;
+        const int32_t cn = cr < p.max_ctx ? cand_n[cw * 8 + cr] : 0;
+        for (int r = 0; r < p.max_ctx; ++r) {
+          unsigned long long wb = ck;
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, wb, o);
+            wb = other > wb ? other : wb;
+          }
+          if (wb != 0ull && ck == wb) {
+            p.out_ids[ctx * L + 1 + r] = (int64_t)cn;
+            p.out_mask[ctx * L + 1 + r] = 1.0f;
+            ck = 0ull;
+          }
+          if (wb == 0ull && lane == 0) {
+            p.out_ids[ctx * L + 1 + r] = 0;
+            p.out_mask[ctx * L + 1 + r] = 0.0f;
+          }
+        }
+      }
+    } else
     for (int r = 0; r < p.max_ctx; ++r) {
       unsigned long long best = 0ull;
       for (int i = tid; i < p.table_cap; i += kSamplerThreads) {
         if (tkeys[i] != 0) {
-          unsigned long long kk = ((unsigned long long)tscore[i] << 32) |
-                                  (unsigned long long)(0xffffffffu - tfirst[i]);
+          unsigned long long kk = ((unsigned long long)tscore[i] << 32) | (unsigned long long)tfirst[i];
           if (kk < bound && kk > best) best = kk;
         }
       }
@@ -173,8 +228,7 @@ sample_contexts_kernel(const SamplerParams p) {
       if (best != 0ull) {
         for (int i = tid; i < p.table_cap; i += kSamplerThreads) {
           if (tkeys[i] != 0) {
-            unsigned long long kk = ((unsigned long long)tscore[i] << 32) |
-                                    (unsigned long long)(0xffffffffu - tfirst[i]);
+            unsigned long long kk = ((unsigned long long)tscore[i] << 32) | (unsigned long long)tfirst[i];
             if (kk == best) {
               p.out_ids[ctx * L + 1 + r] = (int64_t)tkeys[i];
               p.out_mask[ctx * L + 1 + r] = 1.0f;
@@ -358,16 +412,22 @@ int pmgt_sample_contexts(const pmgt_graph* gh, const int64_t* roots, const int64
   p.table_shift = 32 - lg;
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
   p.out_ids = out_ids; p.out_mask = out_mask; p.out_visited_deg = out_visited_deg;
-  size_t smem = sizeof(int32_t) * 2 * (size_t)p.list_cap + 12 * (size_t)cap;
+  size_t smem = sizeof(int32_t) * (size_t)((2 * p.list_cap + 3) & ~3) + 12 * (size_t)cap;
   PMGT_CHECK_CUDA(cudaSetDevice(g->device));
+  void (*kern)(const SamplerParams) = sample_contexts_kernel<0>;
+  if (max_ctx <= 8) {
+    if (cap == 4 * kSamplerThreads) kern = sample_contexts_kernel<4>;
+    else if (cap == 8 * kSamplerThreads) kern = sample_contexts_kernel<8>;
+    else if (cap == 16 * kSamplerThreads) kern = sample_contexts_kernel<16>;
+  }
   if (smem > 48 * 1024)
-    PMGT_CHECK_CUDA(cudaFuncSetAttribute(sample_contexts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
-  PMGT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_contexts_kernel, kSamplerThreads, smem));
+  PMGT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSamplerThreads, smem));
   if (occ < 1) occ = 1;
   int64_t grid = (int64_t)num_sms() * occ;
   if (grid > n_ctx) grid = n_ctx;
-  sample_contexts_kernel<<<(unsigned)grid, kSamplerThreads, smem, (cudaStream_t)stream>>>(p);
+  kern<<<(unsigned)grid, kSamplerThreads, smem, (cudaStream_t)stream>>>(p);
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
 }
