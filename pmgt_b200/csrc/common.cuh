@@ -139,13 +139,32 @@ __device__ __forceinline__ void unpack_bf16x2(uint32_t v, float& lo, float& hi) 
   hi = __uint_as_float(v & 0xffff0000u);
 }
 
+// erf-GELU (transformers ACT2FN["gelu"]) and its derivative.  erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7,
+// far below the bf16 rounding of the stored activations): one reciprocal, one exp2, five FMAs -- the libdevice
+// erff costs ~3x the instructions and these epilogues are issue-bound.  The exponential e^{-x^2/2} is shared
+// between erf(x / sqrt 2) and the Gaussian density of the derivative.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf_x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;           // |x| / sqrt(2)
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float e = exp2f(-0.72134752044448170368f * x * x);      // e^{-x^2/2} = 2^{-x^2 / (2 ln 2)}
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfc_abs = poly * t * e;                          // 1 - erf(|x| / sqrt 2)
+  const float half = 0.5f * erfc_abs;
+  cdf = x >= 0.f ? 1.0f - half : half;                          // Phi(x)
+  pdf_x = x * 0.39894228040143267794f * e;                      // x * phi(x)
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  float cdf, pdf_x;
+  gelu_parts(x, cdf, pdf_x);
+  return x * cdf;
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float kInvSqrt2Pi = 0.39894228040143267794f;
-  float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  return cdf + x * kInvSqrt2Pi * __expf(-0.5f * x * x);
+  float cdf, pdf_x;
+  gelu_parts(x, cdf, pdf_x);
+  return cdf + pdf_x;
 }
 
 }  // namespace pmgt

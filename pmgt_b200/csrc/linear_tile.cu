@@ -636,7 +636,7 @@ int pmgt_linear_tile(const pmgt_linear_tile_args* a, void* stream) {
   switch (a->epi) {
     case PMGT_LT_BIAS:
       PMGT_REQUIRE(a->bias, "pmgt_linear_tile: bias required");
-      if (nc == 4) return launch_lt<4, 1, false, LT_BIAS, 1, 2, 1>(a, st);
+      if (nc == 4) return launch_lt<4, 1, false, LT_BIAS, 2, 1, 1>(a, st);
       return launch_lt<1, 1, false, LT_BIAS, 2, 3, 1>(a, st);
     case PMGT_LT_GELU:
       PMGT_REQUIRE(a->bias && a->aux_out && a->ld_aux_out % 8 == 0, "pmgt_linear_tile: GELU needs bias and aux_out");
