@@ -248,12 +248,14 @@ def ours(a):
 
     # ---- per-kernel-family profile (CUDA events on the launching stream, inside real steps) -> roofline
     roof, prof = None, None
+    # every rank runs the profiled steps (they contain the gradient allreduce); only rank 0 records events
+    n_prof = min(3, a.steps)
     if rank == 0:
         ops.PROFILE = []
-        n_prof = min(3, a.steps)
-        for s in range(n_prof):
-            tm.train_on_indices(ds, idx_dev[a.warmup + s], epoch=a.warmup + s)
-        torch.cuda.synchronize()
+    for s in range(n_prof):
+        tm.train_on_indices(ds, idx_dev[a.warmup + s], epoch=a.warmup + s)
+    barrier()
+    if rank == 0:
         recs, ops.PROFILE = ops.PROFILE, None
         prof = ops.profile_summary(recs)
         tot = sum(d["ms"] for d in prof.values())
