@@ -26,6 +26,8 @@ namespace pmgt {
 constexpr int kImgBytes = 32768;
 constexpr int kSlabBytes = 16384;
 constexpr int kAccSlots = 4;
+constexpr int kEpiWarps = 16;                     // 4 TMEM lane quarters x 4 column quarters (32 columns per thread)
+constexpr int kLtThreads = 96 + 32 * kEpiWarps;   // producer | MMA | store | 16 epilogue warps
 
 enum { LT_BIAS = PMGT_LT_BIAS, LT_GELU = PMGT_LT_GELU, LT_RES_LN = PMGT_LT_RES_LN, LT_PLAIN = PMGT_LT_PLAIN,
        LT_GELU_BWD = PMGT_LT_GELU_BWD };
@@ -64,7 +66,7 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
          ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-template <int NC, int KC, int EPI, int NG, int SA, int SE>
+template <int NC, int KC, int EPI, int SA, int SE, int NSTG>
 struct LtLayout {
   static constexpr bool kHasE = (EPI == LT_RES_LN || EPI == LT_GELU_BWD);
   static constexpr int kNOut = (EPI == LT_GELU) ? 2 : 1;
@@ -72,7 +74,7 @@ struct LtLayout {
   static constexpr int kA = kW + NC * KC * kImgBytes;
   static constexpr int kE = kA + SA * kImgBytes;
   static constexpr int kStg = kE + (kHasE ? SE : 0) * kImgBytes;
-  static constexpr int kBar = kStg + NG * kNOut * kImgBytes;
+  static constexpr int kBar = kStg + NSTG * kNOut * kImgBytes;
   static constexpr int kTotal = kBar + 256 + 1024;  // barriers + alignment slack
 };
 
@@ -81,18 +83,45 @@ struct LtBars {
   uint64_t a_full[4], a_empty[4];
   uint64_t e_full[4], e_empty[4];
   uint64_t acc_full[kAccSlots], acc_empty[kAccSlots];
+  uint64_t stg_full[2], stg_empty[2];
   uint32_t tmem_base;
 };
+static_assert(sizeof(LtBars) <= 256, "barrier block");
 
-template <int NC, int KC, bool B_MN, int EPI, int NG, int SA, int SE>
-__global__ void __launch_bounds__(64 + 128 * NG, 1)
+__device__ __forceinline__ void ld8f(const float* __restrict__ p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ uint4 pack8f(const float* v) {
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  return o;
+}
+__device__ __forceinline__ void unpack8f(const uint4& u, float* v) {
+  unpack_bf16x2(u.x, v[0], v[1]); unpack_bf16x2(u.y, v[2], v[3]);
+  unpack_bf16x2(u.z, v[4], v[5]); unpack_bf16x2(u.w, v[6], v[7]);
+}
+
+// Work item = one 128-token x 128-column output block.  Roles:
+//   warp 0      TMA producer: weights once, then activation (A) and epilogue-input (E) images, SA / SE deep
+//   warp 1      MMA issuer, accumulators in 4 TMEM slots of 128 columns
+//   warp 2      store warp: waits for a staged output block, issues the TMA stores, waits until they have READ the
+//               staging images and hands the buffers (and, for RES_LN, the E slot that doubles as the z image) back
+//   warps 3-18  epilogue: warp w reads TMEM lanes 32*(w%4).. (its hardware quarter) and columns 32*((w-3)/4)..,
+//               i.e. one row x 32 columns per thread.  Sixteen warps (instead of four per block) are what keeps the
+//               issue slots busy: the epilogue math (GELU, LayerNorm, Philox dropout) was the limiter, not HBM.
+template <int NC, int KC, bool B_MN, int EPI, int SA, int SE, int NSTG>
+__global__ void __launch_bounds__(kLtThreads, 1)
 linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_out,
                    const __grid_constant__ CUtensorMap tm_aux, const LtParams p) {
-  using Lay = LtLayout<NC, KC, EPI, NG, SA, SE>;
+  using Lay = LtLayout<NC, KC, EPI, SA, SE, NSTG>;
   constexpr bool kHasE = Lay::kHasE;
   constexpr int kNOut = Lay::kNOut;
   static_assert(!kHasE || NC == 1, "epilogue-input variants are single-chunk");
+  static_assert(NSTG == 1 || NSTG == 2, "one or two staging buffers");
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   LtBars* bars = reinterpret_cast<LtBars*>(smem + Lay::kBar);
@@ -104,11 +133,15 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       mbar_init(&bars->a_full[s], 1);
       mbar_init(&bars->a_empty[s], 1);
       mbar_init(&bars->e_full[s], 1);
-      mbar_init(&bars->e_empty[s], 1);
+      mbar_init(&bars->e_empty[s], EPI == LT_RES_LN ? 1 : kEpiWarps);
     }
     for (int s = 0; s < kAccSlots; ++s) {
       mbar_init(&bars->acc_full[s], 1);
-      mbar_init(&bars->acc_empty[s], 128);
+      mbar_init(&bars->acc_empty[s], kEpiWarps);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->stg_full[s], kEpiWarps);
+      mbar_init(&bars->stg_empty[s], 1);
     }
     fence_barrier_init();
     prefetch_tmap(&tm_x);
@@ -186,24 +219,64 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         }
       }
     }
+  } else if (warp == 2) {
+    // ===================== store warp =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int n = 0; n < NC; ++n, ++it) {
+          const uint32_t buf = it % NSTG;
+          mbar_wait(&bars->stg_full[buf], (it / NSTG) & 1u);
+          const uint32_t stg0 = smem_u32(smem + Lay::kStg + buf * kNOut * kImgBytes);
+          const int col = n * 128, row = tile * 128;
+          if (EPI == LT_GELU) {
+            tma_store_2d(&tm_aux, stg0, col, row);
+            tma_store_2d(&tm_aux, stg0 + kSlabBytes, col + 64, row);
+            tma_store_2d(&tm_out, stg0 + kImgBytes, col, row);
+            tma_store_2d(&tm_out, stg0 + kImgBytes + kSlabBytes, col + 64, row);
+          } else {
+            tma_store_2d(&tm_out, stg0, col, row);
+            tma_store_2d(&tm_out, stg0 + kSlabBytes, col + 64, row);
+            if (EPI == LT_RES_LN) {
+              const uint32_t eimg = smem_u32(smem + Lay::kE + (it % SE) * kImgBytes);
+              tma_store_2d(&tm_aux, eimg, col, row);
+              tma_store_2d(&tm_aux, eimg + kSlabBytes, col + 64, row);
+            }
+          }
+          tma_store_commit();
+          tma_store_wait_read0();
+          mbar_arrive(&bars->stg_empty[buf]);
+          if (EPI == LT_RES_LN) mbar_arrive(&bars->e_empty[it % SE]);
+        }
+      }
+      tma_store_wait_all0();
+    }
   } else {
-    // ===================== epilogue groups =====================
-    const int eg = (warp - 2) >> 2;
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;                   // tile row == TMEM lane
-    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
-    const uint32_t bar_id = 1u + (uint32_t)eg;
-    unsigned char* stg0 = smem + Lay::kStg + (eg * kNOut) * kImgBytes;
-    unsigned char* stg1 = stg0 + kImgBytes;  // only when kNOut == 2
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may access
+    const int cq = (warp - 3) >> 2;             // column quarter
+    const int r = quarter * 32 + lane;          // tile row == TMEM lane
+    const int c0 = cq * 32;
     const float ks = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
-    uint32_t item = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, item += NC) {
-      for (int n = 0; n < NC; ++n) {
-        const uint32_t it = item + n;
-        if ((int)(it % NG) != eg) continue;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int n = 0; n < NC; ++n, ++it) {
         const uint32_t slot = it % kAccSlots;
         mbar_wait(&bars->acc_full[slot], (it / kAccSlots) & 1u);
         tcgen05_fence_after();
+        float v[32];
+        {
+          uint32_t acc[32];
+          tmem_ld_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 128u + (uint32_t)c0, acc);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+        }
+        // accumulator slot drained: the MMAs of a later block may overwrite it while this block is post-processed
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[slot]);
+
         unsigned char* eimg = nullptr;
         int se = 0;
         if (kHasE) {
@@ -211,149 +284,100 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           mbar_wait(&bars->e_full[se], (it / SE) & 1u);
           eimg = smem + Lay::kE + se * kImgBytes;
         }
-        // the previous TMA store of this group must have finished reading the staging images
-        named_bar_sync(bar_id, 128);
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 128u;
+        const uint32_t buf = it % NSTG;
+        mbar_wait(&bars->stg_empty[buf], ((it / NSTG) & 1u) ^ 1u);
+        unsigned char* stg0 = smem + Lay::kStg + buf * kNOut * kImgBytes;
+        unsigned char* stg1 = stg0 + kImgBytes;  // only when kNOut == 2
         const long long tok = (long long)tile * 128 + r;
-        float zsum = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t acc[32];
-          tmem_ld_x32(taddr + (uint32_t)c0, acc);
-          tmem_wait_ld();
+
+        if (EPI == LT_BIAS || EPI == LT_GELU || EPI == LT_RES_LN) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int c8 = (c0 >> 3) + g;
-            const int col = n * 128 + c0 + g * 8;
-            float v[8];
+            float b[8];
+            ld8f(p.bias + n * 128 + c0 + g * 8, b);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
-            if (EPI == LT_BIAS || EPI == LT_GELU || EPI == LT_RES_LN) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (EPI == LT_GELU) {
-              uint4 pre;
-              pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
-              pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(stg0 + img_off(r, c8)) = pre;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(stg1 + img_off(r, c8)) = o;
-            } else if (EPI == LT_GELU_BWD) {
-              const uint4 pre = *reinterpret_cast<const uint4*>(eimg + img_off(r, c8));
-              float x[8];
-              unpack_bf16x2(pre.x, x[0], x[1]); unpack_bf16x2(pre.y, x[2], x[3]);
-              unpack_bf16x2(pre.z, x[4], x[5]); unpack_bf16x2(pre.w, x[6], x[7]);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(x[j]);
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(stg0 + img_off(r, c8)) = o;
-            } else if (EPI == LT_RES_LN) {
-              if (p.dropout_p > 0.f) {
-                const uint64_t idx = (uint64_t)tok * 128u + (uint64_t)(c0 + g * 8);
-                const uint32_t k8 = dropout_keep8(p.seed, p.site, idx, p.dropout_p);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = (k8 >> j) & 1u ? v[j] * ks : 0.f;
-              }
-              uint4* zp = reinterpret_cast<uint4*>(eimg + img_off(r, c8));
-              const uint4 rs = *zp;
-              float x[8];
-              unpack_bf16x2(rs.x, x[0], x[1]); unpack_bf16x2(rs.y, x[2], x[3]);
-              unpack_bf16x2(rs.z, x[4], x[5]); unpack_bf16x2(rs.w, x[6], x[7]);
-              uint4 z;
-              z.x = pack_bf16x2(v[0] + x[0], v[1] + x[1]); z.y = pack_bf16x2(v[2] + x[2], v[3] + x[3]);
-              z.z = pack_bf16x2(v[4] + x[4], v[5] + x[5]); z.w = pack_bf16x2(v[6] + x[6], v[7] + x[7]);
-              *zp = z;  // z replaces the residual in place (the row is private to this thread)
-              float zf[8];
-              unpack_bf16x2(z.x, zf[0], zf[1]); unpack_bf16x2(z.y, zf[2], zf[3]);
-              unpack_bf16x2(z.z, zf[4], zf[5]); unpack_bf16x2(z.w, zf[6], zf[7]);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) zsum += zf[j];
-            } else {  // LT_BIAS, LT_PLAIN
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(stg0 + img_off(r, c8)) = o;
-            }
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] += b[j];
           }
         }
-        // accumulator slot drained
-        tcgen05_fence_before();
-        mbar_arrive(&bars->acc_empty[slot]);
-        if (EPI == LT_RES_LN) {
-          // LayerNorm over the bf16-rounded z (exactly what the backward pass re-reads)
-          const float mean = zsum * (1.f / 128.f);
+        if (EPI == LT_GELU) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            *reinterpret_cast<uint4*>(stg0 + img_off(r, cq * 4 + g)) = pack8f(v + g * 8);
+            float h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = gelu_erf(v[g * 8 + j]);
+            *reinterpret_cast<uint4*>(stg1 + img_off(r, cq * 4 + g)) = pack8f(h);
+          }
+        } else if (EPI == LT_GELU_BWD) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 pre = *reinterpret_cast<const uint4*>(eimg + img_off(r, cq * 4 + g));
+            float x[8];
+            unpack8f(pre, x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] * gelu_erf_grad(x[j]);
+            *reinterpret_cast<uint4*>(stg0 + img_off(r, cq * 4 + g)) = pack8f(x);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->e_empty[se]);  // pre-activation image consumed
+        } else if (EPI == LT_RES_LN) {
+          float* scr = reinterpret_cast<float*>(stg0);      // row-statistics exchange lives in the (still unused) y staging image
+          float zsum = 0.f;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (p.dropout_p > 0.f) {
+              const uint64_t idx = (uint64_t)tok * 128u + (uint64_t)(c0 + g * 8);
+              const uint32_t k8 = dropout_keep8(p.seed, p.site, idx, p.dropout_p);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] = (k8 >> j) & 1u ? v[g * 8 + j] * ks : 0.f;
+            }
+            uint4* zp = reinterpret_cast<uint4*>(eimg + img_off(r, cq * 4 + g));
+            float x[8];
+            unpack8f(*zp, x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] += v[g * 8 + j];
+            const uint4 z = pack8f(x);
+            *zp = z;  // z replaces the residual in place (the chunk is private to this thread)
+            unpack8f(z, v + g * 8);  // LayerNorm over the bf16-rounded z (exactly what the backward pass re-reads)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) zsum += v[g * 8 + j];
+          }
+          scr[cq * 128 + r] = zsum;
+          named_bar_sync(1, 32 * kEpiWarps);
+          const float mean = (scr[r] + scr[128 + r] + scr[256 + r] + scr[384 + r]) * (1.f / 128.f);
           float q = 0.f;
 #pragma unroll
-          for (int c8 = 0; c8 < 16; ++c8) {
-            const uint4 z = *reinterpret_cast<const uint4*>(eimg + img_off(r, c8));
-            float zf[8];
-            unpack_bf16x2(z.x, zf[0], zf[1]); unpack_bf16x2(z.y, zf[2], zf[3]);
-            unpack_bf16x2(z.z, zf[4], zf[5]); unpack_bf16x2(z.w, zf[6], zf[7]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { const float d = zf[j] - mean; q = fmaf(d, d, q); }
-          }
-          const float rstd = rsqrtf(q * (1.f / 128.f) + p.ln_eps);
+          for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+          scr[512 + cq * 128 + r] = q;
+          named_bar_sync(1, 32 * kEpiWarps);
+          const float rstd =
+              rsqrtf((scr[512 + r] + scr[640 + r] + scr[768 + r] + scr[896 + r]) * (1.f / 128.f) + p.ln_eps);
+          named_bar_sync(1, 32 * kEpiWarps);  // every thread has read the exchange area: y may overwrite it
           const bool f32_ok = p.out_f32 != nullptr && tok < p.T;
 #pragma unroll
-          for (int c8 = 0; c8 < 16; ++c8) {
-            const uint4 z = *reinterpret_cast<const uint4*>(eimg + img_off(r, c8));
-            float zf[8];
-            unpack_bf16x2(z.x, zf[0], zf[1]); unpack_bf16x2(z.y, zf[2], zf[3]);
-            unpack_bf16x2(z.z, zf[4], zf[5]); unpack_bf16x2(z.w, zf[6], zf[7]);
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c8 * 8));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c8 * 8 + 4));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c8 * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c8 * 8 + 4));
-            float y[8];
-            y[0] = (zf[0] - mean) * rstd * g0.x + b0.x; y[1] = (zf[1] - mean) * rstd * g0.y + b0.y;
-            y[2] = (zf[2] - mean) * rstd * g0.z + b0.z; y[3] = (zf[3] - mean) * rstd * g0.w + b0.w;
-            y[4] = (zf[4] - mean) * rstd * g1.x + b1.x; y[5] = (zf[5] - mean) * rstd * g1.y + b1.y;
-            y[6] = (zf[6] - mean) * rstd * g1.z + b1.z; y[7] = (zf[7] - mean) * rstd * g1.w + b1.w;
-            uint4 o;
-            o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
-            o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
-            *reinterpret_cast<uint4*>(stg0 + img_off(r, c8)) = o;
+          for (int g = 0; g < 4; ++g) {
+            float gm[8], bt[8], y[8];
+            ld8f(p.ln_g + c0 + g * 8, gm);
+            ld8f(p.ln_b + c0 + g * 8, bt);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = (v[g * 8 + j] - mean) * rstd * gm[j] + bt[j];
+            *reinterpret_cast<uint4*>(stg0 + img_off(r, cq * 4 + g)) = pack8f(y);
             if (f32_ok) {
-              float* o32 = p.out_f32 + tok * 128 + c8 * 8;
+              float* o32 = p.out_f32 + tok * 128 + c0 + g * 8;
               *reinterpret_cast<float4*>(o32) = make_float4(y[0], y[1], y[2], y[3]);
               *reinterpret_cast<float4*>(o32 + 4) = make_float4(y[4], y[5], y[6], y[7]);
             }
           }
+        } else {  // LT_BIAS, LT_PLAIN
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(stg0 + img_off(r, cq * 4 + g)) = pack8f(v + g * 8);
         }
-        // hand the staged images to the TMA store engine
+        // hand the staged block to the store warp
         fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
-        if (leader) {
-          const int col = n * 128, row = tile * 128;
-          if (EPI == LT_GELU) {
-            tma_store_2d(&tm_aux, smem_u32(stg0), col, row);
-            tma_store_2d(&tm_aux, smem_u32(stg0) + kSlabBytes, col + 64, row);
-            tma_store_2d(&tm_out, smem_u32(stg1), col, row);
-            tma_store_2d(&tm_out, smem_u32(stg1) + kSlabBytes, col + 64, row);
-          } else {
-            tma_store_2d(&tm_out, smem_u32(stg0), col, row);
-            tma_store_2d(&tm_out, smem_u32(stg0) + kSlabBytes, col + 64, row);
-            if (EPI == LT_RES_LN) {
-              tma_store_2d(&tm_aux, smem_u32(eimg), col, row);
-              tma_store_2d(&tm_aux, smem_u32(eimg) + kSlabBytes, col + 64, row);
-            }
-          }
-          tma_store_commit();
-          tma_store_wait_read0();
-          if (kHasE) mbar_arrive(&bars->e_empty[se]);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->stg_full[buf]);
       }
     }
-    if (leader) tma_store_wait_all0();
   }
 
   tcgen05_fence_before();
@@ -544,11 +568,11 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant_
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-template <int NC, int KC, bool B_MN, int EPI, int NG, int SA, int SE>
+template <int NC, int KC, bool B_MN, int EPI, int SA, int SE, int NSTG>
 static int launch_lt(const pmgt_linear_tile_args* a, cudaStream_t st) {
-  using Lay = LtLayout<NC, KC, EPI, NG, SA, SE>;
+  using Lay = LtLayout<NC, KC, EPI, SA, SE, NSTG>;
   static_assert(Lay::kTotal <= 232448, "shared memory budget (227 KiB)");
-  auto kern = linear_tile_kernel<NC, KC, B_MN, EPI, NG, SA, SE>;
+  auto kern = linear_tile_kernel<NC, KC, B_MN, EPI, SA, SE, NSTG>;
   static bool configured = false;
   if (!configured) {
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay::kTotal));
@@ -575,7 +599,7 @@ static int launch_lt(const pmgt_linear_tile_args* a, cudaStream_t st) {
   p.out_f32 = a->out_f32;
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
-  kern<<<grid, 64 + 128 * NG, Lay::kTotal, st>>>(tx, tw, te, to, ta, p);
+  kern<<<grid, kLtThreads, Lay::kTotal, st>>>(tx, tw, te, to, ta, p);
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
 }
@@ -636,19 +660,19 @@ int pmgt_linear_tile(const pmgt_linear_tile_args* a, void* stream) {
   switch (a->epi) {
     case PMGT_LT_BIAS:
       PMGT_REQUIRE(a->bias, "pmgt_linear_tile: bias required");
-      if (nc == 4) return launch_lt<4, 1, false, LT_BIAS, 2, 1, 1>(a, st);
-      return launch_lt<1, 1, false, LT_BIAS, 2, 3, 1>(a, st);
+      if (nc == 4) return launch_lt<4, 1, false, LT_BIAS, 1, 1, 2>(a, st);
+      return launch_lt<1, 1, false, LT_BIAS, 3, 1, 2>(a, st);
     case PMGT_LT_GELU:
       PMGT_REQUIRE(a->bias && a->aux_out && a->ld_aux_out % 8 == 0, "pmgt_linear_tile: GELU needs bias and aux_out");
-      return launch_lt<1, 1, false, LT_GELU, 2, 2, 1>(a, st);
+      return launch_lt<1, 1, false, LT_GELU, 2, 1, 2>(a, st);
     case PMGT_LT_RES_LN:
       PMGT_REQUIRE(a->bias && a->aux_out && a->e_in && a->ln_g && a->ln_b && a->ld_aux_out % 8 == 0 && a->ld_e % 8 == 0,
                    "pmgt_linear_tile: RES_LN needs bias, residual (e_in), z out (aux_out), ln_g, ln_b");
       PMGT_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "pmgt_linear_tile: bad dropout_p");
       return launch_lt<1, 1, false, LT_RES_LN, 2, 2, 2>(a, st);
     case PMGT_LT_PLAIN:
-      if (kc == 4) return launch_lt<1, 4, true, LT_PLAIN, 1, 2, 1>(a, st);
-      return launch_lt<1, 1, true, LT_PLAIN, 2, 3, 1>(a, st);
+      if (kc == 4) return launch_lt<1, 4, true, LT_PLAIN, 2, 1, 1>(a, st);
+      return launch_lt<1, 1, true, LT_PLAIN, 3, 1, 2>(a, st);
     case PMGT_LT_GELU_BWD:
       PMGT_REQUIRE(a->e_in && a->ld_e % 8 == 0, "pmgt_linear_tile: GELU_BWD needs the pre-activation (e_in)");
       return launch_lt<1, 1, true, LT_GELU_BWD, 2, 2, 2>(a, st);

@@ -726,6 +726,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
+// hidden size 128 (the default encoder): half-warp-per-token kernels in embed128.cu
+int embed128_supported(const pmgt_embed_args* a);
+int embed128_fwd(const pmgt_embed_args* a, cudaStream_t st);
+int embed128_bwd(const pmgt_embed_args* a, cudaStream_t st);
+
 static int persistent_grid(long long work_warps, int warps_per_cta, int ctas_per_sm) {
   long long need = (work_warps + warps_per_cta - 1) / warps_per_cta;
   long long cap = (long long)num_sms() * ctas_per_sm;
@@ -751,6 +756,7 @@ int pmgt_embed_fuse_fwd(const pmgt_embed_args* a, void* stream) {
   PMGT_REQUIRE(a->H % 4 == 0 && a->H >= 4 && a->H <= 1024, "pmgt_embed_fuse_fwd: H must be a multiple of 4 in [4,1024]");
   PMGT_REQUIRE(a->L >= 1 && a->rows >= 0, "pmgt_embed_fuse_fwd: bad sizes");
   if (a->rows == 0) return PMGT_OK;
+  if (embed128_supported(a)) return embed128_fwd(a, (cudaStream_t)stream);
   const int grid = persistent_grid(a->rows * a->L, kRowThreads / 32, 8);
   PMGT_DISPATCH_G(a->H, (embed_fuse_fwd_kernel<1><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)),
                   (embed_fuse_fwd_kernel<8><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)));
@@ -765,6 +771,7 @@ int pmgt_embed_fuse_bwd(const pmgt_embed_args* a, void* stream) {
                "pmgt_embed_fuse_bwd: null argument");
   PMGT_REQUIRE(a->H % 4 == 0 && a->H >= 4 && a->H <= 1024, "pmgt_embed_fuse_bwd: H must be a multiple of 4 in [4,1024]");
   if (a->rows == 0) return PMGT_OK;
+  if (embed128_supported(a)) return embed128_bwd(a, (cudaStream_t)stream);
   const size_t smem = (size_t)(kRowThreads / 32) * 9 * a->H * sizeof(float);
   const int grid = persistent_grid(a->rows, kRowThreads / 32, 2);
   if (a->H <= 128) {

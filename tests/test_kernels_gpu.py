@@ -30,7 +30,7 @@ def _r(*shape, s=1.0):
     return (torch.randn(*shape, device="cuda") * s).to(BF16)
 
 
-@pytest.mark.parametrize("R,L,H", [(7, 6, 128), (5, 9, 64), (3, 33, 256), (4, 6, 32)])
+@pytest.mark.parametrize("R,L,H", [(7, 6, 128), (5, 9, 64), (3, 33, 256), (4, 6, 32), (20001, 6, 128), (1, 1, 128)])
 def test_embed_fuse_fwd_bwd(R, L, H):
     ops = _ops()
     T = R * L
@@ -75,6 +75,93 @@ def test_embed_fuse_fwd_bwd(R, L, H):
     _close(d["d_ln_b"], bb.grad, 5e-3, "d_ln_b")
     _close(d["d_bias_v"], evf.grad.sum(0), 1e-2, "d_bias_v")
     _close(d["d_bias_t"], etf.grad.sum(0), 1e-2, "d_bias_t")
+
+
+@pytest.mark.parametrize("R,L,rows", [(9, 6, 40), (9001, 6, 300)])
+def test_embed_fuse_projected_table_mode(R, L, rows):
+    """Projected-table mode (row_idx gather, fp32 per-row gradient accumulation) + the second gradient term dx_b."""
+    ops = _ops()
+    H, T = 128, R * L
+    tv, tt = _r(rows, H), _r(rows, H)
+    idx = torch.randint(0, rows, (T,), device="cuda")
+    idx[::7] = 0  # pad rows
+    w_att = torch.randn(2, 2 * H, device="cuda") * 0.2
+    b_att = torch.randn(2, device="cuda") * 0.1
+    pos = torch.randn(100, H, device="cuda") * 0.1
+    role = torch.randn(2, H, device="cuda") * 0.1
+    g = 1 + 0.1 * torch.randn(H, device="cuda")
+    b = 0.1 * torch.randn(H, device="cuda")
+    x = torch.empty(T, H, device="cuda", dtype=BF16)
+    ops.embed_fuse_fwd(ops.embed_args(R, L, H, tv, tt, w_att, b_att, pos, role, g, b, 1e-12, 0.0, 0, 0, x_out=x, row_idx=idx))
+    leaves = [t.float().requires_grad_(True) for t in (tv, tt)]
+    leaves += [t.clone().requires_grad_(True) for t in (w_att, b_att, pos, role, g, b)]
+    tvf, ttf, wa, ba, po, ro, gg, bb = leaves
+    e = [tvf[idx].view(R, L, H), ttf[idx].view(R, L, H)]
+    att = torch.softmax(torch.nn.functional.linear(torch.tanh(torch.cat(e, -1)), wa, ba), -1)
+    fused = att[..., :1] * e[0] + att[..., 1:] * e[1]
+    role_ids = torch.tensor([0] + [1] * (L - 1), device="cuda")
+    want = torch.nn.functional.layer_norm(fused + po[:L] + ro[role_ids], (H,), gg, bb, 1e-12)
+    _close(x.view(R, L, H), want.detach(), name="x")
+    dx, dxb = _r(T, H), _r(T, H)
+    want.backward((dx.float() + dxb.float()).view(R, L, H))
+
+    def z(*s):
+        return torch.zeros(*s, device="cuda")
+
+    d = dict(d_w_att=z(2, 2 * H), d_b_att=z(2), d_pos=z(100, H), d_role=z(2, H), d_ln_g=z(H), d_ln_b=z(H),
+             d_bias_v=z(H), d_bias_t=z(H))
+    acc_v, acc_t = z(rows, H), z(rows, H)
+    ops.embed_fuse_bwd(ops.embed_args(R, L, H, tv, tt, w_att, b_att, pos, role, g, b, 1e-12, 0.0, 0, 0, dx=dx, dx_b=dxb,
+                                      row_idx=idx, dev_acc=acc_v, det_acc=acc_t, skip_row0=0, **d))
+    _close(acc_v, tvf.grad, name="dev_acc")
+    _close(acc_t, ttf.grad, name="det_acc")
+    for k, want_g in (("d_w_att", wa.grad), ("d_b_att", ba.grad), ("d_pos", po.grad), ("d_role", ro.grad),
+                      ("d_ln_g", gg.grad), ("d_ln_b", bb.grad)):
+        _close(d[k], want_g, 5e-3, k)
+    _close(d["d_bias_v"], tvf.grad.sum(0), 1e-2, "d_bias_v")
+    _close(d["d_bias_t"], ttf.grad.sum(0), 1e-2, "d_bias_t")
+    # skip_row0: the <pad> row receives nothing, every other row is unchanged
+    acc_v2, acc_t2 = z(rows, H), z(rows, H)
+    d2 = {k: torch.zeros_like(v) for k, v in d.items()}
+    ops.embed_fuse_bwd(ops.embed_args(R, L, H, tv, tt, w_att, b_att, pos, role, g, b, 1e-12, 0.0, 0, 0, dx=dx, dx_b=dxb,
+                                      row_idx=idx, dev_acc=acc_v2, det_acc=acc_t2, skip_row0=1, **d2))
+    assert float(acc_v2[0].abs().max()) == 0.0 and float(acc_t2[0].abs().max()) == 0.0
+    _close(acc_v2[1:], tvf.grad[1:], name="dev_acc[1:]")
+
+
+def test_embed_fuse_dropout_mask_agrees_between_fwd_and_bwd():
+    """Train-mode dropout of the embedding block: keep rate, 1/(1-p) scaling, and the backward pass regenerating the
+    same mask (gradient of dropped elements is exactly zero in d LayerNorm beta's per-element view)."""
+    ops = _ops()
+    R, L, H, p = 3000, 6, 128, 0.1
+    T = R * L
+    ev, et = _r(T, H), _r(T, H)
+    w_att = torch.randn(2, 2 * H, device="cuda") * 0.2
+    b_att = torch.zeros(2, device="cuda")
+    pos = torch.zeros(100, H, device="cuda")
+    role = torch.zeros(2, H, device="cuda")
+    g = torch.ones(H, device="cuda")
+    b = torch.full((H,), 3.0, device="cuda")  # keeps every undropped output away from zero
+    x0 = torch.empty(T, H, device="cuda", dtype=BF16)
+    x1 = torch.empty(T, H, device="cuda", dtype=BF16)
+    ops.embed_fuse_fwd(ops.embed_args(R, L, H, ev, et, w_att, b_att, pos, role, g, b, 1e-12, 0.0, 5, 0, x_out=x0))
+    ops.embed_fuse_fwd(ops.embed_args(R, L, H, ev, et, w_att, b_att, pos, role, g, b, 1e-12, p, 5, 0, x_out=x1))
+    keep = x1 != 0
+    rate = float(keep.float().mean())
+    assert abs(rate - (1 - p)) < 5e-3, rate
+    _close(x1[keep].float(), x0[keep].float() / (1 - p), 1e-2, "kept values scaled by 1/(1-p)")
+
+    def z(*s):
+        return torch.zeros(*s, device="cuda")
+
+    d = dict(d_w_att=z(2, 2 * H), d_b_att=z(2), d_pos=z(100, H), d_role=z(2, H), d_ln_g=z(H), d_ln_b=z(H),
+             d_bias_v=z(H), d_bias_t=z(H))
+    dx = torch.ones(T, H, device="cuda", dtype=BF16)
+    dev_, det_ = torch.empty_like(ev), torch.empty_like(et)
+    ops.embed_fuse_bwd(ops.embed_args(R, L, H, ev, et, w_att, b_att, pos, role, g, b, 1e-12, p, 5, 0, dx=dx, dev=dev_,
+                                      det=det_, **d))
+    # d LayerNorm beta = column sums of the masked, rescaled upstream gradient (all ones here)
+    _close(d["d_ln_b"], keep.float().sum(0) / (1 - p), 1e-4, "d_ln_b counts the kept elements")
 
 
 @pytest.mark.parametrize("R,L,H,heads,beta", [(9, 6, 128, 1, 0.5), (5, 9, 64, 4, 0.3), (3, 33, 192, 3, 0.5),
