@@ -231,6 +231,16 @@ class FlatParams:
     def f32(self, name, span=None):
         return self._view(self.flat, self._views32, name, span)
 
+    def step_arena(self) -> "GradArena":
+        """The persistent gradient arena of this parameter set (one per flat buffer), zeroed for a new step."""
+        a = getattr(self, "_step_arena", None)
+        if a is None or a.buf is None or a.buf.device != self.flat.device or a.buf.numel() != self.total:
+            a = GradArena(self, persistent=True)
+            a.get()
+            self._step_arena = a
+            return a
+        return a.reset()
+
     def bf16(self, name, span=None):
         return self._view(self.flat_bf16, self._views16, name, span)
 
@@ -239,9 +249,15 @@ class GradArena:
     """One fp32 buffer per backward pass holding every parameter gradient in
     FlatParams order; autograd receives views of it."""
 
-    def __init__(self, fp: FlatParams):
+    def __init__(self, fp: FlatParams, persistent: bool = False):
         self.fp = fp
         self.buf = None
+        self.persistent = persistent  # the same buffer every step (zeroed by `reset`): what a launch plan needs
+
+    def reset(self):
+        if self.buf is not None:
+            self.buf.zero_()
+        return self
 
     def get(self):
         if self.buf is None:
@@ -298,6 +314,101 @@ def encoder_param_order(bert: "PMGTModel", prefix: str = "") -> List[Tuple[str, 
 # ---------------------------------------------------------------------------
 # encoder forward / backward orchestration
 # ---------------------------------------------------------------------------
+class _BufPool:
+    """Shape-keyed free list for the backward pass of a launch plan: a buffer released after its last reader was
+    enqueued is handed to a later allocation of the same shape (everything runs on one stream, so stream order makes
+    the reuse safe).  Without it a recorded backward pass would pin every temporary of every layer."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free = {}
+        self.owned = []
+
+    def get(self, shape, dtype):
+        key = (tuple(shape), dtype)
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop()
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        self.owned.append(t)
+        return t
+
+    def release(self, *ts):
+        seen = set()
+        for t in ts:
+            if t is None or id(t) in seen:
+                continue
+            seen.add(id(t))
+            self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+
+class _EncoderPlan:
+    """The launch sequence of one encoder pass at fixed shapes, recorded on the first step and re-issued afterwards.
+
+    Everything the recorded argument blocks point at is owned by the plan (inputs are copied into ``rows_idx`` /
+    ``mask``; activations, temporaries, ``hidden`` and ``d_hidden`` stay allocated), so a replay is ~170 ctypes calls
+    with ready-made arguments; only the dropout seed is patched.  Outputs are valid until the next pass through the
+    same plan -- which is why plans are opt-in (``PMGTModel.use_launch_plans``; the trainer's step loop turns them on).
+    """
+
+    def __init__(self, key, R, L, H, device):
+        self.key, self.R, self.L, self.T, self.H = key, R, L, R * L, H
+        self.device = device
+        self.rows_idx = torch.empty(R * L, dtype=torch.int64, device=device)
+        self.mask = torch.empty(R, L, dtype=torch.float32, device=device)
+        self.fwd_tape, self.bwd_tape = None, None
+        self.fwd_seeds, self.bwd_seeds = [], []
+        self.hidden, self.run, self.d_hidden = None, None, None
+        self.pool = _BufPool(device)
+        self.pending_backward = False
+
+    def grad_buffer(self) -> torch.Tensor:
+        """fp32 [T, H] buffer the caller may build d(loss)/d(hidden) in (saves the copy in ``backward``)."""
+        if self.d_hidden is None:
+            self.d_hidden = torch.empty(self.T, self.H, dtype=torch.float32, device=self.device)
+        return self.d_hidden
+
+    def forward(self, fp, pre, cfg, src, rows_idx, mask, training, seed, keep):
+        self.rows_idx.copy_(rows_idx.reshape(-1))
+        self.mask.copy_(mask)
+        if self.fwd_tape is None:
+            tape = []
+            ops.TAPE = tape
+            try:
+                self.held = []
+                self.hidden, self.run = _encode_forward(fp, pre, cfg, src, self.rows_idx, self.R, self.L, self.mask,
+                                                        training, seed, keep, hold=self.held)
+            finally:
+                ops.TAPE = None
+            self.fwd_tape, self.fwd_seeds = tape, ops.tape_seed_blocks(tape)
+        else:
+            for a in self.fwd_seeds:
+                a.dropout_seed = seed
+            if self.run is not None:
+                self.run.seed = seed
+            ops.replay(self.fwd_tape)
+        self.pending_backward = keep
+        return self.hidden.view(self.R, self.L, self.H)
+
+    def backward(self, fp, pre, cfg, d_hidden, arena):
+        buf = self.grad_buffer()
+        if d_hidden.data_ptr() != buf.data_ptr():
+            buf.copy_(d_hidden.reshape(self.T, self.H))
+        if self.bwd_tape is None:
+            tape = []
+            ops.TAPE = tape
+            try:
+                _encode_backward(fp, pre, cfg, self.run, buf, arena, pool=self.pool)
+            finally:
+                ops.TAPE = None
+            self.bwd_tape, self.bwd_seeds = tape, ops.tape_seed_blocks(tape)
+        else:
+            for a in self.bwd_seeds:
+                a.dropout_seed = self.run.seed
+            ops.replay(self.bwd_tape)
+        self.pending_backward = False
+
+
 class _EncoderRun:
     """Activations of one encoder pass kept for the backward pass."""
     __slots__ = ("R", "L", "T", "mask", "rows_idx", "src", "src_rows", "ev", "et", "x0", "layers", "seed", "p_hid",
@@ -318,7 +429,7 @@ def _tile_path(H: int, I: int) -> bool:
 
 
 def _encode_forward(fp: FlatParams, pre: str, cfg: PMGTConfig, src: List[torch.Tensor], rows_idx, R: int, L: int,
-                    mask: torch.Tensor, training: bool, seed: int, keep: bool):
+                    mask: torch.Tensor, training: bool, seed: int, keep: bool, hold: Optional[list] = None):
     """PMGTModel.forward (modeling_pmgt.py:80-152) on ``R`` sequences of length ``L``.
 
     ``src``: per modality either the bf16 feature table (``rows_idx`` = flat int64
@@ -333,7 +444,10 @@ def _encode_forward(fp: FlatParams, pre: str, cfg: PMGTConfig, src: List[torch.T
     E = pre + "embeddings."
 
     def new(*shape, dtype=BF16):
-        return torch.empty(shape, dtype=dtype, device=dev)
+        t = torch.empty(shape, dtype=dtype, device=dev)
+        if hold is not None:  # a launch plan keeps every buffer its recorded launches point at
+            hold.append(t)
+        return t
 
     # K2: per-modality projections on tensor cores, then the fusion kernel.  Two modes:
     #  * gather-fused GEMM: rows of the feature tables are fetched inside the GEMM, one projection per TOKEN
@@ -433,15 +547,22 @@ def _encode_forward(fp: FlatParams, pre: str, cfg: PMGTConfig, src: List[torch.T
 
 
 def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun, d_hidden: torch.Tensor,
-                     arena: GradArena):
-    """Reverse of ``_encode_forward``; parameter gradients are accumulated into ``arena``."""
+                     arena: GradArena, pool: Optional[_BufPool] = None):
+    """Reverse of ``_encode_forward``; parameter gradients are accumulated into ``arena``.  ``pool`` (launch plans)
+    recycles the per-layer temporaries instead of leaving that to torch's allocator."""
     H, I, heads = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
     R, L, T = run.R, run.L, run.T
     dev = d_hidden.device
     seed, p_hid, p_att = run.seed, run.p_hid, run.p_att
 
     def new(*shape, dtype=BF16):
+        if pool is not None:
+            return pool.get(shape, dtype)
         return torch.empty(shape, dtype=dtype, device=dev)
+
+    def done(*ts):
+        if pool is not None:
+            pool.release(*ts)
 
     G = arena.view
     dy_f32 = d_hidden.contiguous().view(T, H)
@@ -481,6 +602,7 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
         ops.dw_tile(dqkvc, x, G(P + "attention.self.query.weight", 4), G(P + "attention.self.query.bias", 4))
         dx = new(T, H)
         ops.linear_tile(dqkvc, fp.bf16(P + "attention.self.query.weight", 4), dx, ops.LT_PLAIN, w_mn=True, tag="lt_dx_qkvc")
+        done(dy, dy_b, dz2, do2, dh_pre, da, dctx, dqkvc, *((do1,) if do1 is not dz1 else ()))
         dy, dy_b = dx, dz1  # d x = dx (projection branch) + dz1 (residual branch): summed by the consumer
     for i in reversed(range(0 if run.tile else cfg.num_hidden_layers)):
         P = f"{pre}encoder.layer.{i}."
@@ -535,7 +657,9 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
              fp.f32(E + "LayerNorm.weight"), fp.f32(E + "LayerNorm.bias"), cfg.layer_norm_eps, p_hid, seed, 0)
     if run.dense_tables:
         # per-table-row gradient of the projected rows (fp32 red.add), then ONE dense dW GEMM per modality
-        accs = [torch.zeros(n, H, dtype=torch.float32, device=dev) for n in run.src_rows]
+        accs = [new(n, H, dtype=torch.float32) for n in run.src_rows]
+        for acc in accs:
+            ops.zero_(acc)
         skip0 = int(all(getattr(t, "_pmgt_row0_zero", False) for t in run.src))
         ops.embed_fuse_bwd(ops.embed_args(*eargs, row_idx=run.rows_idx, dev_acc=accs[0], det_acc=accs[1], skip_row0=skip0,
                                           **common))
@@ -558,18 +682,28 @@ class _EncodeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, host, src_v, src_t, rows_idx, mask, R, L, training, seed, arena, keep, *params):
         fp, pre, cfg = host._fp, host._fp_prefix, host.config
-        hidden, run = _encode_forward(fp, pre, cfg, [src_v, src_t], rows_idx, R, L, mask, training, seed, keep)
-        ctx.host, ctx.run, ctx.arena, ctx.n_params = host, run, arena, len(params)
+        plan = host._plan_for(fp, [src_v, src_t], rows_idx, R, L, training, keep, arena)
+        host._active_plan = plan
+        if plan is not None:
+            hidden, run = plan.forward(fp, pre, cfg, [src_v, src_t], rows_idx, mask, training, seed, keep), None
+        else:
+            hidden, run = _encode_forward(fp, pre, cfg, [src_v, src_t], rows_idx, R, L, mask, training, seed, keep)
+        ctx.host, ctx.run, ctx.arena, ctx.n_params, ctx.plan, ctx.keep = host, run, arena, len(params), plan, keep
         return hidden
 
     @staticmethod
     def backward(ctx, d_hidden):
-        host, run, arena = ctx.host, ctx.run, ctx.arena
-        if run is None:
-            raise PMGTError("encoder backward called but activations were not kept")
+        host, run, arena, plan = ctx.host, ctx.run, ctx.arena, ctx.plan
         fp, pre, cfg = host._fp, host._fp_prefix, host.config
-        _encode_backward(fp, pre, cfg, run, d_hidden, arena)
-        ctx.run = None
+        if plan is not None:
+            if not ctx.keep or not plan.pending_backward:
+                raise PMGTError("encoder backward called but the launch plan holds no activations for it")
+            plan.backward(fp, pre, cfg, d_hidden, arena)
+        else:
+            if run is None:
+                raise PMGTError("encoder backward called but activations were not kept")
+            _encode_backward(fp, pre, cfg, run, d_hidden, arena)
+            ctx.run = None
         grads = tuple(arena.view(n) for n in host._encoder_param_names)
         return (None,) * 11 + grads
 
@@ -632,6 +766,28 @@ class PMGTModel(PMGTPretrainedModel):
         self._fp = None
         self._fp_prefix = ""
         self._encoder_param_names = [n for n, _ in encoder_param_order(self)]
+        self.use_launch_plans = False  # opt-in: outputs of a planned pass alias plan-owned buffers (see _EncoderPlan)
+        self._plans = {}
+        self._active_plan = None
+
+    def _plan_for(self, fp, src, rows_idx, R, L, training, keep, arena) -> Optional["_EncoderPlan"]:
+        """The launch plan for this call, or None when plans are off or the call is not plannable (dense inputs,
+        a transient gradient arena, or a forward whose backward is still outstanding on the same plan)."""
+        if not self.use_launch_plans or rows_idx is None or (keep and not getattr(arena, "persistent", False)):
+            return None
+        cfg = self.config
+        key = (R, L, bool(training), bool(keep), float(cfg.hidden_dropout_prob), float(cfg.attention_probs_dropout_prob),
+               tuple((t.data_ptr(), tuple(t.shape)) for t in src), fp.flat.data_ptr(), fp.flat_bf16.data_ptr(),
+               arena.get().data_ptr() if keep else 0, ops.cur_stream(), PROJECTION_MODE)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 4:  # e.g. full batch, tail batch, eval batch; drop the oldest beyond that
+                self._plans.pop(next(iter(self._plans)))
+            plan = _EncoderPlan(key, R, L, cfg.hidden_size, rows_idx.device)
+            self._plans[key] = plan
+        elif plan.pending_backward:
+            return None
+        return plan
 
     # -- flat storage: standalone use owns its own FlatParams; inside PMGT the parent's is shared
     def _attach(self, fp: FlatParams, prefix: str):

@@ -31,17 +31,22 @@ class _TakeRows(torch.autograd.Function):
     """rows = hidden_flat[idx]; backward scatters into one zero buffer (idx unique)."""
 
     @staticmethod
-    def forward(ctx, hidden_flat, idx):
+    def forward(ctx, hidden_flat, idx, grad_buf=None):
         ctx.save_for_backward(idx)
         ctx.shape = hidden_flat.shape
+        ctx.grad_buf = grad_buf  # launch plans: build the gradient in the buffer the recorded backward pass reads
         return hidden_flat.index_select(0, idx)
 
     @staticmethod
     def backward(ctx, g):
         (idx,) = ctx.saved_tensors
-        out = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
+        out = ctx.grad_buf
+        if out is not None and out.shape == ctx.shape and out.dtype == g.dtype:
+            out.zero_()
+        else:
+            out = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
         out.index_copy_(0, idx, g)
-        return out, None
+        return out, None, None
 
 
 class PMGT(PMGTPretrainedModel):
@@ -126,8 +131,9 @@ class PMGT(PMGTPretrainedModel):
             self._tables_bf16, self._tables_key = out, key
         return self._tables_bf16
 
-    def mask_nodes(self, node_ids: torch.Tensor):
-        """models.py:131-151, same RNG consumption order (rand, randint, rand)."""
+    def mask_nodes(self, node_ids: torch.Tensor, with_positions: bool = False):
+        """models.py:131-151, same RNG consumption order (rand, randint, rand).  ``with_positions`` appends the
+        (row, position-1) index pairs of the masked slots, so that ``forward`` needs no host sync of its own."""
         device = node_ids.device
         masked_input_ids = node_ids.clone()
         shape = masked_input_ids.size()
@@ -138,6 +144,8 @@ class PMGT(PMGTPretrainedModel):
         mask = (rand < self.mask_node_ratio) * (masked_input_ids[:, 1:] != 0)
         target_idx = masked_input_ids[:, 1:][mask]
         masked_input_ids[:, 1:][mask] = 1  # Fill mask index
+        if with_positions:
+            return masked_input_ids, mask, target_idx, mask.nonzero(as_tuple=False)
         return masked_input_ids, mask, target_idx
 
     # ------------------------------------------------------------------
@@ -167,7 +175,13 @@ class PMGT(PMGTPretrainedModel):
         fp = self._flat()
         fp.refresh_bf16()
         tables = self.feature_tables_bf16()
-        arena = GradArena(fp)
+        # launch plans need the gradients of every step at the same address; the persistent arena is only safe while
+        # no gradient of an earlier step is still attached (zero_grad(set_to_none=True) between steps)
+        if (self.bert.use_launch_plans and torch.is_grad_enabled() and all(p.grad is None for p in fp.params)
+                and not any(pl.pending_backward for pl in self.bert._plans.values())):
+            arena = fp.step_arena()
+        else:
+            arena = GradArena(fp)
 
         ids = [t_ids]
         masks = [t_mask]
@@ -182,12 +196,12 @@ class PMGT(PMGTPretrainedModel):
                 nfr_on = True
                 if masked_inputs is None:
                     masked_inputs = self.mask_nodes(t_ids)
-                m_ids, m_mask, target_idx = masked_inputs
+                m_ids, m_mask, target_idx = masked_inputs[:3]
                 ids.append(m_ids)
                 masks.append(t_mask)
                 # data-dependent shapes are resolved HERE, before the encoder is enqueued: nonzero() synchronises
                 # the stream, and a sync after the encoder launch would drain the whole launch pipeline
-                m_pos = m_mask.nonzero(as_tuple=False)  # (Mm, 2): row, position-1
+                m_pos = masked_inputs[3] if len(masked_inputs) > 3 else m_mask.nonzero(as_tuple=False)  # (Mm, 2): row, position-1
         ids_all = ids[0] if len(ids) == 1 else torch.cat(ids, dim=0)
         mask_all = masks[0] if len(masks) == 1 else torch.cat(masks, dim=0)
         R = ids_all.shape[0]
@@ -204,7 +218,9 @@ class PMGT(PMGTPretrainedModel):
             tok = [torch.arange(0, (B + SP) * L, L, device=dev)]
             if nfr_on:
                 tok.append((B + SP + m_pos[:, 0]) * L + m_pos[:, 1] + 1)
-            rows = _TakeRows.apply(hidden.view(R * L, H), torch.cat(tok) if len(tok) > 1 else tok[0])
+            plan = self.bert._active_plan
+            rows = _TakeRows.apply(hidden.view(R * L, H), torch.cat(tok) if len(tok) > 1 else tok[0],
+                                   plan.grad_buffer() if plan is not None and hidden.requires_grad else None)
             pair_off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
             torch.cumsum(num_pairs.to(dev), 0, out=pair_off[1:])
             gsr_loss, prediction_logits = self.gsr_loss.batched(rows[:B], rows[B: B + SP], pair_off,

@@ -188,6 +188,8 @@ class PMGTTrainerModel:
         self.optimizer = get_optimizer(args)
         self.global_step = 0
         self._sumsq = None
+        self._side = None        # high-priority stream the next step's batch is prepared on
+        self._prefetched = None  # (dataset, indices, epoch, batch, masked, ready-event)
 
     # -- inference: net(x)[0][:, 0] (trainer.py:153-154)
     def forward(self, x):
@@ -203,13 +205,57 @@ class PMGTTrainerModel:
         loss, logits, labels = outputs[0], outputs[1], batch[-1]
         return loss, logits.sigmoid().cpu().numpy(), labels.cpu().numpy()
 
+    # -- the batch of a LATER step, prepared while the current step is still running on the device
+    def prefetch(self, dataset: PMGTDataset, indices, epoch: int) -> None:
+        """Sample the contexts of ``indices`` and draw their NFR corruption on a side stream.
+
+        The corruption (models.py:131-151) has data-dependent shapes, i.e. host syncs; issued here they wait for the
+        small side stream only, while the main stream still holds the queued kernels of the current step.  The next
+        ``train_on_indices`` call with the same ``(dataset, indices, epoch)`` picks the result up; anything else
+        discards it.  The torch generator is consumed once per step in the reference's order either way.
+        """
+        dev = self.args.device
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev, priority=-1)
+        # No wait on the main stream (that would serialise us behind the very step we want to overlap): host indices
+        # are copied on the side stream; device-resident indices must already be complete.
+        with torch.cuda.stream(self._side):
+            idx = indices if isinstance(indices, torch.Tensor) else torch.as_tensor(np.asarray(indices))
+            idx = idx.to(dev, non_blocking=True)
+            batch = dataset.sample_batch(idx, epoch=epoch)
+            masked = None
+            if dataset.is_training:
+                masked = self.net.mask_nodes(batch[0]["node_ids"], with_positions=True)
+            ready = torch.cuda.Event()
+            ready.record(self._side)
+        self._prefetched = (dataset, indices, epoch, batch, masked, ready)
+
+    def _take_prefetched(self, dataset, indices, epoch):
+        pf, self._prefetched = self._prefetched, None
+        if pf is None or pf[0] is not dataset or pf[1] is not indices or pf[2] != epoch:
+            return None
+        _, _, _, batch, masked, ready = pf
+        main = torch.cuda.current_stream(self.args.device)
+        main.wait_event(ready)
+        for t in (batch[0]["node_ids"], batch[0]["attention_mask"], batch[1]["node_ids"], batch[1]["attention_mask"],
+                  batch[2], batch[3], *masked):
+            t.record_stream(main)  # allocated on the side stream, consumed on the main one
+        return batch, masked
+
     # -- one optimisation step on a sampled batch (sample -> fwd -> bwd -> allreduce -> AdamW)
     def train_on_indices(self, dataset: PMGTDataset, indices, epoch: int) -> torch.Tensor:
         args = self.args
-        self.net.train()
-        batch = dataset.sample_batch(indices, epoch=epoch)
+        if not self.net.training:
+            self.net.train()
+        self.net.bert.use_launch_plans = True  # fixed-shape steps: record the encoder's launch list once, then replay
+        pf = self._take_prefetched(dataset, indices, epoch)
         self.optimizer.zero_grad(set_to_none=True)
-        loss = self.training_step(batch)
+        if pf is not None:
+            batch, masked = pf
+            loss = self.net(*batch, masked_inputs=masked)[0]
+        else:
+            batch = dataset.sample_batch(indices, epoch=epoch)
+            loss = self.training_step(batch)
         loss.backward()
         rank, ws = world()
         scale = 1.0
@@ -295,8 +341,11 @@ def train(args: AttrDict, is_hptuning: bool = False, trial=None, enable_trial_pr
         perm = epoch_permutation(len(ds), args.seed, epoch)
         t0 = time.time()
         running = []
+        shards = [shard_indices(perm, step, B, rank, ws) for step in range(steps_per_epoch)]
         for step in range(steps_per_epoch):
-            loss = tm.train_on_indices(ds, shard_indices(perm, step, B, rank, ws), epoch)
+            loss = tm.train_on_indices(ds, shards[step], epoch)
+            if step + 1 < steps_per_epoch:
+                tm.prefetch(ds, shards[step + 1], epoch)  # sampling + corruption of the next batch overlap this step
             running.append(loss)
         train_loss = float(torch.stack(running).mean())
         val = tm.evaluate(args.valid_dataset, args.test_batch_size)

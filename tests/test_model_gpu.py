@@ -234,3 +234,75 @@ def test_training_reduces_loss_with_dropout():
         losses.append(float(loss))
     assert all(l == l for l in losses), losses
     assert sum(losses[-3:]) < sum(losses[:3]), losses
+
+
+@pytest.mark.parametrize("projection", ["gather", "table"])
+def test_launch_plan_replay_matches_the_unplanned_path(projection, monkeypatch):
+    """Recorded-and-replayed encoder launches (PMGTModel.use_launch_plans) must give the same losses and gradients
+    as issuing every launch from Python, step after step (dropout on: the per-step seed is patched into the tape)."""
+    from pmgt_b200 import PMGT, PMGTConfig, PMGTDataset, modeling_pmgt, synthetic
+    monkeypatch.setattr(modeling_pmgt, "PROJECTION_MODE", projection)
+    g = synthetic.make_item_graph((400, 3000), seed=1)
+    feats = synthetic.make_features(g.num_nodes, seed=3)
+    ds = PMGTDataset(g, seed=0)
+    results = []
+    for planned in (False, True):
+        torch.manual_seed(0)
+        modeling_pmgt._seed_counter[0] = 0
+        net = PMGT(g.num_nodes, config=PMGTConfig(num_hidden_layers=2), feat_init_emb=feats).cuda().train()
+        net.bert.use_launch_plans = planned
+        steps = []
+        for step in range(4):
+            batch = ds.sample_batch(torch.arange(0, 96), epoch=step)
+            for p in net.parameters():
+                p.grad = None
+            out = net(*batch)
+            out.loss.backward()
+            steps.append((float(out.loss), out.prediction_logits.clone(), out.last_hidden_state.clone(),
+                          {n: p.grad.clone() for n, p in net.named_parameters() if p.requires_grad}))
+        if planned:
+            plans = list(net.bert._plans.values())
+            assert len(plans) == 1 and plans[0].fwd_tape and plans[0].bwd_tape, "the plan was not used"
+        results.append(steps)
+    for (l0, lg0, h0, g0), (l1, lg1, h1, g1) in zip(*results):
+        assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
+        assert torch.equal(h0, h1), "hidden states differ"
+        assert float((lg0 - lg1).abs().max()) <= 1e-5
+        for n in g0:  # fp32 atomics reorder between runs: not bit-exact, but far below bf16 resolution
+            d = float((g0[n] - g1[n]).abs().max())
+            assert d <= 1e-3 * float(g0[n].abs().max()) + 1e-7, (n, d)
+
+
+def test_launch_plan_outputs_and_fallbacks():
+    """Plans are opt-in; a second forward while a backward is outstanding falls back to the unplanned path; eval-mode
+    (no-grad) passes get their own plan and agree with the unplanned result."""
+    from pmgt_b200 import PMGT, PMGTConfig, PMGTDataset, synthetic
+    g = synthetic.make_item_graph((300, 2000), seed=2)
+    feats = synthetic.make_features(g.num_nodes, seed=4)
+    torch.manual_seed(1)
+    net = PMGT(g.num_nodes, config=PMGTConfig(num_hidden_layers=1, hidden_dropout_prob=0.0,
+                                              attention_probs_dropout_prob=0.0), feat_init_emb=feats).cuda().train()
+    ds = PMGTDataset(g, seed=0)
+    batch = ds.sample_batch(torch.arange(0, 64), epoch=0)
+    torch.manual_seed(5)
+    masked = net.mask_nodes(batch[0]["node_ids"])
+    ref = net(*batch, masked_inputs=masked)
+    assert not net.bert._plans, "plans must be opt-in"
+    ref.loss.backward()
+    ref_grad = net.bert.encoder.layer[0].output.dense.weight.grad.clone()
+    for p in net.parameters():
+        p.grad = None
+    net.bert.use_launch_plans = True
+    a = net(*batch, masked_inputs=masked)      # records
+    b = net(*batch, masked_inputs=masked)      # backward of `a` outstanding -> unplanned fallback, `a` stays intact
+    assert abs(float(a.loss) - float(ref.loss)) <= 1e-6 and abs(float(b.loss) - float(ref.loss)) <= 1e-6
+    a.loss.backward()
+    got = net.bert.encoder.layer[0].output.dense.weight.grad
+    assert float((got - ref_grad).abs().max()) <= 1e-3 * float(ref_grad.abs().max())
+    net.eval()
+    with torch.no_grad():
+        e1 = net(batch[0])[0].clone()
+        e2 = net(batch[0])[0].clone()   # replayed
+        net.bert.use_launch_plans = False
+        e3 = net(batch[0])[0]
+    assert torch.equal(e1, e2) and torch.equal(e1, e3)

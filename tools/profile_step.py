@@ -33,6 +33,7 @@ n = len(ds)
 idx = [torch.from_numpy(np.resize(trainer.epoch_permutation(n, 0, s), a.batch).astype(np.int64)).to(dev) for s in range(a.steps + 3)]
 for s in range(3):
     tm.train_on_indices(ds, idx[s], epoch=s)
+    tm.prefetch(ds, idx[s + 1], epoch=s + 1)
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
@@ -41,6 +42,8 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     e0.record()
     for s in range(3, 3 + a.steps):
         tm.train_on_indices(ds, idx[s], epoch=s)
+        if s + 1 < 3 + a.steps:
+            tm.prefetch(ds, idx[s + 1], epoch=s + 1)
     e1.record()
     torch.cuda.synchronize()
 wall = e0.elapsed_time(e1) / a.steps
