@@ -730,6 +730,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 int embed128_supported(const pmgt_embed_args* a);
 int embed128_fwd(const pmgt_embed_args* a, cudaStream_t st);
 int embed128_bwd(const pmgt_embed_args* a, cudaStream_t st);
+int ln_bwd_stream(const pmgt_lnbwd_args* a, cudaStream_t st);  // ln_bwd_stream.cu
 
 static int persistent_grid(long long work_warps, int warps_per_cta, int ctas_per_sm) {
   long long need = (work_warps + warps_per_cta - 1) / warps_per_cta;
@@ -827,6 +828,10 @@ int pmgt_ln_bwd(const pmgt_lnbwd_args* a, void* stream) {
   PMGT_REQUIRE(a->dropout_p == 0.f || (a->d_o && a->d_o != a->dz), "pmgt_ln_bwd: dropout needs a separate d_o buffer");
   PMGT_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "pmgt_ln_bwd: bad dropout_p");
   if (a->T == 0) return PMGT_OK;
+  {
+    const int rc = ln_bwd_stream(a, (cudaStream_t)stream);  // bulk-copy-staged version; 1 = combination not covered
+    if (rc != 1) return rc;
+  }
   long long ctas = (a->T + 31) / 32;
   const long long cap = (long long)num_sms() * 8;
   if (ctas > cap) ctas = cap;

@@ -103,37 +103,52 @@ sample_contexts_kernel(const SamplerParams p) {
       const uint32_t n_k = n_prev * s;
       const uint32_t hop_w = (uint32_t)(p.depth - k + 1);
       const bool store = k < p.depth;
-      const uint32_t q_lo = base >> 2, q_hi = (base + n_k - 1) >> 2;
-      for (uint32_t q = q_lo + tid; q <= q_hi; q += kSamplerThreads) {
-        Philox4 r = philox4x32_10(q, PMGT_STREAM_CTX, key_lo, key_hi, p.seed_lo, p.seed_hi);
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const uint32_t gd = (q << 2) + w;
-          if (gd < base || gd >= base + n_k) continue;
-          const uint32_t d = gd - base;
-          const uint32_t ppos = d / s;
-          const int32_t parent = (k == 1) ? (root_ok ? root : 0) : prev[ppos];
-          int32_t nb = 0;
-          if (parent != 0) {
-            const int64_t rs = __ldg(p.indptr + parent);
-            const int deg = (int)(__ldg(p.indptr + parent + 1) - rs);
-            if (d - ppos * s == 0) my_deg += (unsigned long long)deg;
-            if (deg > 0) {
-              const float u = (float)(philox_word(r, w) >> 8) * (1.0f / 16777216.0f);
-              const int pos = upper_bound_cdf(p.cdf + rs, deg, u);
-              nb = __ldg(p.indices + rs + pos);
-            }
+      // one draw: parent row -> inverse-CDF position -> neighbour -> score table
+      auto draw = [&](uint32_t gd, uint32_t word) {
+        const uint32_t d = gd - base;
+        const uint32_t ppos = d / s;
+        const int32_t parent = (k == 1) ? (root_ok ? root : 0) : prev[ppos];
+        int32_t nb = 0;
+        if (parent != 0) {
+          const int64_t rs = __ldg(p.indptr + parent);
+          const int deg = (int)(__ldg(p.indptr + parent + 1) - rs);
+          if (d - ppos * s == 0) my_deg += (unsigned long long)deg;
+          if (deg > 0) {
+            const float u = (float)(word >> 8) * (1.0f / 16777216.0f);
+            const int pos = upper_bound_cdf(p.cdf + rs, deg, u);
+            nb = __ldg(p.indices + rs + pos);
           }
-          if (store) cur[d] = nb;
-          if (nb != 0 && nb != root) {
-            uint32_t slot = ((uint32_t)nb * 2654435761u) >> p.table_shift;
-            while (true) {
-              int32_t old = atomicCAS(&tkeys[slot], 0, nb);
-              if (old == 0 || old == nb) break;
-              slot = (slot + 1) & (uint32_t)(p.table_cap - 1);
-            }
-            atomicAdd(&tscore[slot], hop_w);
-            atomicMax(&tfirst[slot], 0xffffffffu - gd);
+        }
+        if (store) cur[d] = nb;
+        if (nb != 0 && nb != root) {
+          uint32_t slot = ((uint32_t)nb * 2654435761u) >> p.table_shift;
+          while (true) {
+            int32_t old = atomicCAS(&tkeys[slot], 0, nb);
+            if (old == 0 || old == nb) break;
+            slot = (slot + 1) & (uint32_t)(p.table_cap - 1);
+          }
+          atomicAdd(&tscore[slot], hop_w);
+          atomicMax(&tfirst[slot], 0xffffffffu - gd);
+        }
+      };
+      if (n_k <= (uint32_t)kSamplerThreads) {
+        // early hops (16 and 128 draws with the default sizes): one THREAD per draw.  Up to four threads recompute the
+        // same Philox block, but the dependent-load chain of every draw (row pointer -> CDF search -> neighbour ->
+        // table) runs in parallel instead of four deep per thread; these hops were barrier-stall bound.
+        if ((uint32_t)tid < n_k) {
+          const uint32_t gd = base + (uint32_t)tid;
+          const Philox4 r = philox4x32_10(gd >> 2, PMGT_STREAM_CTX, key_lo, key_hi, p.seed_lo, p.seed_hi);
+          draw(gd, philox_word(r, (int)(gd & 3u)));
+        }
+      } else {
+        const uint32_t q_lo = base >> 2, q_hi = (base + n_k - 1) >> 2;
+        for (uint32_t q = q_lo + tid; q <= q_hi; q += kSamplerThreads) {
+          const Philox4 r = philox4x32_10(q, PMGT_STREAM_CTX, key_lo, key_hi, p.seed_lo, p.seed_hi);
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const uint32_t gd = (q << 2) + w;
+            if (gd < base || gd >= base + n_k) continue;
+            draw(gd, philox_word(r, w));
           }
         }
       }

@@ -125,6 +125,30 @@ def test_ln_bwd(T):
     _close(db, bb.grad, 5e-3, "d_b")
 
 
+@pytest.mark.parametrize("T", [1, 63, 64, 77, 5000, 20011])
+@pytest.mark.parametrize("combo", ["a", "ab", "b", "f32"])
+def test_ln_bwd_streamed_variants(T, combo):
+    """The bulk-copy-staged kernel covers (dy_a), (dy_a + dy_b), (dy_b) and (dy_f32) -- the combinations the encoder
+    issues; ragged tails (T % 64 != 0) must not read the stale part of a stage."""
+    ops = _ops()
+    z = _r(T, 128)
+    dya = _r(T, 128) if "a" in combo else None
+    dyb = _r(T, 128) if "b" in combo else None
+    dy32 = torch.randn(T, 128, device="cuda") if combo == "f32" else None
+    g = 1 + 0.1 * torch.randn(128, device="cuda")
+    zf = z.float().requires_grad_(True)
+    gg = g.clone().requires_grad_(True)
+    bb = torch.zeros(128, device="cuda", requires_grad=True)
+    total = sum(t.float() for t in (dya, dyb, dy32) if t is not None)
+    F.layer_norm(zf, (128,), gg, bb, 1e-12).backward(total)
+    dz = torch.empty_like(z)
+    dg, db = torch.zeros(128, device="cuda"), torch.zeros(128, device="cuda")
+    ops.ln_bwd(T, 128, z, g, 1e-12, 0.0, 0, 0, dz, dz, dg, db, dy_a=dya, dy_b=dyb, dy_f32=dy32)
+    _close(dz, zf.grad, name="dz")
+    _close(dg, gg.grad, 5e-3, "d_g")
+    _close(db, bb.grad, 5e-3, "d_b")
+
+
 def test_res_ln_dropout_matches_ln_bwd_mask():
     """The RES_LN epilogue and pmgt_ln_bwd must regenerate the same Philox mask: with x = 0 and bias = 1 the
     dense output is 1 everywhere, so z - res is 0 exactly where the forward dropped."""
