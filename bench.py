@@ -41,6 +41,18 @@ def parse():
     return ap.parse_args()
 
 
+def load_traffic(workload, batch):
+    """Measured DRAM bytes per launch of each kernel family (one ncu --set full capture, summarised in profiles/)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return {}
+    with open(p) as f:
+        d = json.load(f)
+    if d.get("workload") != workload or d.get("targets_per_gpu_per_step") != batch:
+        return {}
+    return d.get("traffic_bytes_per_launch", {})
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -260,9 +272,11 @@ def ours(a):
     n_prof = min(3, a.steps)
     if rank == 0:
         ops.PROFILE = []
-    # (no side-stream prefetch here: every kernel is timed alone on the launching stream)
+    # (no side-stream prefetch and no programmatic dependent launch here: every kernel is timed alone)
+    pdl_was = ops.set_pdl(False)
     run_steps(idx_dev, a.warmup, n_prof, prefetch=False)
     barrier()
+    ops.set_pdl(pdl_was)
     if rank == 0:
         recs, ops.PROFILE = ops.PROFILE, None
         prof = ops.profile_summary(recs)
@@ -283,7 +297,8 @@ def ours(a):
             per_ctx = float(vdeg.float().mean()) * 8 + 145 * 8 + 6 * 12
             d["gbs"] = per_ctx * contexts_per_step / ws / (d["ms_per_step"] * 1e-3) / 1e9
         roof = {"kernel": top, "bound": "hbm", "achieved": d["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": d["gbs"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                "frac": d["gbs"] / peaks["hbm_gbs"], "traffic": load_traffic(a.workload, B).get(top),
+                "algorithmic_bytes_per_launch": d["bytes"] / d["calls"], "peak_source": peaks["source"],
                 "share_of_step": d["share"], "launches_per_step": d["calls"] / n_prof,
                 "avg_launch_us": 1e3 * d["ms"] / d["calls"], "tensor_tflops": d["tflops"]}
         if a.profile_out:

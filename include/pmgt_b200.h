@@ -39,9 +39,17 @@ typedef enum pmgt_status {
 } pmgt_status;
 
 /* ABI version of this header; bumped on any signature change. */
-#define PMGT_B200_ABI_VERSION 2
+#define PMGT_B200_ABI_VERSION 3
 int pmgt_abi_version(void);
 const char* pmgt_last_error(void);
+
+/*
+ * Programmatic dependent launch of the encoder's kernel chain (token-tile GEMMs, dW, LayerNorm backward, attention
+ * core): on by default (environment PMGT_PDL=0 turns it off at load time).  Returns the previous setting.  Timing
+ * single kernels with events is only meaningful with it off, because a dependent kernel's prologue then overlaps
+ * its predecessor's tail.
+ */
+int pmgt_set_pdl(int enabled);
 
 /* ------------------------------------------------------------------------ */
 /* Item graph (CSR)                                                          */

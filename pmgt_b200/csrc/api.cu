@@ -1,6 +1,7 @@
 // Library-wide plumbing of libpmgt_b200.so: thread-local error string, ABI
 // version, cached device properties.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -29,9 +30,26 @@ int num_sms() {
   return cached;
 }
 
+static int g_pdl = -1;
+
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("PMGT_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl == 1;
+}
+
+int set_pdl(int enabled) {
+  const int prev = pdl_enabled() ? 1 : 0;
+  g_pdl = enabled ? 1 : 0;
+  return prev;
+}
+
 }  // namespace pmgt
 
 extern "C" {
 int pmgt_abi_version(void) { return PMGT_B200_ABI_VERSION; }
 const char* pmgt_last_error(void) { return pmgt::g_err; }
+int pmgt_set_pdl(int enabled) { return pmgt::set_pdl(enabled); }
 }

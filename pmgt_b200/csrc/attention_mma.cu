@@ -265,8 +265,10 @@ __global__ void __launch_bounds__(AttnRing<L, DH, 4>::kWarps * 32, 1) attn_mma_f
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned char* wbuf = smem + (size_t)wib * Ring::kPerWarp;
   unsigned char* zero = wbuf + S * Ring::kItem;
+  pdl_launch_dependents();
   for (int i = lane * 16; i < Ring::kZero; i += 32 * 16) *reinterpret_cast<uint4*>(zero + i) = make_uint4(0, 0, 0, 0);
   __syncwarp();
+  pdl_wait();
   const int H = a.H, heads = a.heads;
   const long long ld = 4ll * H;
   const long long n_items = a.rows * heads;
@@ -338,8 +340,10 @@ __global__ void __launch_bounds__(AttnRing<L, DH, 5>::kWarps * 32, 1) attn_mma_b
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned char* wbuf = smem + (size_t)wib * Ring::kPerWarp;
   unsigned char* zero = wbuf + S * Ring::kItem;
+  pdl_launch_dependents();
   for (int i = lane * 16; i < Ring::kZero; i += 32 * 16) *reinterpret_cast<uint4*>(zero + i) = make_uint4(0, 0, 0, 0);
   __syncwarp();
+  pdl_wait();
   const int H = a.H, heads = a.heads;
   const long long ld = 4ll * H;
   const long long n_items = a.rows * heads;
@@ -456,9 +460,10 @@ static int launch_mma(const pmgt_attn_args* a, cudaStream_t st) {
   const long long per_sm = (227 * 1024) / smem;
   const long long cap = (long long)num_sms() * (per_sm < 1 ? 1 : per_sm);
   if (ctas > cap) ctas = cap;
-  if (BWD) attn_mma_bwd_kernel<L, DH><<<(unsigned)ctas, kWarps * 32, smem, st>>>(*a);
-  else attn_mma_fwd_kernel<L, DH><<<(unsigned)ctas, kWarps * 32, smem, st>>>(*a);
-  PMGT_LAUNCH_CHECK();
+  if (BWD)
+    PMGT_CHECK_CUDA(launch_kernel(true, attn_mma_bwd_kernel<L, DH>, dim3((unsigned)ctas), dim3(kWarps * 32), smem, st, *a));
+  else
+    PMGT_CHECK_CUDA(launch_kernel(true, attn_mma_fwd_kernel<L, DH>, dim3((unsigned)ctas), dim3(kWarps * 32), smem, st, *a));
   return PMGT_OK;
 }
 

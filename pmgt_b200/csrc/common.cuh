@@ -42,6 +42,35 @@ void set_error(const char* fmt, ...);
 int num_sms();  // SM count of the current device (cached)
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch.  The encoder is a chain of ~170 short persistent kernels; launched the ordinary
+// way, each one pays launch latency + its own prologue (barrier init, TMEM allocation, tensor-map fetch) + the idle
+// tail of its predecessor (CTAs that ran one tile fewer).  With the stream-serialization attribute a kernel's CTAs
+// are scheduled as soon as the predecessor's CTAs have all started and SM resources free up, run their prologue,
+// and block in pdl_wait() until the predecessor has completed and its writes are visible.  Rules: every kernel
+// launched through launch_kernel(pdl = true) executes pdl_wait() in EVERY thread before its first global-memory
+// access, and calls pdl_launch_dependents() at its start.  PMGT_PDL=0 turns the attribute off.
+// ---------------------------------------------------------------------------
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  The same function is restated in
 // plain C in oracle/philox_sampler.c; the two must agree bit for bit.
 // ---------------------------------------------------------------------------

@@ -126,6 +126,7 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   LtBars* bars = reinterpret_cast<LtBars*>(smem + Lay::kBar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();  // the next kernel's CTAs may take an SM as soon as this grid's CTAs leave it
 
   if (threadIdx.x == 0) {
     mbar_init(&bars->w_full, 1);
@@ -159,6 +160,7 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();  // everything above overlapped the predecessor's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -421,6 +423,7 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant_
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   DwBars* bars = reinterpret_cast<DwBars*>(smem + kBar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < 4; ++s) {
       mbar_init(&bars->x_full[s], 1);
@@ -445,6 +448,7 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   const bool has_tiles = (int)blockIdx.x < p.num_tiles;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -599,8 +603,7 @@ static int launch_lt(const pmgt_linear_tile_args* a, cudaStream_t st) {
   p.out_f32 = a->out_f32;
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
-  kern<<<grid, kLtThreads, Lay::kTotal, st>>>(tx, tw, te, to, ta, p);
-  PMGT_LAUNCH_CHECK();
+  PMGT_CHECK_CUDA(launch_kernel(true, kern, dim3(grid), dim3(kLtThreads), Lay::kTotal, st, tx, tw, te, to, ta, p));
   return PMGT_OK;
 }
 
@@ -624,8 +627,7 @@ static int launch_dw(const pmgt_dw_tile_args* a, cudaStream_t st) {
   p.dw = a->dw; p.ld_dw = a->ld_dw; p.dbias = a->dbias;
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
-  kern<<<grid, 192, smem, st>>>(tdy, tx, p);
-  PMGT_LAUNCH_CHECK();
+  PMGT_CHECK_CUDA(launch_kernel(true, kern, dim3(grid), dim3(192), smem, st, tdy, tx, p));
   return PMGT_OK;
 }
 

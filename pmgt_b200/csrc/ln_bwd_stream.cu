@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kThreadsLn, 1) ln_bwd_stream_kernel(const pmgt
   extern __shared__ __align__(128) unsigned char smem[];
   LnBars* bars = reinterpret_cast<LnBars*>(smem + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bars->full[s], 1);
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(kThreadsLn, 1) ln_bwd_stream_kernel(const pmgt
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();
   const long long T = a.T;
   const long long n_chunks = (T + kRows - 1) / kRows;
 
@@ -212,8 +214,7 @@ int launch(const pmgt_lnbwd_args* a, const uint16_t* g0, const uint16_t* g1, cud
   long long chunks = (a->T + kRows - 1) / kRows;
   int grid = num_sms();
   if (grid > chunks) grid = (int)chunks;
-  kern<<<grid, kThreadsLn, smem, st>>>(*a, g0, g1);
-  PMGT_LAUNCH_CHECK();
+  PMGT_CHECK_CUDA(launch_kernel(true, kern, dim3(grid), dim3(kThreadsLn), smem, st, *a, g0, g1));
   return PMGT_OK;
 }
 

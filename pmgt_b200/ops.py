@@ -58,6 +58,11 @@ def replay(tape):
     LAUNCHES[0] += n
 
 
+def set_pdl(enabled: bool) -> bool:
+    """Programmatic dependent launch of the encoder's kernel chain on/off; returns the previous setting."""
+    return bool(_lib.lib().pmgt_set_pdl(int(bool(enabled))))
+
+
 def zero_(t):
     """``t.zero_()`` that a tape can replay (a torch memset on the current stream; not counted as one of our launches)."""
     def fn():
