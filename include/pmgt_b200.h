@@ -39,7 +39,7 @@ typedef enum pmgt_status {
 } pmgt_status;
 
 /* ABI version of this header; bumped on any signature change. */
-#define PMGT_B200_ABI_VERSION 3
+#define PMGT_B200_ABI_VERSION 4
 int pmgt_abi_version(void);
 const char* pmgt_last_error(void);
 
@@ -300,6 +300,12 @@ typedef struct pmgt_linear_tile_args {
   const float* ln_g; const float* ln_b; float ln_eps;
   float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
   float* out_f32;                           /* RES_LN only, optional, [T][N] fp32 */
+  /* Fused weight gradient of the SAME Linear (dX calls only: PLAIN / GELU_BWD with w_mn = 1, K = N = 128): when dw is
+   * non-NULL the call also accumulates dw[K][ld_dw] += x^T dw_x  (x = the dY operand of this call, dw_x = the
+   * Linear's forward input, [T][128] bf16) and dbias[K] += column sums of x (optional).  One pass over dY serves
+   * dX, dW and dbias. */
+  const uint16_t* dw_x; int64_t ld_dw_x;
+  float* dw; int64_t ld_dw; float* dbias;
 } pmgt_linear_tile_args;
 
 int pmgt_linear_tile_supported(int64_t K, int64_t N, int w_mn, int epi);

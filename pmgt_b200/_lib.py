@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmgt_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib = None
 
@@ -98,6 +98,8 @@ class LinearTileArgs(C.Structure):
         ("ln_g", c_vp), ("ln_b", c_vp), ("ln_eps", C.c_float),
         ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("dropout_site", C.c_uint32),
         ("out_f32", c_vp),
+        ("dw_x", c_vp), ("ld_dw_x", C.c_int64),
+        ("dw", c_vp), ("ld_dw", C.c_int64), ("dbias", c_vp),
     ]
 
 

@@ -28,6 +28,7 @@ constexpr int kSlabBytes = 16384;
 constexpr int kAccSlots = 4;
 constexpr int kEpiWarps = 16;                     // 4 TMEM lane quarters x 4 column quarters (32 columns per thread)
 constexpr int kLtThreads = 96 + 32 * kEpiWarps;   // producer | MMA | store | 16 epilogue warps
+constexpr int kDwWarps = 4;                       // fused dX + dW variant: column sums of dY, then the dW flush
 
 enum { LT_BIAS = PMGT_LT_BIAS, LT_GELU = PMGT_LT_GELU, LT_RES_LN = PMGT_LT_RES_LN, LT_PLAIN = PMGT_LT_PLAIN,
        LT_GELU_BWD = PMGT_LT_GELU_BWD };
@@ -42,6 +43,9 @@ struct LtParams {
   uint64_t seed;
   uint32_t site;
   float* out_f32;
+  float* dw;          // fused dW (DW variants): [N][ld_dw] fp32, accumulated
+  long long ld_dw;
+  float* dbias;       // [N] fp32, accumulated, may be NULL
 };
 
 // 16-byte chunk c8 (8 columns) of row r of an image
@@ -66,24 +70,27 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
          ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-template <int NC, int KC, int EPI, int SA, int SE, int NSTG>
+template <int NC, int KC, int EPI, int SA, int SE, int NSTG, int SX = 0>
 struct LtLayout {
   static constexpr bool kHasE = (EPI == LT_RES_LN || EPI == LT_GELU_BWD);
   static constexpr int kNOut = (EPI == LT_GELU) ? 2 : 1;
   static constexpr int kW = 0;
   static constexpr int kA = kW + NC * KC * kImgBytes;
-  static constexpr int kE = kA + SA * kImgBytes;
+  static constexpr int kX = kA + SA * kImgBytes;          // SX > 0: second activation stream (the dW operand)
+  static constexpr int kE = kX + SX * kImgBytes;
   static constexpr int kStg = kE + (kHasE ? SE : 0) * kImgBytes;
   static constexpr int kBar = kStg + NSTG * kNOut * kImgBytes;
-  static constexpr int kTotal = kBar + 256 + 1024;  // barriers + alignment slack
+  static constexpr int kTotal = kBar + 256 + 1024;        // barriers + alignment slack
 };
 
 struct LtBars {
   uint64_t w_full;
-  uint64_t a_full[4], a_empty[4];
-  uint64_t e_full[4], e_empty[4];
+  uint64_t a_full[3], a_empty[3];
+  uint64_t e_full[2], e_empty[2];
   uint64_t acc_full[kAccSlots], acc_empty[kAccSlots];
   uint64_t stg_full[2], stg_empty[2];
+  uint64_t x_full[2], x_empty[2];
+  uint64_t dw_done;
   uint32_t tmem_base;
 };
 static_assert(sizeof(LtBars) <= 256, "barrier block");
@@ -112,16 +119,24 @@ __device__ __forceinline__ void unpack8f(const uint4& u, float* v) {
 //   warps 3-18  epilogue: warp w reads TMEM lanes 32*(w%4).. (its hardware quarter) and columns 32*((w-3)/4)..,
 //               i.e. one row x 32 columns per thread.  Sixteen warps (instead of four per block) are what keeps the
 //               issue slots busy: the epilogue math (GELU, LayerNorm, Philox dropout) was the limiter, not HBM.
-template <int NC, int KC, bool B_MN, int EPI, int SA, int SE, int NSTG>
-__global__ void __launch_bounds__(kLtThreads, 1)
+template <int NC, int KC, bool B_MN, int EPI, int SA, int SE, int NSTG, int SX>
+__global__ void __launch_bounds__(kLtThreads + (SX > 0 ? 32 * kDwWarps : 0), 1)
 linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_out,
                    const __grid_constant__ CUtensorMap tm_aux, const LtParams p) {
-  using Lay = LtLayout<NC, KC, EPI, SA, SE, NSTG>;
+  using Lay = LtLayout<NC, KC, EPI, SA, SE, NSTG, SX>;
   constexpr bool kHasE = Lay::kHasE;
   constexpr int kNOut = Lay::kNOut;
+  // DW: the dX kernels of a Linear also form its weight gradient.  The dY tile already in shared memory is the K-major
+  // operand of dX = dY W and, read MN-major, the operand of dW += dY^T X; X (the Linear's input) arrives as a second
+  // TMA stream (tensor map passed in the tm_aux slot), dW accumulates in the last 128 TMEM columns over all tiles of
+  // the CTA and is flushed once, four extra warps form the bias gradient from the staged dY images.
+  constexpr bool DW = SX > 0;
+  constexpr int kSlots = DW ? kAccSlots - 1 : kAccSlots;
   static_assert(!kHasE || NC == 1, "epilogue-input variants are single-chunk");
   static_assert(NSTG == 1 || NSTG == 2, "one or two staging buffers");
+  static_assert(SA <= 3 && SE <= 2 && SX <= 2, "barrier arrays");
+  static_assert(!DW || (B_MN && NC == 1 && KC == 1 && (EPI == LT_PLAIN || EPI == LT_GELU_BWD)), "dW fusion: dX kernels only");
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   LtBars* bars = reinterpret_cast<LtBars*>(smem + Lay::kBar);
@@ -130,26 +145,29 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
   if (threadIdx.x == 0) {
     mbar_init(&bars->w_full, 1);
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < 3; ++s) {
       mbar_init(&bars->a_full[s], 1);
-      mbar_init(&bars->a_empty[s], 1);
+      mbar_init(&bars->a_empty[s], DW ? 1 + kDwWarps : 1);  // MMA commit (+ one arrival per column-sum warp)
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->e_full[s], 1);
       mbar_init(&bars->e_empty[s], EPI == LT_RES_LN ? 1 : kEpiWarps);
+      mbar_init(&bars->stg_full[s], kEpiWarps);
+      mbar_init(&bars->stg_empty[s], 1);
+      mbar_init(&bars->x_full[s], 1);
+      mbar_init(&bars->x_empty[s], 1);
     }
     for (int s = 0; s < kAccSlots; ++s) {
       mbar_init(&bars->acc_full[s], 1);
       mbar_init(&bars->acc_empty[s], kEpiWarps);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars->stg_full[s], kEpiWarps);
-      mbar_init(&bars->stg_empty[s], 1);
-    }
+    mbar_init(&bars->dw_done, 1);
     fence_barrier_init();
     prefetch_tmap(&tm_x);
     prefetch_tmap(&tm_w);
     prefetch_tmap(&tm_out);
     if (kHasE) prefetch_tmap(&tm_e);
-    if (EPI == LT_GELU || EPI == LT_RES_LN) prefetch_tmap(&tm_aux);
+    if (EPI == LT_GELU || EPI == LT_RES_LN || DW) prefetch_tmap(&tm_aux);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
@@ -173,7 +191,8 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           tma_load_2d(dst, &tm_w, &bars->w_full, col0, row0);
           tma_load_2d(dst + kSlabBytes, &tm_w, &bars->w_full, col0 + 64, row0);
         }
-      uint32_t ia = 0, ie = 0;
+      uint32_t ia = 0, ie = 0, ix = 0;
+      (void)ix;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < KC; ++kc, ++ia) {
           const int s = ia % SA;
@@ -182,6 +201,15 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           const uint32_t dst = smem_u32(smem + Lay::kA + s * kImgBytes);
           tma_load_2d(dst, &tm_x, &bars->a_full[s], kc * 128, tile * 128);
           tma_load_2d(dst + kSlabBytes, &tm_x, &bars->a_full[s], kc * 128 + 64, tile * 128);
+        }
+        if (DW) {
+          const int s = ix % (SX > 0 ? SX : 1);
+          mbar_wait(&bars->x_empty[s], ((ix / (SX > 0 ? SX : 1)) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&bars->x_full[s], (uint32_t)kImgBytes);
+          const uint32_t dst = smem_u32(smem + Lay::kX + s * kImgBytes);
+          tma_load_2d(dst, &tm_aux, &bars->x_full[s], 0, tile * 128);
+          tma_load_2d(dst + kSlabBytes, &tm_aux, &bars->x_full[s], 64, tile * 128);
+          ++ix;
         }
         if (kHasE) {
           const int s = ie % SE;
@@ -200,7 +228,8 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       constexpr uint32_t idesc = make_idesc(false, B_MN);
       mbar_wait(&bars->w_full, 0u);
       tcgen05_fence_after();
-      uint32_t ia = 0, item = 0;
+      uint32_t ia = 0, item = 0, ix = 0;
+      (void)ix;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, item += NC) {
         for (int kc = 0; kc < KC; ++kc, ++ia) {
           const int s = ia % SA;
@@ -208,18 +237,30 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           tcgen05_fence_after();
           const uint32_t a_img = smem_u32(smem + Lay::kA + s * kImgBytes);
           for (int n = 0; n < NC; ++n) {
-            const uint32_t it = item + n, slot = it % kAccSlots;
+            const uint32_t it = item + n, slot = it % kSlots;
             if (kc == 0) {
-              mbar_wait(&bars->acc_empty[slot], ((it / kAccSlots) & 1u) ^ 1u);
+              mbar_wait(&bars->acc_empty[slot], ((it / kSlots) & 1u) ^ 1u);
               tcgen05_fence_after();
             }
             const uint32_t b_img = smem_u32(smem + Lay::kW + (kc * NC + n) * kImgBytes);
             mma_128x128x128(tmem_base + slot * 128u, a_img, false, b_img, B_MN, idesc, kc > 0);
             if (kc == KC - 1) umma_commit(&bars->acc_full[slot]);
           }
+          if (DW) {
+            // dW[128 x 128] += dY^T (M = dY columns, K = tokens) * X (K = tokens, N = X columns): both MN-major
+            constexpr uint32_t idesc_dw = make_idesc(true, true);
+            const int sx = ix % (SX > 0 ? SX : 1);
+            mbar_wait(&bars->x_full[sx], (ix / (SX > 0 ? SX : 1)) & 1u);
+            tcgen05_fence_after();
+            const uint32_t x_img = smem_u32(smem + Lay::kX + sx * kImgBytes);
+            mma_128x128x128(tmem_base + (uint32_t)(kSlots * 128), a_img, true, x_img, true, idesc_dw, ix > 0);
+            umma_commit(&bars->x_empty[sx]);
+            ++ix;
+          }
           umma_commit(&bars->a_empty[s]);
         }
       }
+      if (DW) umma_commit(&bars->dw_done);
     }
   } else if (warp == 2) {
     // ===================== store warp =====================
@@ -253,7 +294,7 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       }
       tma_store_wait_all0();
     }
-  } else {
+  } else if (warp < 3 + kEpiWarps) {
     // ===================== epilogue warps =====================
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
     const int cq = (warp - 3) >> 2;             // column quarter
@@ -263,8 +304,8 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int n = 0; n < NC; ++n, ++it) {
-        const uint32_t slot = it % kAccSlots;
-        mbar_wait(&bars->acc_full[slot], (it / kAccSlots) & 1u);
+        const uint32_t slot = it % kSlots;
+        mbar_wait(&bars->acc_full[slot], (it / kSlots) & 1u);
         tcgen05_fence_after();
         float v[32];
         {
@@ -378,6 +419,58 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->stg_full[buf]);
+      }
+    }
+  } else if (DW) {
+    // ===================== column sums of dY, then the dW flush =====================
+    const int t = threadIdx.x - kLtThreads;   // 0..127
+    const int cg = t & 15, rg = t >> 4;       // 8 columns x 16 rows per thread
+    float cs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = 0.f;
+    uint32_t ia = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ia) {
+      const int s = ia % SA;
+      mbar_wait(&bars->a_full[s], (ia / SA) & 1u);
+      if (p.dbias) {
+        const unsigned char* img = smem + Lay::kA + s * kImgBytes;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          float f[8];
+          unpack8f(*reinterpret_cast<const uint4*>(img + img_off(rg * 16 + i, cg)), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cs[j] += f[j];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->a_empty[s]);
+    }
+    mbar_wait(&bars->dw_done, 0u);  // every MMA of this CTA has completed: the X slots are idle, dW is final
+    tcgen05_fence_after();
+    if (p.dbias) {
+      float* red = reinterpret_cast<float*>(smem + Lay::kX);  // [8][128]
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[rg * 128 + cg * 8 + j] = cs[j];
+      named_bar_sync(2, 32 * kDwWarps);
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) v += red[g * 128 + t];
+      if (v != 0.f) atomicAdd(p.dbias + t, v);
+    }
+    {
+      const int quarter = warp & 3;
+      const int r = quarter * 32 + lane;
+      float* dst = p.dw + (long long)r * p.ld_dw;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kSlots * 128 + c0), acc);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(acc[j])),
+                       "f"(__uint_as_float(acc[j + 1])), "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3]))
+                       : "memory");
       }
     }
   }
@@ -572,11 +665,11 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant_
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-template <int NC, int KC, bool B_MN, int EPI, int SA, int SE, int NSTG>
+template <int NC, int KC, bool B_MN, int EPI, int SA, int SE, int NSTG, int SX = 0>
 static int launch_lt(const pmgt_linear_tile_args* a, cudaStream_t st) {
-  using Lay = LtLayout<NC, KC, EPI, SA, SE, NSTG>;
+  using Lay = LtLayout<NC, KC, EPI, SA, SE, NSTG, SX>;
   static_assert(Lay::kTotal <= 232448, "shared memory budget (227 KiB)");
-  auto kern = linear_tile_kernel<NC, KC, B_MN, EPI, SA, SE, NSTG>;
+  auto kern = linear_tile_kernel<NC, KC, B_MN, EPI, SA, SE, NSTG, SX>;
   static bool configured = false;
   if (!configured) {
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay::kTotal));
@@ -594,6 +687,7 @@ static int launch_lt(const pmgt_linear_tile_args* a, cudaStream_t st) {
   if (Lay::kHasE && (rc = make_tmap(&te, a->e_in, a->N, a->T, a->ld_e, 64, 128))) return rc;
   if ((EPI == LT_GELU || EPI == LT_RES_LN) && (rc = make_tmap(&ta, a->aux_out, a->N, a->T, a->ld_aux_out, 64, 128)))
     return rc;
+  if (SX > 0 && (rc = make_tmap(&ta, a->dw_x, 128, a->T, a->ld_dw_x, 64, 128))) return rc;  // the dW operand stream
   LtParams p;
   p.T = (int)a->T;
   p.num_tiles = (int)((a->T + 127) / 128);
@@ -601,9 +695,11 @@ static int launch_lt(const pmgt_linear_tile_args* a, cudaStream_t st) {
   p.bias = a->bias; p.ln_g = a->ln_g; p.ln_b = a->ln_b; p.ln_eps = a->ln_eps;
   p.dropout_p = a->dropout_p; p.seed = a->dropout_seed; p.site = a->dropout_site;
   p.out_f32 = a->out_f32;
+  p.dw = a->dw; p.ld_dw = a->ld_dw; p.dbias = a->dbias;
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
-  PMGT_CHECK_CUDA(launch_kernel(true, kern, dim3(grid), dim3(kLtThreads), Lay::kTotal, st, tx, tw, te, to, ta, p));
+  PMGT_CHECK_CUDA(launch_kernel(true, kern, dim3(grid), dim3(kLtThreads + (SX > 0 ? 32 * kDwWarps : 0)), Lay::kTotal, st, tx,
+                                tw, te, to, ta, p));
   return PMGT_OK;
 }
 
@@ -659,6 +755,12 @@ int pmgt_linear_tile(const pmgt_linear_tile_args* a, void* stream) {
   PMGT_REQUIRE((((uintptr_t)a->x | (uintptr_t)a->w | (uintptr_t)a->out) & 15) == 0, "pmgt_linear_tile: 16-byte alignment");
   const int kc = a->K / 128, nc = a->N / 128;
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->dw) {
+    PMGT_REQUIRE((a->epi == PMGT_LT_PLAIN || a->epi == PMGT_LT_GELU_BWD) && a->w_mn && kc == 1 && nc == 1,
+                 "pmgt_linear_tile: the fused weight gradient needs a dX call (w_mn = 1) with K = N = 128");
+    PMGT_REQUIRE(a->dw_x && a->ld_dw_x % 8 == 0 && a->ld_dw % 4 == 0 && (((uintptr_t)a->dw_x | (uintptr_t)a->dw) & 15) == 0,
+                 "pmgt_linear_tile: dw_x / dw alignment");
+  }
   switch (a->epi) {
     case PMGT_LT_BIAS:
       PMGT_REQUIRE(a->bias, "pmgt_linear_tile: bias required");
@@ -674,9 +776,11 @@ int pmgt_linear_tile(const pmgt_linear_tile_args* a, void* stream) {
       return launch_lt<1, 1, false, LT_RES_LN, 2, 2, 2>(a, st);
     case PMGT_LT_PLAIN:
       if (kc == 4) return launch_lt<1, 4, true, LT_PLAIN, 2, 1, 1>(a, st);
+      if (a->dw) return launch_lt<1, 1, true, LT_PLAIN, 2, 1, 2, 2>(a, st);
       return launch_lt<1, 1, true, LT_PLAIN, 3, 1, 2>(a, st);
     case PMGT_LT_GELU_BWD:
       PMGT_REQUIRE(a->e_in && a->ld_e % 8 == 0, "pmgt_linear_tile: GELU_BWD needs the pre-activation (e_in)");
+      if (a->dw) return launch_lt<1, 1, true, LT_GELU_BWD, 2, 2, 1, 1>(a, st);
       return launch_lt<1, 1, true, LT_GELU_BWD, 2, 2, 2>(a, st);
   }
   set_error("pmgt_linear_tile: unknown epilogue %d", a->epi);

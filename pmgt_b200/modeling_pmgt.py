@@ -415,6 +415,9 @@ class _EncoderRun:
                  "p_att", "hidden_f32", "tile", "dense_tables")
 
 
+# dX kernels of the 128 x 128 Linears also produce dW / dbias (one pass over dY); False: separate pmgt_dw_tile launches
+FUSED_DW = True
+
 # "auto": projected tables when 4 * table rows <= tokens, else the gather-fused GEMM; "table" / "gather" force a mode
 PROJECTION_MODE = "auto"
 
@@ -578,23 +581,38 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
         ops.ln_bwd(T, H, z2, fp.f32(P + "output.LayerNorm.weight"), cfg.layer_norm_eps, p_hid, seed, site + 4, dz2, do2,
                    G(P + "output.LayerNorm.weight"), G(P + "output.LayerNorm.bias"), dy_a=dy, dy_b=dy_b, dy_f32=dy_f32)
         dy_f32 = None
-        ops.dw_tile(do2, h, G(P + "output.dense.weight"), G(P + "output.dense.bias"))
+        # each dX kernel of a 128 x 128 Linear also forms that Linear's dW / dbias from the dY tile it already holds
+        fused = FUSED_DW and H == 128 and I == 128
         dh_pre = new(T, I)
-        ops.linear_tile(do2, fp.bf16(P + "output.dense.weight"), dh_pre, ops.LT_GELU_BWD, w_mn=True, e_in=h_pre,
-                        tag="lt_dx_gelu")
+        if fused:
+            ops.linear_tile(do2, fp.bf16(P + "output.dense.weight"), dh_pre, ops.LT_GELU_BWD, w_mn=True, e_in=h_pre,
+                            dw_x=h, dw=G(P + "output.dense.weight"), dbias=G(P + "output.dense.bias"), tag="lt_dxdw_gelu")
+        else:
+            ops.dw_tile(do2, h, G(P + "output.dense.weight"), G(P + "output.dense.bias"))
+            ops.linear_tile(do2, fp.bf16(P + "output.dense.weight"), dh_pre, ops.LT_GELU_BWD, w_mn=True, e_in=h_pre,
+                            tag="lt_dx_gelu")
         # ---- BertIntermediate
-        ops.dw_tile(dh_pre, a, G(P + "intermediate.dense.weight"), G(P + "intermediate.dense.bias"))
         da = new(T, H)
-        ops.linear_tile(dh_pre, fp.bf16(P + "intermediate.dense.weight"), da, ops.LT_PLAIN, w_mn=True, tag="lt_dx")
+        if fused:
+            ops.linear_tile(dh_pre, fp.bf16(P + "intermediate.dense.weight"), da, ops.LT_PLAIN, w_mn=True, dw_x=a,
+                            dw=G(P + "intermediate.dense.weight"), dbias=G(P + "intermediate.dense.bias"), tag="lt_dxdw")
+        else:
+            ops.dw_tile(dh_pre, a, G(P + "intermediate.dense.weight"), G(P + "intermediate.dense.bias"))
+            ops.linear_tile(dh_pre, fp.bf16(P + "intermediate.dense.weight"), da, ops.LT_PLAIN, w_mn=True, tag="lt_dx")
         # ---- BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x); d a = da (FFN branch) + dz2 (residual branch)
         dz1 = new(T, H)
         do1 = new(T, H) if p_hid > 0 else dz1
         ops.ln_bwd(T, H, z1, fp.f32(P + "attention.output.LayerNorm.weight"), cfg.layer_norm_eps, p_hid, seed, site + 3,
                    dz1, do1, G(P + "attention.output.LayerNorm.weight"), G(P + "attention.output.LayerNorm.bias"),
                    dy_a=da, dy_b=dz2)
-        ops.dw_tile(do1, ctx, G(P + "attention.output.dense.weight"), G(P + "attention.output.dense.bias"))
         dctx = new(T, H)
-        ops.linear_tile(do1, fp.bf16(P + "attention.output.dense.weight"), dctx, ops.LT_PLAIN, w_mn=True, tag="lt_dx")
+        if fused:
+            ops.linear_tile(do1, fp.bf16(P + "attention.output.dense.weight"), dctx, ops.LT_PLAIN, w_mn=True, dw_x=ctx,
+                            dw=G(P + "attention.output.dense.weight"), dbias=G(P + "attention.output.dense.bias"),
+                            tag="lt_dxdw")
+        else:
+            ops.dw_tile(do1, ctx, G(P + "attention.output.dense.weight"), G(P + "attention.output.dense.bias"))
+            ops.linear_tile(do1, fp.bf16(P + "attention.output.dense.weight"), dctx, ops.LT_PLAIN, w_mn=True, tag="lt_dx")
         # ---- dual-softmax attention core, then the fused Q/K/V/C projection
         dqkvc = new(T, 4 * H)
         ops.attn_core_bwd(ops.attn_args(R, L, H, heads, float(cfg.beta), qkvc, run.mask, p_att, seed, site, dctx=dctx,

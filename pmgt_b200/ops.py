@@ -171,7 +171,7 @@ def dw_tile_supported(N, K) -> bool:
 
 
 def linear_tile(x, w, out, epi, *, w_mn=False, bias=None, aux_out=None, e_in=None, ln_g=None, ln_b=None, ln_eps=0.0,
-                p=0.0, seed=0, site=0, out_f32=None, tag=None):
+                p=0.0, seed=0, site=0, out_f32=None, dw_x=None, dw=None, dbias=None, tag=None):
     """``pmgt_linear_tile``: out[T,N] = epi(x[T,K] @ w^T) (w_mn=False, w [N,K]) or epi(x[T,K] @ w) (w_mn=True, w [K,N])."""
     _require_cuda(x, "x")
     T, K = x.shape
@@ -188,14 +188,20 @@ def linear_tile(x, w, out, epi, *, w_mn=False, bias=None, aux_out=None, e_in=Non
     a.ln_g, a.ln_b, a.ln_eps = ptr(ln_g), ptr(ln_b), ln_eps
     a.dropout_p, a.dropout_seed, a.dropout_site = p, seed, site
     a.out_f32 = ptr(out_f32)
+    a.dw_x, a.ld_dw_x = ptr(dw_x), (dw_x.stride(0) if dw_x is not None else 0)
+    a.dw, a.ld_dw, a.dbias = ptr(dw), (dw.stride(0) if dw is not None else 0), ptr(dbias)
     nbytes = 2 * T * K + 2 * K * N + 2 * T * N
+    flops = 2 * T * N * K
+    if dw is not None:  # fused weight gradient: one more activation stream, one more GEMM
+        nbytes += 2 * T * dw_x.shape[1] + 4 * K * dw_x.shape[1]
+        flops += 2 * T * K * dw_x.shape[1]
     if aux_out is not None:
         nbytes += 2 * T * N
     if e_in is not None:
         nbytes += 2 * T * N
     if out_f32 is not None:
         nbytes += 4 * T * N
-    _run(tag or "linear_tile", _lib.lib().pmgt_linear_tile, (C.byref(a), cur_stream()), 1, nbytes, 2 * T * N * K)
+    _run(tag or "linear_tile", _lib.lib().pmgt_linear_tile, (C.byref(a), cur_stream()), 1, nbytes, flops)
 
 
 def dw_tile(dy, x, dw_f32, dbias=None, tag="dw_tile"):

@@ -107,6 +107,34 @@ def test_dw(T, N):
     _close(dw2, dy.float().t() @ x.float(), 2e-3, name="dw (no bias)")
 
 
+@pytest.mark.parametrize("T", SIZES)
+@pytest.mark.parametrize("gelu", [False, True])
+def test_dx_with_fused_dw(T, gelu):
+    """dX call that also forms dW += dY^T X and dbias += colsum(dY) (pmgt_linear_tile with dw != NULL)."""
+    ops = _ops()
+    dy, x_in = _r(T, 128, s=0.5), _r(T, 128, s=0.5)
+    w = _r(128, 128, s=0.1)                      # nn.Linear weight [N = out][K = in]; dX = dY W
+    pre = _r(T, 128) if gelu else None
+    out = torch.empty(T, 128, device="cuda", dtype=BF16)
+    dw = torch.full((128, 128), 0.25, device="cuda")  # accumulates on top of what is there
+    db = torch.full((128,), -1.0, device="cuda")
+    ops.linear_tile(dy, w, out, ops.LT_GELU_BWD if gelu else ops.LT_PLAIN, w_mn=True, e_in=pre, dw_x=x_in, dw=dw, dbias=db)
+    want = dy.float() @ w.float()
+    if gelu:
+        p = pre.float().requires_grad_(True)
+        F.gelu(p).sum().backward()
+        want = want * p.grad
+    _close(out, want, name="dx")
+    _close(dw - 0.25, dy.float().t() @ x_in.float(), 2e-3, "dw")
+    _close(db + 1.0, dy.float().sum(0), 2e-3, "dbias")
+    # without dbias
+    dw2 = torch.zeros(128, 128, device="cuda")
+    out2 = torch.empty_like(out)
+    ops.linear_tile(dy, w, out2, ops.LT_GELU_BWD if gelu else ops.LT_PLAIN, w_mn=True, e_in=pre, dw_x=x_in, dw=dw2)
+    assert torch.equal(out, out2)
+    _close(dw2, dy.float().t() @ x_in.float(), 2e-3, "dw (no dbias)")
+
+
 @pytest.mark.parametrize("T", [77, 5000])
 def test_ln_bwd(T):
     ops = _ops()
