@@ -103,6 +103,8 @@ def test_pretrain_step_matches_reference_golden(golden_dir, name):
     (dict(hidden_size=32, num_hidden_layers=3, intermediate_size=32, beta=1.0), 16, 10, 6, 200),   # scripts/run_pmgt.sh
     (dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
           feat_hidden_sizes=[256, 128], mask_node_ratio=0.3), 8, 4, 33, 120),                     # wide-style: L = 33
+    (dict(hidden_size=768, num_hidden_layers=2, num_attention_heads=12, intermediate_size=3072,
+          mask_node_ratio=0.3), 4, 3, 33, 90),      # BASELINE config 5 dimensions (BERT-base widths, 32 neighbours)
 ])
 @pytest.mark.parametrize("projection", ["gather", "table"])
 def test_pretrain_step_matches_oracle_on_device(over, B, P, L, node_size, projection, monkeypatch):
@@ -333,9 +335,13 @@ def test_data_parallel_gradient_equivalence_on_one_device():
     assert abs(l_full - 0.5 * (l_a + l_b)) <= 1e-5 * abs(l_full)
     assert set(g_full) == set(g_a) == set(g_b)
     for n in g_full:
+        # bf16 rounding points differ (e.g. the per-table-row feature gradients are summed in fp32 over ALL tokens of a
+        # pass and rounded once): agreement is at bf16 resolution, not bit-exact
         want = 0.5 * (g_a[n] + g_b[n])
         d = float((g_full[n] - want).abs().max())
-        assert d <= 2e-3 * float(want.abs().max()) + 1e-7, (n, d)
+        assert d <= 1e-2 * float(want.abs().max()) + 1e-7, (n, d)
+        cos = float((g_full[n] * want).sum() / (g_full[n].norm() * want.norm()).clamp_min(1e-30))
+        assert cos >= 0.9999 or float(want.norm()) < 1e-7, (n, cos)
 
 
 def test_full_size_step_properties():
