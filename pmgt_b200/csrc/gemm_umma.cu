@@ -407,10 +407,12 @@ extern "C" int pmgt_gemm_bf16(const pmgt_gemm_args* a, void* stream) {
   dim3 grid((unsigned)((a->N + BN - 1) / BN), (unsigned)((a->M + BM - 1) / BM), (unsigned)split);
   PMGT_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "pmgt_gemm_bf16: grid too large (M tiles %u, split %u)", grid.y, grid.z);
   cudaStream_t st = (cudaStream_t)stream;
+  // 3 stages = 96 KiB of operand ring: TWO CTAs fit per SM, so one tile's prologue / epilogue overlaps the other's
+  // main loop (with 4 stages a single resident CTA left the SM idle during every tile's head and tail)
   const bool deep = kb_per > 2;
 
 #define PMGT_DISPATCH(AM, BMN, GA_, GB_)                                              \
-  return deep ? launch<AM, BMN, GA_, GB_, 4>(ta, tb, ka, grid, st) : launch<AM, BMN, GA_, GB_, 2>(ta, tb, ka, grid, st)
+  return deep ? launch<AM, BMN, GA_, GB_, 3>(ta, tb, ka, grid, st) : launch<AM, BMN, GA_, GB_, 2>(ta, tb, ka, grid, st)
   if (!a->a_mn && !a->b_mn && !ga) { PMGT_DISPATCH(false, false, false, false); }
   if (!a->a_mn && !a->b_mn && ga) { PMGT_DISPATCH(false, false, true, false); }
   if (!a->a_mn && a->b_mn && !ga && !gb) { PMGT_DISPATCH(false, true, false, false); }

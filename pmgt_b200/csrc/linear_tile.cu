@@ -301,6 +301,11 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const int r = quarter * 32 + lane;          // tile row == TMEM lane
     const int c0 = cq * 32;
     const float ks = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+    float ln_gm[8], ln_bt[8];  // LayerNorm affine of the 8 columns this lane owns in phase B of the RES_LN epilogue
+    if (EPI == LT_RES_LN) {
+      ld8f(p.ln_g + (lane & 15) * 8, ln_gm);
+      ld8f(p.ln_b + (lane & 15) * 8, ln_bt);
+    }
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int n = 0; n < NC; ++n, ++it) {
@@ -364,8 +369,8 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->e_empty[se]);  // pre-activation image consumed
         } else if (EPI == LT_RES_LN) {
-          float* scr = reinterpret_cast<float*>(stg0);      // row-statistics exchange lives in the (still unused) y staging image
-          float zsum = 0.f;
+          // phase A (row x 32 columns per thread, the TMEM layout): z = dropout(acc + bias) + residual, rounded to
+          // bf16 and written over the residual image in place
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (p.dropout_p > 0.f) {
@@ -379,34 +384,37 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             unpack8f(*zp, x);
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] += v[g * 8 + j];
-            const uint4 z = pack8f(x);
-            *zp = z;  // z replaces the residual in place (the chunk is private to this thread)
-            unpack8f(z, v + g * 8);  // LayerNorm over the bf16-rounded z (exactly what the backward pass re-reads)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) zsum += v[g * 8 + j];
+            *zp = pack8f(x);
           }
-          scr[cq * 128 + r] = zsum;
           named_bar_sync(1, 32 * kEpiWarps);
-          const float mean = (scr[r] + scr[128 + r] + scr[256 + r] + scr[384 + r]) * (1.f / 128.f);
-          float q = 0.f;
+          // phase B (half-warp per row, 8 rows per warp): LayerNorm over the bf16-rounded z (exactly what the backward
+          // pass re-reads) with the row statistics in four shuffles -- one block barrier per tile instead of an
+          // all-to-all exchange of partial sums, and the optional fp32 copy leaves as 512-byte-contiguous rows
+          const int hl = lane & 15, sub = lane >> 4;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
-          scr[512 + cq * 128 + r] = q;
-          named_bar_sync(1, 32 * kEpiWarps);
-          const float rstd =
-              rsqrtf((scr[512 + r] + scr[640 + r] + scr[768 + r] + scr[896 + r]) * (1.f / 128.f) + p.ln_eps);
-          named_bar_sync(1, 32 * kEpiWarps);  // every thread has read the exchange area: y may overwrite it
-          const bool f32_ok = p.out_f32 != nullptr && tok < p.T;
+          for (int i2 = 0; i2 < 4; ++i2) {
+            const int row = (warp - 3) * 8 + i2 * 2 + sub;
+            float zf[8];
+            unpack8f(*reinterpret_cast<const uint4*>(eimg + img_off(row, hl)), zf);
+            float sum = 0.f;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float gm[8], bt[8], y[8];
-            ld8f(p.ln_g + c0 + g * 8, gm);
-            ld8f(p.ln_b + c0 + g * 8, bt);
+            for (int j = 0; j < 8; ++j) sum += zf[j];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = (v[g * 8 + j] - mean) * rstd * gm[j] + bt[j];
-            *reinterpret_cast<uint4*>(stg0 + img_off(r, cq * 4 + g)) = pack8f(y);
-            if (f32_ok) {
-              float* o32 = p.out_f32 + tok * 128 + c0 + g * 8;
+            for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float mean = sum * (1.f / 128.f);
+            float q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { zf[j] -= mean; q = fmaf(zf[j], zf[j], q); }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            const float rstd = rsqrtf(q * (1.f / 128.f) + p.ln_eps);
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = zf[j] * rstd * ln_gm[j] + ln_bt[j];
+            *reinterpret_cast<uint4*>(stg0 + img_off(row, hl)) = pack8f(y);
+            const long long trow = (long long)tile * 128 + row;
+            if (p.out_f32 != nullptr && trow < p.T) {
+              float* o32 = p.out_f32 + trow * 128 + hl * 8;
               *reinterpret_cast<float4*>(o32) = make_float4(y[0], y[1], y[2], y[3]);
               *reinterpret_cast<float4*>(o32 + 4) = make_float4(y[4], y[5], y[6], y[7]);
             }

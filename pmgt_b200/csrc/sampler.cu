@@ -60,7 +60,10 @@ __device__ __forceinline__ int upper_bound_cdf(const float* __restrict__ cdf, in
 // SPT > 0: table_cap == SPT * 128 and max_ctx <= 8 -- the top-k keeps every thread's slots in registers, each warp
 // extracts its own max_ctx best without block barriers, and warp 0 merges the 4 * max_ctx finalists (one barrier
 // instead of two table scans and two barriers per output position).  SPT == 0: any table size / max_ctx.
-template <int SPT>
+// ILP: the late hops advance the four draws of a Philox block in lock-step (memory-level parallelism for graphs that
+// spill out of L2: every step of a draw's pointer chase is then an HBM round trip).  On L2-resident graphs the kernel
+// is issue-bound and the sequential form, with its smaller register footprint and higher occupancy, is faster.
+template <int SPT, bool ILP>
 __global__ void __launch_bounds__(kSamplerThreads)
 sample_contexts_kernel(const SamplerParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -139,6 +142,78 @@ sample_contexts_kernel(const SamplerParams p) {
           const uint32_t gd = base + (uint32_t)tid;
           const Philox4 r = philox4x32_10(gd >> 2, PMGT_STREAM_CTX, key_lo, key_hi, p.seed_lo, p.seed_hi);
           draw(gd, philox_word(r, (int)(gd & 3u)));
+        }
+      } else if constexpr (ILP) {
+        // late hops: one Philox block = four draws per thread, advanced in LOCK-STEP so that their dependent-load
+        // chains (row pointers -> CDF binary search -> neighbour id) overlap four deep instead of running one after
+        // the other; on graphs that do not fit in L2 every step of such a chain is an HBM round trip
+        const uint32_t q_lo = base >> 2, q_hi = (base + n_k - 1) >> 2;
+        for (uint32_t q = q_lo + tid; q <= q_hi; q += kSamplerThreads) {
+          const Philox4 r = philox4x32_10(q, PMGT_STREAM_CTX, key_lo, key_hi, p.seed_lo, p.seed_hi);
+          bool act[4];
+          uint32_t dd[4];
+          int32_t par[4];
+          int64_t rs[4];
+          int dg[4], lo[4], hi[4];
+          float uu[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const uint32_t gd = (q << 2) + w;
+            act[w] = gd >= base && gd < base + n_k;
+            dd[w] = gd - base;
+            par[w] = 0;
+            if (act[w]) par[w] = (k == 1) ? (root_ok ? root : 0) : prev[dd[w] / s];
+          }
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            rs[w] = 0;
+            dg[w] = 0;
+            if (par[w] != 0) {
+              rs[w] = __ldg(p.indptr + par[w]);
+              dg[w] = (int)(__ldg(p.indptr + par[w] + 1) - rs[w]);
+            }
+          }
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            if (par[w] != 0 && dd[w] % s == 0) my_deg += (unsigned long long)dg[w];
+            uu[w] = (float)(philox_word(r, w) >> 8) * (1.0f / 16777216.0f);
+            lo[w] = 0;
+            hi[w] = dg[w];
+          }
+          while ((lo[0] < hi[0]) | (lo[1] < hi[1]) | (lo[2] < hi[2]) | (lo[3] < hi[3])) {
+            float cv[4];
+            int mid[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              mid[w] = (lo[w] + hi[w]) >> 1;
+              cv[w] = lo[w] < hi[w] ? __ldg(p.cdf + rs[w] + mid[w]) : 0.f;
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+              if (lo[w] < hi[w]) {
+                if (cv[w] <= uu[w]) lo[w] = mid[w] + 1; else hi[w] = mid[w];
+              }
+          }
+          int32_t nb[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            nb[w] = dg[w] > 0 ? __ldg(p.indices + rs[w] + (lo[w] < dg[w] ? lo[w] : dg[w] - 1)) : 0;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            if (!act[w]) continue;
+            if (store) cur[dd[w]] = nb[w];
+            if (nb[w] != 0 && nb[w] != root) {
+              const uint32_t gd = (q << 2) + w;
+              uint32_t slot = ((uint32_t)nb[w] * 2654435761u) >> p.table_shift;
+              while (true) {
+                int32_t old = atomicCAS(&tkeys[slot], 0, nb[w]);
+                if (old == 0 || old == nb[w]) break;
+                slot = (slot + 1) & (uint32_t)(p.table_cap - 1);
+              }
+              atomicAdd(&tscore[slot], hop_w);
+              atomicMax(&tfirst[slot], 0xffffffffu - gd);
+            }
+          }
         }
       } else {
         const uint32_t q_lo = base >> 2, q_hi = (base + n_k - 1) >> 2;
@@ -429,11 +504,14 @@ int pmgt_sample_contexts(const pmgt_graph* gh, const int64_t* roots, const int64
   p.out_ids = out_ids; p.out_mask = out_mask; p.out_visited_deg = out_visited_deg;
   size_t smem = sizeof(int32_t) * (size_t)((2 * p.list_cap + 3) & ~3) + 12 * (size_t)cap;
   PMGT_CHECK_CUDA(cudaSetDevice(g->device));
-  void (*kern)(const SamplerParams) = sample_contexts_kernel<0>;
+  // CSR footprint (row pointers + neighbour ids + CDF) against the L2 capacity decides the late-hop strategy
+  const double csr_mb = ((double)g->num_edges * 8.0 + (double)g->num_nodes * 8.0) / 1.0e6;
+  const bool ilp = csr_mb > 48.0;
+  void (*kern)(const SamplerParams) = ilp ? sample_contexts_kernel<0, true> : sample_contexts_kernel<0, false>;
   if (max_ctx <= 8) {
-    if (cap == 4 * kSamplerThreads) kern = sample_contexts_kernel<4>;
-    else if (cap == 8 * kSamplerThreads) kern = sample_contexts_kernel<8>;
-    else if (cap == 16 * kSamplerThreads) kern = sample_contexts_kernel<16>;
+    if (cap == 4 * kSamplerThreads) kern = ilp ? sample_contexts_kernel<4, true> : sample_contexts_kernel<4, false>;
+    else if (cap == 8 * kSamplerThreads) kern = ilp ? sample_contexts_kernel<8, true> : sample_contexts_kernel<8, false>;
+    else if (cap == 16 * kSamplerThreads) kern = ilp ? sample_contexts_kernel<16, true> : sample_contexts_kernel<16, false>;
   }
   if (smem > 48 * 1024)
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

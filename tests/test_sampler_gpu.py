@@ -36,6 +36,21 @@ def test_contexts_bit_exact_vs_cpu_replay(hops, max_ctx):
     assert got[0].dtype == np.int64 and got[1].dtype == np.float32
 
 
+@pytest.mark.parametrize("hops,max_ctx", [([16, 8, 4], 5), ([6, 5, 4, 3], 7)])
+def test_contexts_bit_exact_on_a_graph_larger_than_l2(hops, max_ctx):
+    """A CSR above the L2-residency threshold (> 48 MB) switches the late hops to the lock-step variant (four draws of a
+    Philox block advanced together); it must replay bit for bit like the sequential one."""
+    g = synthetic.make_item_graph((150_000, 3_300_000), seed=11)   # 6.6 M directed entries -> ~54 MB of CSR
+    assert (len(g.indices) * 8 + g.num_nodes * 8) / 1e6 > 48.0
+    rng = np.random.default_rng(5)
+    roots = rng.integers(2, g.num_nodes + 2, size=600).astype(np.int64)
+    roots[:3] = [0, 1, g.num_nodes + 5]                            # invalid roots -> all-pad contexts
+    keys = (np.arange(len(roots), dtype=np.int64) << 8) | 1
+    got, want = _run_both(g, roots, keys, hops, max_ctx, seed=0xABCDEF)
+    for a, b, name in zip(got, want, ("ids", "mask", "visited_deg")):
+        assert np.array_equal(a, b), name
+
+
 def test_contexts_ragged_rows_and_padding():
     """TG-like sparse graph: many rows shorter than a hop's sample size -> padded contexts."""
     g = synthetic.make_item_graph((400, 420), seed=9)  # mean degree ~2
