@@ -188,6 +188,15 @@ class FlatParams:
     def ensure(self):
         """(Re)attach parameters to the flat buffer if ``.to()`` / ``.cuda()`` moved them."""
         p0 = self.params[0]
+        # fast path (every step): the first and the last parameter still sit where the flat buffer put them.  A move of
+        # the module (.to / .cuda) relocates all of them; anything subtler is caught by the full check below, which
+        # runs whenever either pointer changed.
+        if self.flat is not None:
+            base = self.flat.data_ptr()
+            pl = self.params[-1]
+            if (p0.data_ptr() == base + 4 * self.offsets[self.names[0]]
+                    and pl.data_ptr() == base + 4 * self.offsets[self.names[-1]]):
+                return self
         dev = p0.device
         if dev.type != "cuda":
             raise PMGTError("pmgt_b200 modules must live on a CUDA device (no CPU fallback); call .cuda() first")
@@ -818,7 +827,11 @@ class PMGTModel(PMGTPretrainedModel):
         return self._fp.ensure()
 
     def _encoder_params(self):
-        return [p for _, p in encoder_param_order(self)]
+        ps = self.__dict__.get("_encoder_params_cache")
+        if ps is None:  # Parameter objects keep their identity across .to() / load_state_dict
+            ps = [p for _, p in encoder_param_order(self)]
+            self.__dict__["_encoder_params_cache"] = ps
+        return ps
 
     def encode(self, src_v, src_t, rows_idx, mask, R, L, arena=None, refresh=True):
         fp = self._flat()

@@ -190,6 +190,8 @@ class PMGTTrainerModel:
         self._sumsq = None
         self._side = None        # high-priority stream the next step's batch is prepared on
         self._prefetched = None  # (dataset, indices, epoch, batch, masked, ready-event)
+        self._loss_pin = None    # pinned host scalar the step's loss is copied into right after the forward pass
+        self._loss_event = None
 
     # -- inference: net(x)[0][:, 0] (trainer.py:153-154)
     def forward(self, x):
@@ -256,6 +258,13 @@ class PMGTTrainerModel:
         else:
             batch = dataset.sample_batch(indices, epoch=epoch)
             loss = self.training_step(batch)
+        # the loss is final once the forward pass is: copy it out NOW (pinned buffer + event), so that reading it on the
+        # host (`last_loss`) waits for the forward kernels only, not for the backward pass and the optimizer behind them
+        if self._loss_pin is None:
+            self._loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
+            self._loss_event = torch.cuda.Event()
+        self._loss_pin.copy_(loss.detach(), non_blocking=True)
+        self._loss_event.record()
         loss.backward()
         rank, ws = world()
         scale = 1.0
@@ -282,6 +291,15 @@ class PMGTTrainerModel:
         self.optimizer.step(grad_scale=scale, grad_scale_dev=scale_dev)
         self.global_step += 1
         return loss.detach()
+
+    def last_loss(self) -> float:
+        """Host value of the most recent ``train_on_indices`` loss (device -> pinned-host copy issued right after the
+        forward pass; this call waits for that copy only).  ``float(loss)`` on the returned tensor gives the same number
+        but drains the whole stream first."""
+        if self._loss_event is None:
+            raise RuntimeError("last_loss() before the first train_on_indices()")
+        self._loss_event.synchronize()
+        return float(self._loss_pin)
 
     @torch.no_grad()
     def evaluate(self, dataset: PMGTDataset, batch_size: int) -> Dict[str, float]:

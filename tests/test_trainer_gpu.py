@@ -78,3 +78,31 @@ def test_inference_export_and_downstream_remap(tmp_path):
     assert np.allclose(np.linalg.norm(out, axis=1), 1.0, atol=1e-5)
     want = emb[n - 1] / np.linalg.norm(emb[n - 1])
     assert np.allclose(out[0], want, atol=1e-6)
+
+
+def test_prefetch_and_early_loss_readback(tmp_path):
+    """`prefetch` (next batch sampled + corrupted on the side stream) must give the step the same batch it would have
+    sampled itself, and `last_loss()` (pinned copy issued after the forward pass) the same number as float(loss)."""
+    from pmgt_b200 import trainer
+    losses = {}
+    for use_prefetch in (False, True):
+        args = _args(tmp_path, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        trainer.init_run(args)
+        trainer.init_dataloader(args)
+        trainer.init_model(args)
+        tm = trainer.PMGTTrainerModel(args)
+        ds = args.train_dataset
+        shards = [np.arange(s * 64, (s + 1) * 64) for s in range(4)]
+        out = []
+        for s in range(4):
+            loss = tm.train_on_indices(ds, shards[s], epoch=7)
+            if use_prefetch and s + 1 < 4:
+                tm.prefetch(ds, shards[s + 1], epoch=7)
+            host = tm.last_loss()
+            assert host == float(loss)
+            out.append(host)
+        losses[use_prefetch] = out
+    # no dropout; the NFR corruption consumes the torch generator once per step in the same order either way
+    # -> the two runs are the same computation up to fp32 atomic ordering
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) <= 1e-4 * abs(a), (losses[False], losses[True])

@@ -1,23 +1,47 @@
-import os, sys, time, numpy as np, torch
+"""Host-side cost of a step in the end-to-end loop (sync every step): cProfile of `train_on_indices` + `prefetch`."""
+import cProfile
+import os
+import pstats
+import sys
+import time
+
+import numpy as np
+import torch
+
 sys.path.insert(0, os.getcwd())
 from pmgt_b200 import trainer
+
 dev = torch.device("cuda", 0)
-args = trainer.make_args(synthetic="TG", train_batch_size=4096, seed=0); args.device = dev
+args = trainer.make_args(synthetic="TG", train_batch_size=4096, seed=0)
+args.device = dev
 trainer.set_seed(0)
 args.graph, args.feat_init_emb = trainer._load_graph_and_features(args)
-trainer.init_dataloader(args); trainer.init_model(args)
-tm = trainer.PMGTTrainerModel(args); ds = args.train_dataset
-idx = [torch.from_numpy(np.resize(trainer.epoch_permutation(len(ds), 0, s), 4096).astype(np.int64)).to(dev) for s in range(13)]
-for s in range(3): tm.train_on_indices(ds, idx[s], epoch=s)
+trainer.init_dataloader(args)
+trainer.init_model(args)
+tm = trainer.PMGTTrainerModel(args)
+ds = args.train_dataset
+N = 40
+idx = [torch.from_numpy(np.resize(trainer.epoch_permutation(len(ds), 0, s), 4096).astype(np.int64)).pin_memory() for s in range(N + 1)]
+
+
+def loop(lo, hi):
+    for s in range(lo, hi):
+        loss = tm.train_on_indices(ds, idx[s], epoch=s)
+        tm.prefetch(ds, idx[s + 1], epoch=s + 1)
+        float(loss)
+
+
+loop(0, 5)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-for s in range(3, 13): tm.train_on_indices(ds, idx[s], epoch=s)
-t1 = time.perf_counter()
+loop(5, 20)
 torch.cuda.synchronize()
-t2 = time.perf_counter()
-print(f"host issue {1e2*(t1-t0):.2f} ms/step, total {1e2*(t2-t0):.2f} ms/step")
-import cProfile, pstats
-pr = cProfile.Profile(); pr.enable()
-for s in range(3, 8): tm.train_on_indices(ds, idx[s], epoch=s)
-pr.disable(); torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(35)
+print(f"e2e-style loop: {1e3 * (time.perf_counter() - t0) / 15:.3f} ms/step")
+pr = cProfile.Profile()
+pr.enable()
+loop(20, 35)
+pr.disable()
+torch.cuda.synchronize()
+st = pstats.Stats(pr)
+st.sort_stats("tottime").print_stats(28)
+st.sort_stats("cumulative").print_stats(30)
