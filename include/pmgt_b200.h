@@ -281,6 +281,9 @@ int pmgt_res_ln_bwd(const pmgt_resln_args* a, void* stream);
  *       PMGT_LT_GELU_BWD  out = (x w) * gelu_erf'(e_in)                          (w_mn = 1)
  *   w_mn = 0: w is [N][K] (nn.Linear weight, y = x w^T); w_mn = 1: w is [K][N] (dx = dy w, same storage).
  *   Dropout element index = token * N + column (the same stream pmgt_ln_bwd regenerates).
+ *   With programmatic dependent launch on (default, see pmgt_set_pdl) the weight tiles are fetched while the preceding
+ *   kernel of the stream may still be running: `w` must not be written by the kernels launched immediately before
+ *   this call (activations x / e_in are read only after the predecessor has completed).
  */
 #define PMGT_LT_BIAS 0
 #define PMGT_LT_GELU 1

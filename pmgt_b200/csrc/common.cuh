@@ -108,32 +108,49 @@ __host__ __device__ __forceinline__ uint32_t philox_word(const Philox4& p, int i
   return i == 0 ? p.x : (i == 1 ? p.y : (i == 2 ? p.z : p.w));
 }
 
-// Dropout stream.  One Philox4x32-10 call covers the 8 consecutive elements of block idx >> 3: counter
-// (block_lo, block_hi, site, 0x5eed), key = seed; element j = idx & 7 uses the 16-bit field j of the 128-bit
-// output (word j >> 1, half j & 1) and is KEPT when field >= round(p * 65536).  The caller scales kept values
-// by 1 / (1 - p).  Every kernel (forward and the backward pass that regenerates the mask) goes through these
-// helpers, so the masks agree by construction.
+// Dropout stream: a counter-based hash, not Philox.  The element index is split into a block of 8 consecutive elements
+// (idx >> 3) and a lane j = idx & 7; block b under key (seed, site) expands to four 32-bit words
+//     w_i = fmix32((4 b + i) ^ k1) ^ k2,   i = 0..3      (fmix32 = the MurmurHash3 finaliser, a bijection of 2^32)
+// and element j uses the 16-bit field j of the 128 bits (word j >> 1, half j & 1); it is KEPT when field >=
+// round(p * 65536); the caller scales kept values by 1 / (1 - p).  The LayerNorm epilogues are issue-bound and spent
+// ~45 % of their instructions in Philox4x32-10 (ten rounds for 8 elements); a dropout mask needs decorrelated bits,
+// not a Crush-resistant generator -- the sampler, whose stream must be replayable bit for bit, stays on Philox.
+// Every kernel (forward and the backward pass that regenerates the mask) goes through these helpers, so the masks
+// agree by construction.
 __device__ __forceinline__ uint32_t dropout_threshold(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+
+__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
 
 // keep bits of the 8 elements idx8 .. idx8 + 7 (idx8 a multiple of 8): bit j = keep element idx8 + j
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t site, uint64_t idx8, float p) {
   const uint64_t blk = idx8 >> 3;
-  const Philox4 r = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), site, 0x5eedu, (uint32_t)seed,
-                                  (uint32_t)(seed >> 32));
+  // per-(seed, site) keys: loop-invariant, hoisted by the compiler
+  const uint32_t k1 = fmix32((uint32_t)seed ^ (site * 0x9E3779B9u) ^ 0x5eedu);
+  const uint32_t k2 = fmix32((uint32_t)(seed >> 32) + site) ^ ((uint32_t)(blk >> 30) * 0x9E3779B9u);
+  const uint32_t c = (uint32_t)blk << 2;
+  const uint32_t w0 = fmix32((c + 0u) ^ k1) ^ k2, w1 = fmix32((c + 1u) ^ k1) ^ k2;
+  const uint32_t w2 = fmix32((c + 2u) ^ k1) ^ k2, w3 = fmix32((c + 3u) ^ k1) ^ k2;
   const uint32_t thr = dropout_threshold(p);
   uint32_t m = 0;
-  m |= ((r.x & 0xffffu) >= thr) ? 1u : 0u;
-  m |= ((r.x >> 16) >= thr) ? 2u : 0u;
-  m |= ((r.y & 0xffffu) >= thr) ? 4u : 0u;
-  m |= ((r.y >> 16) >= thr) ? 8u : 0u;
-  m |= ((r.z & 0xffffu) >= thr) ? 16u : 0u;
-  m |= ((r.z >> 16) >= thr) ? 32u : 0u;
-  m |= ((r.w & 0xffffu) >= thr) ? 64u : 0u;
-  m |= ((r.w >> 16) >= thr) ? 128u : 0u;
+  m |= ((w0 & 0xffffu) >= thr) ? 1u : 0u;
+  m |= ((w0 >> 16) >= thr) ? 2u : 0u;
+  m |= ((w1 & 0xffffu) >= thr) ? 4u : 0u;
+  m |= ((w1 >> 16) >= thr) ? 8u : 0u;
+  m |= ((w2 & 0xffffu) >= thr) ? 16u : 0u;
+  m |= ((w2 >> 16) >= thr) ? 32u : 0u;
+  m |= ((w3 & 0xffffu) >= thr) ? 64u : 0u;
+  m |= ((w3 >> 16) >= thr) ? 128u : 0u;
   return m;
 }
 
-// single element (row-wise kernels call it for 4 consecutive elements of one block; the Philox call is shared)
+// single element (row-wise kernels call it for 4 consecutive elements of one block; the hash is shared)
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint64_t idx, float p) {
   return (dropout_keep8(seed, site, idx & ~(uint64_t)7, p) >> (uint32_t)(idx & 7)) & 1u;
 }

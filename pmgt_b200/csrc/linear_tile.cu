@@ -168,6 +168,18 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     prefetch_tmap(&tm_out);
     if (kHasE) prefetch_tmap(&tm_e);
     if (EPI == LT_GELU || EPI == LT_RES_LN || DW) prefetch_tmap(&tm_aux);
+    // The resident weight images are requested BEFORE the dependency wait: weights (the bf16 shadow written once per
+    // step by the cast kernel) are never produced by the kernels that immediately precede this one in the chain, so
+    // their load latency overlaps the predecessor's tail.  Callers that rewrite `w` right before this call must turn
+    // programmatic dependent launch off (pmgt_set_pdl).
+    mbar_arrive_expect_tx(&bars->w_full, (uint32_t)(NC * KC * kImgBytes));
+    for (int kc = 0; kc < KC; ++kc)
+      for (int n = 0; n < NC; ++n) {
+        const uint32_t dst = smem_u32(smem + Lay::kW + (kc * NC + n) * kImgBytes);
+        const int row0 = B_MN ? kc * 128 : n * 128, col0 = B_MN ? n * 128 : kc * 128;
+        tma_load_2d(dst, &tm_w, &bars->w_full, col0, row0);
+        tma_load_2d(dst + kSlabBytes, &tm_w, &bars->w_full, col0 + 64, row0);
+      }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
@@ -183,14 +195,6 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->w_full, (uint32_t)(NC * KC * kImgBytes));
-      for (int kc = 0; kc < KC; ++kc)
-        for (int n = 0; n < NC; ++n) {
-          const uint32_t dst = smem_u32(smem + Lay::kW + (kc * NC + n) * kImgBytes);
-          const int row0 = B_MN ? kc * 128 : n * 128, col0 = B_MN ? n * 128 : kc * 128;
-          tma_load_2d(dst, &tm_w, &bars->w_full, col0, row0);
-          tma_load_2d(dst + kSlabBytes, &tm_w, &bars->w_full, col0 + 64, row0);
-        }
       uint32_t ia = 0, ie = 0, ix = 0;
       (void)ix;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
