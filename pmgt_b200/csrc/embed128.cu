@@ -102,6 +102,10 @@ __global__ void __launch_bounds__(kThreads) embed_fwd128_kernel(const pmgt_embed
     nv = ldg16(a.ev + er * 128 + h0);
     nt = ldg16(a.et + er * 128 + h0);
   }
+  // position of this half-warp's token within its sequence, advanced incrementally (a 64-bit modulo per token costs
+  // more instructions than the LayerNorm)
+  const int l_step = (int)(stride % a.L);
+  int l = (int)((base + sub) % a.L);
   for (; base < T; base += stride) {
     const long long tok = base + sub;
     const bool valid = tok < T;
@@ -113,7 +117,6 @@ __global__ void __launch_bounds__(kThreads) embed_fwd128_kernel(const pmgt_embed
       nt = ldg16(a.et + er * 128 + h0);
     }
     const long long tc = valid ? tok : T - 1;
-    const int l = (int)(tc % a.L);
     float pr[8], rr[8];
     ld8(a.pos + (long long)l * 128 + h0, pr);
     ld8(a.role + (l > 0 ? 128 : 0) + h0, rr);
@@ -132,6 +135,8 @@ __global__ void __launch_bounds__(kThreads) embed_fwd128_kernel(const pmgt_embed
       y[j] = (keep >> j) & 1u ? v * ks : 0.f;
     }
     if (valid) *reinterpret_cast<uint4*>(a.x_out + tok * 128 + h0) = pack8(y);
+    l += l_step;
+    if (l >= a.L) l -= a.L;
   }
 }
 

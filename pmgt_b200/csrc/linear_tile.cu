@@ -86,7 +86,7 @@ struct LtLayout {
 struct LtBars {
   uint64_t w_full;
   uint64_t a_full[3], a_empty[3];
-  uint64_t e_full[2], e_empty[2];
+  uint64_t e_full[3], e_empty[3];
   uint64_t acc_full[kAccSlots], acc_empty[kAccSlots];
   uint64_t stg_full[2], stg_empty[2];
   uint64_t x_full[2], x_empty[2];
@@ -135,7 +135,7 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   constexpr int kSlots = DW ? kAccSlots - 1 : kAccSlots;
   static_assert(!kHasE || NC == 1, "epilogue-input variants are single-chunk");
   static_assert(NSTG == 1 || NSTG == 2, "one or two staging buffers");
-  static_assert(SA <= 3 && SE <= 2 && SX <= 2, "barrier arrays");
+  static_assert(SA <= 3 && SE <= 3 && SX <= 2, "barrier arrays");
   static_assert(!DW || (B_MN && NC == 1 && KC == 1 && (EPI == LT_PLAIN || EPI == LT_GELU_BWD)), "dW fusion: dX kernels only");
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -149,9 +149,11 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       mbar_init(&bars->a_full[s], 1);
       mbar_init(&bars->a_empty[s], DW ? 1 + kDwWarps : 1);  // MMA commit (+ one arrival per column-sum warp)
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 3; ++s) {
       mbar_init(&bars->e_full[s], 1);
       mbar_init(&bars->e_empty[s], EPI == LT_RES_LN ? 1 : kEpiWarps);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->stg_full[s], kEpiWarps);
       mbar_init(&bars->stg_empty[s], 1);
       mbar_init(&bars->x_full[s], 1);
@@ -337,7 +339,9 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           eimg = smem + Lay::kE + se * kImgBytes;
         }
         const uint32_t buf = it % NSTG;
-        mbar_wait(&bars->stg_empty[buf], ((it / NSTG) & 1u) ^ 1u);
+        // RES_LN writes its staging image only in phase B: the wait moves there, so a single staging buffer's drain
+        // (the previous tile's TMA store reading it) overlaps phase A
+        if (EPI != LT_RES_LN) mbar_wait(&bars->stg_empty[buf], ((it / NSTG) & 1u) ^ 1u);
         unsigned char* stg0 = smem + Lay::kStg + buf * kNOut * kImgBytes;
         unsigned char* stg1 = stg0 + kImgBytes;  // only when kNOut == 2
         const long long tok = (long long)tile * 128 + r;
@@ -391,6 +395,7 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             *zp = pack8f(x);
           }
           named_bar_sync(1, 32 * kEpiWarps);
+          mbar_wait(&bars->stg_empty[buf], ((it / NSTG) & 1u) ^ 1u);
           // phase B (half-warp per row, 8 rows per warp): LayerNorm over the bf16-rounded z (exactly what the backward
           // pass re-reads) with the row statistics in four shuffles -- one block barrier per tile instead of an
           // all-to-all exchange of partial sums, and the optional fp32 copy leaves as 512-byte-contiguous rows
@@ -473,8 +478,11 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const int quarter = warp & 3;
       const int r = quarter * 32 + lane;
       float* dst = p.dw + (long long)r * p.ld_dw;
+      // every CTA adds its partial dW into the same 64 KB: the L2 atomic units serialise per address, so CTAs walk
+      // the column chunks in rotated order and rarely meet on one
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c0 = ((ci + (int)blockIdx.x) & 3) * 32;
         uint32_t acc[32];
         tmem_ld_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kSlots * 128 + c0), acc);
         tmem_wait_ld();
@@ -650,19 +658,19 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant_
       tcgen05_fence_after();
       const int quarter = warp & 3;
       const int r = quarter * 32 + lane;
+      // rotated chunk order per CTA (see the fused dX + dW flush): 148 CTAs add into the same NC * 64 KB
 #pragma unroll 1
-      for (int n = 0; n < NC; ++n) {
+      for (int ci = 0; ci < NC * 4; ++ci) {
+        const int ch = (ci + (int)blockIdx.x) % (NC * 4);
+        const int n = ch >> 2, c0 = (ch & 3) * 32;
         float* dst = p.dw + (long long)(n * 128 + r) * p.ld_dw;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t acc[32];
-          tmem_ld_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(n * 128 + c0), acc);
-          tmem_wait_ld();
+        uint32_t acc[32];
+        tmem_ld_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(n * 128 + c0), acc);
+        tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            red_add_v4(dst + c0 + j, __uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
-                       __uint_as_float(acc[j + 3]));
-        }
+        for (int j = 0; j < 32; j += 4)
+          red_add_v4(dst + c0 + j, __uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                     __uint_as_float(acc[j + 3]));
       }
     }
   }
@@ -785,7 +793,7 @@ int pmgt_linear_tile(const pmgt_linear_tile_args* a, void* stream) {
       PMGT_REQUIRE(a->bias && a->aux_out && a->e_in && a->ln_g && a->ln_b && a->ld_aux_out % 8 == 0 && a->ld_e % 8 == 0,
                    "pmgt_linear_tile: RES_LN needs bias, residual (e_in), z out (aux_out), ln_g, ln_b");
       PMGT_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "pmgt_linear_tile: bad dropout_p");
-      return launch_lt<1, 1, false, LT_RES_LN, 2, 2, 2>(a, st);
+      return launch_lt<1, 1, false, LT_RES_LN, 2, 3, 1>(a, st);
     case PMGT_LT_PLAIN:
       if (kc == 4) return launch_lt<1, 4, true, LT_PLAIN, 2, 1, 1>(a, st);
       if (a->dw) return launch_lt<1, 1, true, LT_PLAIN, 2, 1, 2, 2>(a, st);

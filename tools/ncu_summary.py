@@ -92,5 +92,70 @@ def full(src, dst):
     print(open(dst).read()[:4000])
 
 
+FAMILY = [  # kernel-name pattern -> bench.py profile family (for profiles/ncu_traffic.json)
+    (r"linear_tile_kernel<1, 1, 0, 2", "lt_res_ln_fwd"), (r"linear_tile_kernel<4, 1, 0, 0", "lt_qkvc_fwd"),
+    (r"linear_tile_kernel<1, 1, 0, 1", "lt_gelu_fwd"), (r"linear_tile_kernel<1, 4, 1, 3", "lt_dx_qkvc"),
+    (r"linear_tile_kernel<1, 1, 1, 3, \d, \d, \d, [12]", "lt_dxdw"), (r"linear_tile_kernel<1, 1, 1, 4, \d, \d, \d, [12]", "lt_dxdw_gelu"),
+    (r"linear_tile_kernel<1, 1, 1, 3", "lt_dx"), (r"linear_tile_kernel<1, 1, 1, 4", "lt_dx_gelu"),
+    (r"dw_tile_kernel", "dw_tile"), (r"ln_bwd_stream_kernel<[12]", "ln_bwd"), (r"attn_mma_fwd", "attn_core_fwd"),
+    (r"attn_mma_bwd", "attn_core_bwd"), (r"sample_contexts", "sample_contexts"), (r"embed_fwd128", "embed_fuse_fwd"),
+    (r"embed_bwd128", "embed_fuse_bwd"),
+]
+
+
+def rawcsv(src, dst, traffic_json=None, title=""):
+    """Summary of `ncu -i rep --page raw --csv` output (what tools/gpu_ncu.sh / gpu_final.sh bring back)."""
+    import json
+    rows = list(csv.reader(open(src)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    H = {h: i for i, h in enumerate(hdr)}
+
+    def g(r, k):
+        try:
+            return float(r[H[k]].replace(",", ""))
+        except Exception:
+            return float("nan")
+
+    keys = [k for k in KEYS + ["lts__t_sector_hit_rate.pct"] if k in H]
+    fam_traffic = {}
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full summary of `{src}`{title}\n\n")
+        f.write("Cold-cache single launches under ncu; `traffic` = dram__bytes_read.sum + dram__bytes_write.sum. ncu's DRAM % "
+                "is against the HBM3e pin rate (~8 TB/s); bench.py's roofline denominator is the measured copy bandwidth "
+                "(MEASURED_PEAKS.json).\n\n")
+        f.write("| kernel | us | DRAM read MB | DRAM write MB | traffic TB/s | DRAM % | issue % | warps % | regs |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+        for r in data:
+            name = short(r[H["Kernel Name"]]).replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+            rd, wr, dur = g(r, "dram__bytes_read.sum"), g(r, "dram__bytes_write.sum"), g(r, "gpu__time_duration.sum")
+            f.write(f"| `{name}` | {dur:.1f} | {rd:.1f} | {wr:.1f} | {(rd + wr) / dur:.2f} | "
+                    f"{g(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+                    f"{g(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
+                    f"{g(r, 'sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {g(r, 'launch__registers_per_thread'):.0f} |\n")
+            for pat, fam in FAMILY:
+                if re.search(pat, name):
+                    fam_traffic.setdefault(fam, []).append((rd + wr) * 1e6)
+                    break
+        f.write("\n")
+        for r in data:
+            name = short(r[H["Kernel Name"]]).replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+            f.write(f"## `{name}`\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for k in keys:
+                f.write(f"| {k} | {r[H[k]]} | {units[H[k]]} |\n")
+            f.write("\n")
+    if traffic_json:
+        json.dump({"source": f"{dst} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, TG workload, "
+                             "B = 4096, 1-layer step; families with several shapes are launch-weighted)",
+                   "workload": "TG", "targets_per_gpu_per_step": 4096,
+                   # the 5-layer bench model launches the LayerNorm epilogue 10x per step: 9 plain + 1 with the fp32 copy
+                   # of the last hidden state; the 1-layer capture holds one of each, in that order
+                   "traffic_bytes_per_launch": {k: ((9 * v[0] + v[1]) / 10 if k == "lt_res_ln_fwd" and len(v) == 2
+                                                    else sum(v) / len(v)) for k, v in fam_traffic.items()}},
+                  open(traffic_json, "w"), indent=1)
+    print(open(dst).read()[:3500])
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "rawcsv":
+        rawcsv(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
