@@ -39,7 +39,7 @@ typedef enum pmgt_status {
 } pmgt_status;
 
 /* ABI version of this header; bumped on any signature change. */
-#define PMGT_B200_ABI_VERSION 4
+#define PMGT_B200_ABI_VERSION 5
 int pmgt_abi_version(void);
 const char* pmgt_last_error(void);
 
@@ -329,6 +329,10 @@ typedef struct pmgt_dw_tile_args {
 
 int pmgt_dw_tile_supported(int64_t N, int64_t K);
 int pmgt_dw_tile(const pmgt_dw_tile_args* a, void* stream);
+/* n independent problems of one (N, K) shape in one launch: the CTAs are dealt round-robin to the problems, so every dw
+ * receives ~SMs / n partial sums instead of SMs and the fixed cost of the accumulator flush is paid once (used for the
+ * Q/K/V/C weight gradients of all encoder layers, deferred to the end of the backward pass). */
+int pmgt_dw_tile_batch(const pmgt_dw_tile_args* a, int n, void* stream);
 
 /*
  * LayerNorm backward from the saved pre-LayerNorm input z (PMGT_LT_RES_LN's aux_out): dy = dy_a + dy_b +

@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmgt_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _lib = None
 
@@ -173,6 +173,7 @@ SIGNATURES = {
     "pmgt_linear_tile": (C.c_int, [C.POINTER(LinearTileArgs), c_vp]),
     "pmgt_dw_tile_supported": (C.c_int, [C.c_int64, C.c_int64]),
     "pmgt_dw_tile": (C.c_int, [C.POINTER(DwTileArgs), c_vp]),
+    "pmgt_dw_tile_batch": (C.c_int, [C.POINTER(DwTileArgs), C.c_int, c_vp]),
     "pmgt_ln_bwd": (C.c_int, [C.POINTER(LnBwdArgs), c_vp]),
     "pmgt_colsum_bf16": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp]),
     "pmgt_gsr_fwd": (C.c_int, [C.POINTER(GsrArgs), c_vp]),

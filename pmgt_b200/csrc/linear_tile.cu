@@ -524,9 +524,27 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+constexpr int kDwBatchMax = 8;
+
+// Up to kDwBatchMax independent dW problems of one shape in ONE launch (e.g. the Q/K/V/C weight gradients of every
+// layer, deferred to the end of the backward pass): CTA b works on problem b % n with the CTAs b, b + n, b + 2n ...
+// Each dW then receives ~gridDim / n partial sums instead of gridDim, and the TMEM flush -- 148 CTAs adding 256 KB
+// each into the same 256 KB through the L2 atomic units, ~24 us per launch -- is paid once instead of once per layer.
+struct DwBatch {
+  CUtensorMap dy[kDwBatchMax];
+  CUtensorMap x[kDwBatchMax];
+  DwParams p[kDwBatchMax];
+  int n;
+};
+
 template <int NC, int SX, int SD>
-__global__ void __launch_bounds__(192, 1)
-dw_tile_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x, const DwParams p) {
+__global__ void __launch_bounds__(192, 1) dw_tile_kernel(const __grid_constant__ DwBatch batch) {
+  const int prob = (int)blockIdx.x % batch.n;
+  const int cta = (int)blockIdx.x / batch.n;                                   // index among this problem's CTAs
+  const int ncta = ((int)gridDim.x - prob + batch.n - 1) / batch.n;           // how many CTAs share this problem
+  const CUtensorMap& tm_dy = batch.dy[prob];
+  const CUtensorMap& tm_x = batch.x[prob];
+  const DwParams& p = batch.p[prob];
   constexpr int kX = 0;
   constexpr int kDY = SX * kImgBytes;
   constexpr int kRed = kDY + SD * kImgBytes;       // [8][128] floats for the column-sum reduction
@@ -560,13 +578,13 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const bool has_tiles = (int)blockIdx.x < p.num_tiles;
+  const bool has_tiles = cta < p.num_tiles;
   pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t ix = 0, id = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ix) {
+      for (int tile = cta; tile < p.num_tiles; tile += ncta, ++ix) {
         {
           const int s = ix % SX;
           mbar_wait(&bars->x_empty[s], ((ix / SX) & 1u) ^ 1u);
@@ -590,7 +608,7 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant_
       constexpr uint32_t idesc = make_idesc(true, true);
       uint32_t ix = 0, id = 0;
       bool first = true;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ix) {
+      for (int tile = cta; tile < p.num_tiles; tile += ncta, ++ix) {
         const int sx = ix % SX;
         mbar_wait(&bars->x_full[sx], (ix / SX) & 1u);
         const uint32_t x_img = smem_u32(smem + kX + sx * kImgBytes);
@@ -618,7 +636,7 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 8; ++j) cs[n][j] = 0.f;
     uint32_t id = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < p.num_tiles; tile += ncta) {
 #pragma unroll
       for (int n = 0; n < NC; ++n, ++id) {
         const int s = id % SD;
@@ -661,7 +679,7 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant_
       // rotated chunk order per CTA (see the fused dX + dW flush): 148 CTAs add into the same NC * 64 KB
 #pragma unroll 1
       for (int ci = 0; ci < NC * 4; ++ci) {
-        const int ch = (ci + (int)blockIdx.x) % (NC * 4);
+        const int ch = (ci + cta) % (NC * 4);
         const int n = ch >> 2, c0 = (ch & 3) * 32;
         float* dst = p.dw + (long long)(n * 128 + r) * p.ld_dw;
         uint32_t acc[32];
@@ -724,26 +742,33 @@ static int launch_lt(const pmgt_linear_tile_args* a, cudaStream_t st) {
 }
 
 template <int NC, int SX, int SD>
-static int launch_dw(const pmgt_dw_tile_args* a, cudaStream_t st) {
+static int launch_dw(const pmgt_dw_tile_args* a, int n, cudaStream_t st) {
   constexpr int smem = (SX + SD) * kImgBytes + 8 * 128 * 4 + 256 + 1024;
   static_assert(smem <= 232448, "shared memory budget (227 KiB)");
+  static_assert(sizeof(DwBatch) <= 4000, "kernel parameter space");
   auto kern = dw_tile_kernel<NC, SX, SD>;
   static bool configured = false;
   if (!configured) {
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  CUtensorMap tdy, tx;
-  int rc;
-  if ((rc = make_tmap(&tdy, a->dy, a->N, a->T, a->ld_dy, 64, 128))) return rc;
-  if ((rc = make_tmap(&tx, a->x, a->K, a->T, a->ldx, 64, 128))) return rc;
-  DwParams p;
-  p.T = (int)a->T;
-  p.num_tiles = (int)((a->T + 127) / 128);
-  p.dw = a->dw; p.ld_dw = a->ld_dw; p.dbias = a->dbias;
+  DwBatch b;
+  memset(&b, 0, sizeof(b));
+  b.n = n;
+  long long total_tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    int rc;
+    if ((rc = make_tmap(&b.dy[i], a[i].dy, a[i].N, a[i].T, a[i].ld_dy, 64, 128))) return rc;
+    if ((rc = make_tmap(&b.x[i], a[i].x, a[i].K, a[i].T, a[i].ldx, 64, 128))) return rc;
+    b.p[i].T = (int)a[i].T;
+    b.p[i].num_tiles = (int)((a[i].T + 127) / 128);
+    b.p[i].dw = a[i].dw; b.p[i].ld_dw = a[i].ld_dw; b.p[i].dbias = a[i].dbias;
+    total_tiles += b.p[i].num_tiles;
+  }
   int grid = num_sms();
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  PMGT_CHECK_CUDA(launch_kernel(true, kern, dim3(grid), dim3(192), smem, st, tdy, tx, p));
+  if (grid > total_tiles) grid = (int)total_tiles;
+  if (grid < n) grid = n;
+  PMGT_CHECK_CUDA(launch_kernel(true, kern, dim3(grid), dim3(192), smem, st, b));
   return PMGT_OK;
 }
 
@@ -809,17 +834,45 @@ int pmgt_linear_tile(const pmgt_linear_tile_args* a, void* stream) {
 
 int pmgt_dw_tile_supported(int64_t N, int64_t K) { return (K == 128 && (N == 128 || N == 512)) ? 1 : 0; }
 
-int pmgt_dw_tile(const pmgt_dw_tile_args* a, void* stream) {
+static int check_dw_args(const pmgt_dw_tile_args* a) {
   PMGT_REQUIRE(a && a->dy && a->x && a->dw, "pmgt_dw_tile: null argument");
-  PMGT_REQUIRE(a->T >= 0 && a->T < (1ll << 31) - 128, "pmgt_dw_tile: bad T");
-  if (a->T == 0) return PMGT_OK;
+  PMGT_REQUIRE(a->T > 0 && a->T < (1ll << 31) - 128, "pmgt_dw_tile: bad T");
   PMGT_REQUIRE(pmgt_dw_tile_supported(a->N, a->K), "pmgt_dw_tile: unsupported shape N=%d K=%d (use pmgt_gemm_bf16)", a->N,
                a->K);
   PMGT_REQUIRE(a->ld_dy % 8 == 0 && a->ldx % 8 == 0 && a->ld_dw % 4 == 0, "pmgt_dw_tile: row pitch alignment");
   PMGT_REQUIRE((((uintptr_t)a->dy | (uintptr_t)a->x | (uintptr_t)a->dw) & 15) == 0, "pmgt_dw_tile: 16-byte alignment");
+  return PMGT_OK;
+}
+
+int pmgt_dw_tile(const pmgt_dw_tile_args* a, void* stream) {
+  PMGT_REQUIRE(a, "pmgt_dw_tile: null argument");
+  if (a->T == 0) return PMGT_OK;
+  int rc = check_dw_args(a);
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->N == 512) return launch_dw<4, 2, 4>(a, st);
-  return launch_dw<1, 3, 3>(a, st);
+  if (a->N == 512) return launch_dw<4, 2, 4>(a, 1, st);
+  return launch_dw<1, 3, 3>(a, 1, st);
+}
+
+int pmgt_dw_tile_batch(const pmgt_dw_tile_args* a, int n, void* stream) {
+  PMGT_REQUIRE(a && n >= 1, "pmgt_dw_tile_batch: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int lo = 0; lo < n; lo += kDwBatchMax) {  // more than kDwBatchMax problems: several launches
+    pmgt_dw_tile_args chunk[kDwBatchMax];
+    int m = 0;
+    for (int i = lo; i < n && i < lo + kDwBatchMax; ++i) {
+      if (a[i].T == 0) continue;
+      int rc = check_dw_args(&a[i]);
+      if (rc) return rc;
+      PMGT_REQUIRE(m == 0 || (a[i].N == chunk[0].N && a[i].K == chunk[0].K),
+                   "pmgt_dw_tile_batch: all problems of a batch must share N and K");
+      chunk[m++] = a[i];
+    }
+    if (m == 0) continue;
+    int rc = chunk[0].N == 512 ? launch_dw<4, 2, 4>(chunk, m, st) : launch_dw<1, 3, 3>(chunk, m, st);
+    if (rc) return rc;
+  }
+  return PMGT_OK;
 }
 
 }  // extern "C"

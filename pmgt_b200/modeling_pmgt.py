@@ -426,6 +426,8 @@ class _EncoderRun:
 
 # dX kernels of the 128 x 128 Linears also produce dW / dbias (one pass over dY); False: separate pmgt_dw_tile launches
 FUSED_DW = True
+# dW of the fused Q/K/V/C projection: one batched launch for all layers at the end of the backward pass (False: per layer)
+BATCH_DW_QKVC = True
 
 # "auto": projected tables when 4 * table rows <= tokens, else the gather-fused GEMM; "table" / "gather" force a mode
 PROJECTION_MODE = "auto"
@@ -580,6 +582,7 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
     dy_f32 = d_hidden.contiguous().view(T, H)
     dy = None
     dy_b = None  # second gradient term of the layer input (the LayerNorm residual branch), tile path only
+    deferred_dw = []
     for i in reversed(range(cfg.num_hidden_layers if run.tile else 0)):
         P = f"{pre}encoder.layer.{i}."
         site = 10 * (i + 1)
@@ -626,11 +629,19 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
         dqkvc = new(T, 4 * H)
         ops.attn_core_bwd(ops.attn_args(R, L, H, heads, float(cfg.beta), qkvc, run.mask, p_att, seed, site, dctx=dctx,
                                         dqkvc=dqkvc))
-        ops.dw_tile(dqkvc, x, G(P + "attention.self.query.weight", 4), G(P + "attention.self.query.bias", 4))
+        if BATCH_DW_QKVC:
+            # the Q/K/V/C weight gradient is not needed before the optimizer: all layers share ONE launch at the end
+            deferred_dw.append((dqkvc, x, G(P + "attention.self.query.weight", 4), G(P + "attention.self.query.bias", 4)))
+        else:
+            ops.dw_tile(dqkvc, x, G(P + "attention.self.query.weight", 4), G(P + "attention.self.query.bias", 4))
         dx = new(T, H)
         ops.linear_tile(dqkvc, fp.bf16(P + "attention.self.query.weight", 4), dx, ops.LT_PLAIN, w_mn=True, tag="lt_dx_qkvc")
-        done(dy, dy_b, dz2, do2, dh_pre, da, dctx, dqkvc, *((do1,) if do1 is not dz1 else ()))
+        done(dy, dy_b, dz2, do2, dh_pre, da, dctx, *((do1,) if do1 is not dz1 else ()),
+             *(() if BATCH_DW_QKVC else (dqkvc,)))
         dy, dy_b = dx, dz1  # d x = dx (projection branch) + dz1 (residual branch): summed by the consumer
+    if deferred_dw:
+        ops.dw_tile_batch(deferred_dw)
+        done(*(d[0] for d in deferred_dw))
     for i in reversed(range(0 if run.tile else cfg.num_hidden_layers)):
         P = f"{pre}encoder.layer.{i}."
         site = 10 * (i + 1)

@@ -217,6 +217,24 @@ def dw_tile(dy, x, dw_f32, dbias=None, tag="dw_tile"):
     _run(tag, _lib.lib().pmgt_dw_tile, (C.byref(a), cur_stream()), 1, 2 * T * (N + K) + 4 * N * K, 2 * T * N * K)
 
 
+def dw_tile_batch(problems, tag="dw_tile"):
+    """``pmgt_dw_tile_batch``: ``problems`` = [(dy, x, dw_f32, dbias-or-None), ...] of one shape, one launch."""
+    n = len(problems)
+    arr = (DwTileArgs * n)()
+    nbytes = flops = 0
+    for a, (dy, x, dw_f32, dbias) in zip(arr, problems):
+        T, N = dy.shape
+        K = x.shape[1]
+        a.T, a.N, a.K = T, N, K
+        a.dy, a.ld_dy = ptr(dy), dy.stride(0)
+        a.x, a.ldx = ptr(x), x.stride(0)
+        a.dw, a.ld_dw = ptr(dw_f32), dw_f32.stride(0)
+        a.dbias = ptr(dbias)
+        nbytes += 2 * T * (N + K) + 4 * N * K
+        flops += 2 * T * N * K
+    _run(tag, _lib.lib().pmgt_dw_tile_batch, (arr, n, cur_stream()), 1, nbytes, flops)
+
+
 def ln_bwd(T, H, z, ln_g, eps, p, seed, site, dz, d_o, d_g, d_b, dy_a=None, dy_b=None, dy_f32=None):
     a = LnBwdArgs()
     a.T, a.H = T, H

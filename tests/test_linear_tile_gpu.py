@@ -135,6 +135,26 @@ def test_dx_with_fused_dw(T, gelu):
     _close(dw2, dy.float().t() @ x_in.float(), 2e-3, "dw (no dbias)")
 
 
+@pytest.mark.parametrize("N", [128, 512])
+@pytest.mark.parametrize("n", [1, 3, 5])
+def test_dw_batch(N, n):
+    """pmgt_dw_tile_batch: n independent problems (different token counts, one of them a single ragged tile) in one launch."""
+    ops = _ops()
+    sizes = [40000 + 37, 77, 128 * 9, 5000, 200][:n]
+    probs, want = [], []
+    for i, T in enumerate(sizes):
+        dy, x = _r(T, N, s=0.5), _r(T, 128, s=0.5)
+        dw = torch.full((N, 128), float(i), device="cuda")
+        db = torch.zeros(N, device="cuda") if i % 2 == 0 else None
+        probs.append((dy, x, dw, db))
+        want.append((dy.float().t() @ x.float() + float(i), dy.float().sum(0)))
+    ops.dw_tile_batch(probs)
+    for (dy, x, dw, db), (wdw, wdb) in zip(probs, want):
+        _close(dw, wdw, 2e-3, "dw")
+        if db is not None:
+            _close(db, wdb, 2e-3, "dbias")
+
+
 @pytest.mark.parametrize("T", [77, 5000])
 def test_ln_bwd(T):
     ops = _ops()
