@@ -39,7 +39,7 @@ typedef enum pmgt_status {
 } pmgt_status;
 
 /* ABI version of this header; bumped on any signature change. */
-#define PMGT_B200_ABI_VERSION 5
+#define PMGT_B200_ABI_VERSION 6
 int pmgt_abi_version(void);
 const char* pmgt_last_error(void);
 
@@ -50,6 +50,14 @@ const char* pmgt_last_error(void);
  * its predecessor's tail.
  */
 int pmgt_set_pdl(int enabled);
+
+/*
+ * Alternating traversal order of the encoder's persistent kernels (token-tile GEMMs, LayerNorm backward, attention
+ * core): consecutive launches walk the token tiles in opposite directions, so each kernel starts on the rows its
+ * predecessor wrote last, which are still in L2.  Results do not depend on the order.  On by default
+ * (PMGT_ALTERNATE=0 at load time turns it off); returns the previous setting.
+ */
+int pmgt_set_alternate_order(int enabled);
 
 /* ------------------------------------------------------------------------ */
 /* Item graph (CSR)                                                          */

@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmgt_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _lib = None
 
@@ -150,6 +150,7 @@ class NfrArgs(C.Structure):
 SIGNATURES = {
     "pmgt_abi_version": (C.c_int, []),
     "pmgt_set_pdl": (C.c_int, [C.c_int]),
+    "pmgt_set_alternate_order": (C.c_int, [C.c_int]),
     "pmgt_last_error": (C.c_char_p, []),
     "pmgt_graph_create": (C.c_int, [C.POINTER(c_vp), C.c_int, C.c_int64, C.c_int64, c_i64p, c_i32p, c_f32p]),
     "pmgt_graph_destroy": (C.c_int, [c_vp]),

@@ -40,9 +40,31 @@ bool pdl_enabled() {
   return g_pdl == 1;
 }
 
+int set_alternate(int enabled);
+
 int set_pdl(int enabled) {
   const int prev = pdl_enabled() ? 1 : 0;
   g_pdl = enabled ? 1 : 0;
+  return prev;
+}
+
+static int g_alternate = -1;
+static int g_order = 0;
+
+int next_tile_order() {
+  if (g_alternate < 0) {
+    const char* e = getenv("PMGT_ALTERNATE");
+    g_alternate = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!g_alternate) return 0;
+  g_order ^= 1;
+  return g_order;
+}
+
+int set_alternate(int enabled) {
+  const int prev = g_alternate < 0 ? 1 : g_alternate;
+  g_alternate = enabled ? 1 : 0;
+  g_order = 0;
   return prev;
 }
 
@@ -52,4 +74,5 @@ extern "C" {
 int pmgt_abi_version(void) { return PMGT_B200_ABI_VERSION; }
 const char* pmgt_last_error(void) { return pmgt::g_err; }
 int pmgt_set_pdl(int enabled) { return pmgt::set_pdl(enabled); }
+int pmgt_set_alternate_order(int enabled) { return pmgt::set_alternate(enabled); }
 }

@@ -257,7 +257,7 @@ struct AttnRing {
 };
 
 template <int L, int DH>
-__global__ void __launch_bounds__(AttnRing<L, DH, 4>::kWarps * 32, 1) attn_mma_fwd_kernel(const pmgt_attn_args a) {
+__global__ void __launch_bounds__(AttnRing<L, DH, 4>::kWarps * 32, 1) attn_mma_fwd_kernel(const pmgt_attn_args a, const int reverse) {
   using Tile = AttnTile<L, DH>;
   using Ring = AttnRing<L, DH, 4>;
   constexpr int S = Ring::kStages;
@@ -279,8 +279,9 @@ __global__ void __launch_bounds__(AttnRing<L, DH, 4>::kWarps * 32, 1) attn_mma_f
 
   static_assert(S == 2, "the mask prefetch below runs exactly one item ahead");
   float mask_next = 1.f;
-  auto stage = [&](long long item, int slot) {
-    if (item < n_items) {
+  auto stage = [&](long long litem, int slot) {
+    if (litem < n_items) {
+      const long long item = reverse ? n_items - 1 - litem : litem;  // alternating traversal order (next_tile_order)
       const long long row = heads == 1 ? item : item / heads;
       const int head = (int)(item - row * heads);
       stage_item<L, DH, 4>(wbuf + slot * Ring::kItem, a.qkvc + row * L * ld + head * DH, ld, H, nullptr, lane);
@@ -291,10 +292,11 @@ __global__ void __launch_bounds__(AttnRing<L, DH, 4>::kWarps * 32, 1) attn_mma_f
 #pragma unroll
   for (int s = 0; s < S - 1; ++s) stage(w0 + (long long)s * nw, s);
   int cur = 0;
-  for (long long item = w0; item < n_items; item += nw) {
+  for (long long litem = w0; litem < n_items; litem += nw) {
+    const long long item = reverse ? n_items - 1 - litem : litem;
     const float mask_cur = mask_next;
     // slot (cur + S - 1) % S was consumed in the previous iteration (a __syncwarp separates it from this refill)
-    stage(item + (long long)(S - 1) * nw, (cur + S - 1) % S);
+    stage(litem + (long long)(S - 1) * nw, (cur + S - 1) % S);
     cp_async_wait_group<S - 1>();
     __syncwarp();
     unsigned char* buf = wbuf + cur * Ring::kItem;
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(AttnRing<L, DH, 4>::kWarps * 32, 1) attn_mma_f
 }
 
 template <int L, int DH>
-__global__ void __launch_bounds__(AttnRing<L, DH, 5>::kWarps * 32, 1) attn_mma_bwd_kernel(const pmgt_attn_args a) {
+__global__ void __launch_bounds__(AttnRing<L, DH, 5>::kWarps * 32, 1) attn_mma_bwd_kernel(const pmgt_attn_args a, const int reverse) {
   using Tile = AttnTile<L, DH>;
   using Ring = AttnRing<L, DH, 5>;
   constexpr int S = Ring::kStages;
@@ -356,8 +358,9 @@ __global__ void __launch_bounds__(AttnRing<L, DH, 5>::kWarps * 32, 1) attn_mma_b
 
   static_assert(S == 2, "the mask prefetch below runs exactly one item ahead");
   float mask_next = 1.f;
-  auto stage = [&](long long item, int slot) {
-    if (item < n_items) {
+  auto stage = [&](long long litem, int slot) {
+    if (litem < n_items) {
+      const long long item = reverse ? n_items - 1 - litem : litem;  // alternating traversal order (next_tile_order)
       const long long row = heads == 1 ? item : item / heads;
       const int head = (int)(item - row * heads);
       stage_item<L, DH, 5>(wbuf + slot * Ring::kItem, a.qkvc + row * L * ld + head * DH, ld, H,
@@ -369,9 +372,10 @@ __global__ void __launch_bounds__(AttnRing<L, DH, 5>::kWarps * 32, 1) attn_mma_b
 #pragma unroll
   for (int s = 0; s < S - 1; ++s) stage(w0 + (long long)s * nw, s);
   int cur = 0;
-  for (long long item = w0; item < n_items; item += nw) {
+  for (long long litem = w0; litem < n_items; litem += nw) {
+    const long long item = reverse ? n_items - 1 - litem : litem;
     const float mask_cur = mask_next;
-    stage(item + (long long)(S - 1) * nw, (cur + S - 1) % S);
+    stage(litem + (long long)(S - 1) * nw, (cur + S - 1) % S);
     cp_async_wait_group<S - 1>();
     __syncwarp();
     unsigned char* buf = wbuf + cur * Ring::kItem;
@@ -461,9 +465,9 @@ static int launch_mma(const pmgt_attn_args* a, cudaStream_t st) {
   const long long cap = (long long)num_sms() * (per_sm < 1 ? 1 : per_sm);
   if (ctas > cap) ctas = cap;
   if (BWD)
-    PMGT_CHECK_CUDA(launch_kernel(true, attn_mma_bwd_kernel<L, DH>, dim3((unsigned)ctas), dim3(kWarps * 32), smem, st, *a));
+    PMGT_CHECK_CUDA(launch_kernel(true, attn_mma_bwd_kernel<L, DH>, dim3((unsigned)ctas), dim3(kWarps * 32), smem, st, *a, next_tile_order()));
   else
-    PMGT_CHECK_CUDA(launch_kernel(true, attn_mma_fwd_kernel<L, DH>, dim3((unsigned)ctas), dim3(kWarps * 32), smem, st, *a));
+    PMGT_CHECK_CUDA(launch_kernel(true, attn_mma_fwd_kernel<L, DH>, dim3((unsigned)ctas), dim3(kWarps * 32), smem, st, *a, next_tile_order()));
   return PMGT_OK;
 }
 

@@ -51,6 +51,10 @@ int num_sms();  // SM count of the current device (cached)
 // access, and calls pdl_launch_dependents() at its start.  PMGT_PDL=0 turns the attribute off.
 // ---------------------------------------------------------------------------
 bool pdl_enabled();
+// Traversal order of the next persistent kernel of the encoder chain: the kernels alternate between ascending and
+// descending tile order, so each one starts on the tiles its predecessor wrote LAST -- the part of a 75-300 MB
+// activation that is still in the 126 MB L2.  Returns 1 for "descending" and flips the library-wide toggle.
+int next_tile_order();
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

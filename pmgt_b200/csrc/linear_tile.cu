@@ -46,6 +46,7 @@ struct LtParams {
   float* dw;          // fused dW (DW variants): [N][ld_dw] fp32, accumulated
   long long ld_dw;
   float* dbias;       // [N] fp32, accumulated, may be NULL
+  int reverse;        // walk the token tiles in descending order (see next_tile_order)
 };
 
 // 16-byte chunk c8 (8 columns) of row r of an image
@@ -199,7 +200,8 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     if (lane == 0) {
       uint32_t ia = 0, ie = 0, ix = 0;
       (void)ix;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int lt = blockIdx.x; lt < p.num_tiles; lt += gridDim.x) {
+        const int tile = p.reverse ? p.num_tiles - 1 - lt : lt;
         for (int kc = 0; kc < KC; ++kc, ++ia) {
           const int s = ia % SA;
           mbar_wait(&bars->a_empty[s], ((ia / SA) & 1u) ^ 1u);
@@ -272,7 +274,8 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // ===================== store warp =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int lt = blockIdx.x; lt < p.num_tiles; lt += gridDim.x) {
+        const int tile = p.reverse ? p.num_tiles - 1 - lt : lt;
         for (int n = 0; n < NC; ++n, ++it) {
           const uint32_t buf = it % NSTG;
           mbar_wait(&bars->stg_full[buf], (it / NSTG) & 1u);
@@ -313,7 +316,8 @@ linear_tile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       ld8f(p.ln_b + (lane & 15) * 8, ln_bt);
     }
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int lt = blockIdx.x; lt < p.num_tiles; lt += gridDim.x) {
+      const int tile = p.reverse ? p.num_tiles - 1 - lt : lt;
       for (int n = 0; n < NC; ++n, ++it) {
         const uint32_t slot = it % kSlots;
         mbar_wait(&bars->acc_full[slot], (it / kSlots) & 1u);
@@ -734,6 +738,7 @@ static int launch_lt(const pmgt_linear_tile_args* a, cudaStream_t st) {
   p.dropout_p = a->dropout_p; p.seed = a->dropout_seed; p.site = a->dropout_site;
   p.out_f32 = a->out_f32;
   p.dw = a->dw; p.ld_dw = a->ld_dw; p.dbias = a->dbias;
+  p.reverse = next_tile_order();
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   PMGT_CHECK_CUDA(launch_kernel(true, kern, dim3(grid), dim3(kLtThreads + (SX > 0 ? 32 * kDwWarps : 0)), Lay::kTotal, st, tx,

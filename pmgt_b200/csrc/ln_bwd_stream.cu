@@ -50,7 +50,7 @@ __device__ __forceinline__ uint4 pack8s(const float* f) {
 // NB = number of bf16 gradient inputs (1: dy_a, 2: dy_a + dy_b); F32 = an fp32 gradient input instead (last layer)
 template <int NB, bool F32>
 __global__ void __launch_bounds__(kThreadsLn, 1) ln_bwd_stream_kernel(const pmgt_lnbwd_args a, const uint16_t* g0,
-                                                                      const uint16_t* g1) {
+                                                                      const uint16_t* g1, const int reverse) {
   constexpr int kZ = kRows * kRowBytes;                                     // 16 KB
   constexpr int kStageBytes = kZ + (F32 ? 2 * kZ : NB * kZ);
   extern __shared__ __align__(128) unsigned char smem[];
@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(kThreadsLn, 1) ln_bwd_stream_kernel(const pmgt
   if (warp == 0) {
     if (lane == 0) {
       uint32_t i = 0;
-      for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x, ++i) {
+      for (long long lc = blockIdx.x; lc < n_chunks; lc += gridDim.x, ++i) {
+        const long long ch = reverse ? n_chunks - 1 - lc : lc;  // alternating traversal order, see next_tile_order
         const int s = i % kStages;
         mbar_wait(&bars->empty[s], ((i / kStages) & 1u) ^ 1u);
         const long long row0 = ch * kRows;
@@ -104,7 +105,8 @@ __global__ void __launch_bounds__(kThreadsLn, 1) ln_bwd_stream_kernel(const pmgt
       gam[0] = q0.x; gam[1] = q0.y; gam[2] = q0.z; gam[3] = q0.w; gam[4] = q1.x; gam[5] = q1.y; gam[6] = q1.z; gam[7] = q1.w;
     }
     uint32_t i = 0;
-    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x, ++i) {
+    for (long long lc = blockIdx.x; lc < n_chunks; lc += gridDim.x, ++i) {
+      const long long ch = reverse ? n_chunks - 1 - lc : lc;
       const int s = i % kStages;
       mbar_wait(&bars->full[s], (i / kStages) & 1u);
       const unsigned char* st = smem + s * kStageBytes;
@@ -214,7 +216,7 @@ int launch(const pmgt_lnbwd_args* a, const uint16_t* g0, const uint16_t* g1, cud
   long long chunks = (a->T + kRows - 1) / kRows;
   int grid = num_sms();
   if (grid > chunks) grid = (int)chunks;
-  PMGT_CHECK_CUDA(launch_kernel(true, kern, dim3(grid), dim3(kThreadsLn), smem, st, *a, g0, g1));
+  PMGT_CHECK_CUDA(launch_kernel(true, kern, dim3(grid), dim3(kThreadsLn), smem, st, *a, g0, g1, next_tile_order()));
   return PMGT_OK;
 }
 

@@ -63,6 +63,11 @@ def set_pdl(enabled: bool) -> bool:
     return bool(_lib.lib().pmgt_set_pdl(int(bool(enabled))))
 
 
+def set_alternate_order(enabled: bool) -> bool:
+    """Alternating tile traversal order of consecutive encoder kernels (L2 reuse) on/off; returns the previous setting."""
+    return bool(_lib.lib().pmgt_set_alternate_order(int(bool(enabled))))
+
+
 def zero_(t):
     """``t.zero_()`` that a tape can replay (a torch memset on the current stream; not counted as one of our launches)."""
     def fn():
