@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="TG", choices=["VG", "TG", "1M"])
+    ap.add_argument("--encoder", default="default", choices=["default", "wide"],
+                    help="wide = BASELINE config 5: H=768, 12 layers, 12 heads, I=3072, 32 neighbours (L=33)")
     ap.add_argument("--batch", type=int, default=4096, help="targets per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-family event profile to this JSON file")
@@ -96,11 +98,18 @@ def reference_arm(a):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(wl, batch, where):
+ENCODERS = {
+    "default": (dict(), "default encoder H=128 I=128 5 layers 1 head, L=6"),
+    "wide": (dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12, max_ctx_neigh=32),
+             "wide encoder H=768 I=3072 12 layers 12 heads, L=33"),
+}
+
+
+def workload_config(wl, batch, where, encoder="default"):
     from pmgt_b200 import synthetic
     n, m, _, _ = synthetic.SHAPES[wl]
     return {"workload": f"PMGT pre-training step on synthetic {wl}-shaped item graph ({n} nodes / {m} edges, 1536-d visual + "
-                        f"768-d text features), default encoder H=128 I=128 5 layers 1 head, L=6, hops [16,8,4], 10 pairs/target",
+                        f"768-d text features), {ENCODERS[encoder][1]}, hops [16,8,4], 10 pairs/target",
             "targets_per_gpu_per_step": batch, "contexts_per_gpu_per_step": batch * 11, "where": where,
             "l2": "per-step working set (activations, several GB at the default batch) is >> the 126 MB L2; no explicit flush"}
 
@@ -190,7 +199,7 @@ def ours(a):
     from pmgt_b200 import ops, synthetic, trainer
 
     dev = torch.device("cuda", local_rank)
-    args = trainer.make_args(synthetic=a.workload, train_batch_size=a.batch, seed=0)
+    args = trainer.make_args(synthetic=a.workload, train_batch_size=a.batch, seed=0, **ENCODERS[a.encoder][0])
     args.device = dev
     trainer.set_seed(0)
     args.graph, args.feat_init_emb = trainer._load_graph_and_features(args)
@@ -310,7 +319,7 @@ def ours(a):
         line = {
             "metric": "pmgt_pretrain_node_contexts_per_s", "value": value, "unit": "contexts/s", "n_gpus": ws,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(a.workload, B, "gpu"),
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(a.workload, B, "gpu", a.encoder),
             "e2e": {"value": e2e_value, "unit": "contexts/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": 4,
                     "api": "pmgt_b200.trainer.PMGTTrainerModel.train_on_indices(pinned host index batch) + .last_loss() every step"},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "loss_last": loss_host,

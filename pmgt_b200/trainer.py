@@ -240,7 +240,7 @@ class PMGTTrainerModel:
         main = torch.cuda.current_stream(self.args.device)
         main.wait_event(ready)
         for t in (batch[0]["node_ids"], batch[0]["attention_mask"], batch[1]["node_ids"], batch[1]["attention_mask"],
-                  batch[2], batch[3], *masked):
+                  batch[2], batch[3], *(masked or ())):
             t.record_stream(main)  # allocated on the side stream, consumed on the main one
         return batch, masked
 
