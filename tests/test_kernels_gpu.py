@@ -165,7 +165,11 @@ def test_embed_fuse_dropout_mask_agrees_between_fwd_and_bwd():
 
 
 @pytest.mark.parametrize("R,L,H,heads,beta", [(9, 6, 128, 1, 0.5), (5, 9, 64, 4, 0.3), (3, 33, 192, 3, 0.5),
-                                              (4, 6, 32, 1, 1.0)])
+                                              (4, 6, 32, 1, 1.0),
+                                              # medium-L tensor-core kernel (attention_mid.cu): config-5 heads, L = 64,
+                                              # one / three k-tiles, head sizes 32 / 48 / 128, more items than warps
+                                              (4, 33, 768, 12, 0.5), (3, 64, 128, 4, 0.7), (40, 17, 256, 2, 0.2),
+                                              (5, 12, 96, 2, 0.0), (2, 48, 64, 1, 0.5)])
 def test_attention_core_fwd_bwd(R, L, H, heads, beta):
     ops = _ops()
     T = R * L
