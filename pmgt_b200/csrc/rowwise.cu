@@ -440,18 +440,27 @@ __global__ void __launch_bounds__(kRowThreads) res_ln_bwd_kernel(const pmgt_resl
       if (h < H) {
         const float4 g = *reinterpret_cast<const float4*>(a.ln_g + h);
         const float ga[4] = {g.x, g.y, g.z, g.w};
+        // the lane owns these four columns for every token: 16-byte read-modify-write of its accumulators
+        // (conflict-free; the scalar form was a 4-way bank conflict and four times the instructions)
+        float4* pg = reinterpret_cast<float4*>(acc + 0 * H + h);
+        float4* pb = reinterpret_cast<float4*>(acc + 1 * H + h);
+        float4 ag = *pg, ab = *pb;
+        float* agf = reinterpret_cast<float*>(&ag);
+        float* abf = reinterpret_cast<float*>(&ab);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float d = dy.v[i][j];
           const float xh = (z.v[i][j] - mean) * rstd;
-          acc[0 * H + h + j] += d * xh;
-          acc[1 * H + h + j] += d;
+          agf[j] += d * xh;
+          abf[j] += d;
           const float dg = d * ga[j];
           s1 += dg;
           s2 += dg * xh;
           dy.v[i][j] = dg;
           z.v[i][j] = xh;
         }
+        *pg = ag;
+        *pb = ab;
       }
     }
     s1 = warp_sum(s1) / (float)H;
@@ -460,14 +469,18 @@ __global__ void __launch_bounds__(kRowThreads) res_ln_bwd_kernel(const pmgt_resl
 #pragma unroll
     for (int i = 0; i < G; ++i) {
       const int h = (lane + 32 * i) * 4;
+      float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
+      float* adf = reinterpret_cast<float*>(&ad);
+      if (h < H) ad = *reinterpret_cast<const float4*>(acc + 2 * H + h);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float dz = (h < H) ? rstd * (dy.v[i][j] - s1 - z.v[i][j] * s2) : 0.f;
         dy.v[i][j] = dz;
         const float dov = (keep_bits >> (i * 4 + j)) & 1u ? dz * keep_scale : 0.f;
         dout.v[i][j] = dov;
-        if (h < H) acc[2 * H + h + j] += bf16_bits_to_float(float_to_bf16_bits(dov));
+        adf[j] += bf16_bits_to_float(float_to_bf16_bits(dov));
       }
+      if (h < H) *reinterpret_cast<float4*>(acc + 2 * H + h) = ad;
     }
     store_row_bf16<G>(a.dz + tok * H, H, lane, dy);
     if (sep_do) store_row_bf16<G>(a.d_o + tok * H, H, lane, dout);
@@ -744,9 +757,11 @@ static int persistent_grid(long long work_warps, int warps_per_cta, int ctas_per
 
 using namespace pmgt;
 
-#define PMGT_DISPATCH_G(H, CALL1, CALL8)        \
-  do {                                          \
-    if ((H) <= 128) { CALL1; } else { CALL8; }  \
+// G = groups of 128 columns a lane walks (4 columns per lane and group): 1 for H <= 128, 6 for H <= 768 (BERT-base
+// width: no predicated-off groups, smaller register footprint than the 1024-column variant), 8 up to H = 1024
+#define PMGT_DISPATCH_G(H, CALL1, CALL6, CALL8)                                  \
+  do {                                                                           \
+    if ((H) <= 128) { CALL1; } else if ((H) <= 768) { CALL6; } else { CALL8; }   \
   } while (0)
 
 extern "C" {
@@ -760,6 +775,7 @@ int pmgt_embed_fuse_fwd(const pmgt_embed_args* a, void* stream) {
   if (embed128_supported(a)) return embed128_fwd(a, (cudaStream_t)stream);
   const int grid = persistent_grid(a->rows * a->L, kRowThreads / 32, 8);
   PMGT_DISPATCH_G(a->H, (embed_fuse_fwd_kernel<1><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)),
+                  (embed_fuse_fwd_kernel<6><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)),
                   (embed_fuse_fwd_kernel<8><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)));
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
@@ -796,6 +812,7 @@ int pmgt_res_ln_fwd(const pmgt_resln_args* a, void* stream) {
   if (a->T == 0) return PMGT_OK;
   const int grid = persistent_grid(a->T, kRowThreads / 32, 8);
   PMGT_DISPATCH_G(a->H, (res_ln_fwd_kernel<1><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)),
+                  (res_ln_fwd_kernel<6><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)),
                   (res_ln_fwd_kernel<8><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)));
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
@@ -810,6 +827,13 @@ int pmgt_res_ln_bwd(const pmgt_resln_args* a, void* stream) {
   const int grid = persistent_grid(a->T, kRowThreads / 32, 4);
   if (a->H <= 128) {
     res_ln_bwd_kernel<1><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(*a);
+  } else if (a->H <= 768) {
+    static bool cfg6 = false;
+    if (!cfg6) {
+      PMGT_CHECK_CUDA(cudaFuncSetAttribute(res_ln_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      cfg6 = true;
+    }
+    res_ln_bwd_kernel<6><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(*a);
   } else {
     static bool cfg = false;
     if (!cfg) {

@@ -136,11 +136,11 @@ def test_dx_with_fused_dw(T, gelu):
 
 
 @pytest.mark.parametrize("N", [128, 512])
-@pytest.mark.parametrize("n", [1, 3, 5])
+@pytest.mark.parametrize("n", [1, 3, 5, 9])
 def test_dw_batch(N, n):
     """pmgt_dw_tile_batch: n independent problems (different token counts, one of them a single ragged tile) in one launch."""
     ops = _ops()
-    sizes = [40000 + 37, 77, 128 * 9, 5000, 200][:n]
+    sizes = [40000 + 37, 77, 128 * 9, 5000, 200, 300, 1000, 129, 64][:n]   # n = 9 > 8: two launches
     probs, want = [], []
     for i, T in enumerate(sizes):
         dy, x = _r(T, N, s=0.5), _r(T, 128, s=0.5)
@@ -218,3 +218,27 @@ def test_res_ln_dropout_matches_ln_bwd_mask():
                dy_a=dy)
     assert bool((d_o.float()[dropped] == 0).all())
     assert torch.allclose(d_o.float()[~dropped], (dz.float() / (1 - p))[~dropped], rtol=2e-2, atol=1e-3)
+
+
+def test_launch_options_do_not_change_results():
+    """pmgt_set_pdl / pmgt_set_alternate_order only change HOW the chain is launched and walked: outputs are identical."""
+    ops = _ops()
+    T = 40000 + 37
+    x, w = _r(T, 128, s=0.5), _r(128, 128, s=0.1)
+    b = torch.randn(128, device="cuda")
+    outs = []
+    prev_pdl, prev_alt = ops.set_pdl(True), ops.set_alternate_order(True)
+    try:
+        for pdl, alt in ((True, True), (False, True), (True, False), (False, False)):
+            ops.set_pdl(pdl)
+            ops.set_alternate_order(alt)
+            for _ in range(3):  # odd and even positions of the alternation
+                out, pre = torch.empty(T, 128, device="cuda", dtype=BF16), torch.empty(T, 128, device="cuda", dtype=BF16)
+                ops.linear_tile(x, w, out, ops.LT_GELU, bias=b, aux_out=pre)
+                outs.append((out, pre))
+        assert ops.set_pdl(True) is False and ops.set_alternate_order(True) is False   # previous settings are returned
+    finally:
+        ops.set_pdl(prev_pdl)
+        ops.set_alternate_order(prev_alt)
+    for out, pre in outs[1:]:
+        assert torch.equal(out, outs[0][0]) and torch.equal(pre, outs[0][1])
