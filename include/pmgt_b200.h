@@ -39,7 +39,7 @@ typedef enum pmgt_status {
 } pmgt_status;
 
 /* ABI version of this header; bumped on any signature change. */
-#define PMGT_B200_ABI_VERSION 6
+#define PMGT_B200_ABI_VERSION 7
 int pmgt_abi_version(void);
 const char* pmgt_last_error(void);
 
@@ -435,6 +435,10 @@ int pmgt_sumsq_f32(const float* x, int64_t n, float* out, void* stream);
 /* out[r][:] = src[idx[r]][:]   (bf16 rows, D elements, D % 8 == 0) */
 int pmgt_gather_rows_bf16(const uint16_t* src, int64_t ld_src, const int64_t* idx, int64_t n_rows,
                           int64_t D, uint16_t* out, int64_t ld_out, void* stream);
+/* dst[idx[r]][:] = src[r][:]   (the inverse: idx unique, other rows of dst untouched) -- with pmgt_gather_rows_bf16 this
+ * is how the LAST encoder layer runs its post-attention half only on the token rows whose hidden state is consumed */
+int pmgt_scatter_rows_bf16(const uint16_t* src, int64_t ld_src, const int64_t* idx, int64_t n_rows, int64_t D,
+                           uint16_t* dst, int64_t ld_dst, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmgt_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _lib = None
 
@@ -186,6 +186,7 @@ SIGNATURES = {
     "pmgt_cast_f32_bf16": (C.c_int, [c_vp, c_vp, C.c_int64, c_vp]),
     "pmgt_sumsq_f32": (C.c_int, [c_vp, C.c_int64, c_vp, c_vp]),
     "pmgt_gather_rows_bf16": (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int64, C.c_int64, c_vp, C.c_int64, c_vp]),
+    "pmgt_scatter_rows_bf16": (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int64, C.c_int64, c_vp, C.c_int64, c_vp]),
 }
 
 

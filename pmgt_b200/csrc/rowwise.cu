@@ -716,6 +716,21 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint16_t* __rest
   }
 }
 
+// dst[idx[r]][:] = src[r][:]   (idx unique; rows of dst not named by idx are left as they are)
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const uint16_t* __restrict__ src, long long ld_src,
+                                                           const long long* __restrict__ idx, long long n_rows, int D,
+                                                           uint16_t* __restrict__ dst, long long ld_dst) {
+  const int chunks = D / 8;
+  const long long total = n_rows * chunks;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / chunks;
+    const int c = (int)(i % chunks) * 8;
+    const long long d = idx[r];
+    if (d >= 0) *reinterpret_cast<uint4*>(dst + d * ld_dst + c) = *reinterpret_cast<const uint4*>(src + r * ld_src + c);
+  }
+}
+
 // AdamW, dense branch of DenseSparseAdamW (pmgt/optimizers.py:256-270)
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v,
@@ -919,6 +934,21 @@ int pmgt_gather_rows_bf16(const uint16_t* src, int64_t ld_src, const int64_t* id
   if (blocks > cap) blocks = cap;
   gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (const long long*)idx, n_rows, (int)D,
                                                                         out, ld_out);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+int pmgt_scatter_rows_bf16(const uint16_t* src, int64_t ld_src, const int64_t* idx, int64_t n_rows, int64_t D,
+                           uint16_t* dst, int64_t ld_dst, void* stream) {
+  PMGT_REQUIRE(src && idx && dst, "pmgt_scatter_rows_bf16: null argument");
+  PMGT_REQUIRE(D % 8 == 0 && ld_src % 8 == 0 && ld_dst % 8 == 0, "pmgt_scatter_rows_bf16: D/ld must be multiples of 8");
+  if (n_rows == 0 || D == 0) return PMGT_OK;
+  long long total = n_rows * (D / 8);
+  long long blocks = (total + 255) / 256;
+  long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  scatter_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (const long long*)idx, n_rows, (int)D,
+                                                                         dst, ld_dst);
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
 }

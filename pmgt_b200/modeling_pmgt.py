@@ -360,11 +360,12 @@ class _EncoderPlan:
     same plan -- which is why plans are opt-in (``PMGTModel.use_launch_plans``; the trainer's step loop turns them on).
     """
 
-    def __init__(self, key, R, L, H, device):
+    def __init__(self, key, R, L, H, device, n_last=0):
         self.key, self.R, self.L, self.T, self.H = key, R, L, R * L, H
         self.device = device
         self.rows_idx = torch.empty(R * L, dtype=torch.int64, device=device)
         self.mask = torch.empty(R, L, dtype=torch.float32, device=device)
+        self.last_rows = torch.empty(n_last, dtype=torch.int64, device=device) if n_last else None
         self.fwd_tape, self.bwd_tape = None, None
         self.fwd_seeds, self.bwd_seeds = [], []
         self.hidden, self.run, self.d_hidden = None, None, None
@@ -374,19 +375,22 @@ class _EncoderPlan:
     def grad_buffer(self) -> torch.Tensor:
         """fp32 [T, H] buffer the caller may build d(loss)/d(hidden) in (saves the copy in ``backward``)."""
         if self.d_hidden is None:
-            self.d_hidden = torch.empty(self.T, self.H, dtype=torch.float32, device=self.device)
+            n = self.last_rows.numel() if self.last_rows is not None else self.T
+            self.d_hidden = torch.empty(n, self.H, dtype=torch.float32, device=self.device)
         return self.d_hidden
 
-    def forward(self, fp, pre, cfg, src, rows_idx, mask, training, seed, keep):
+    def forward(self, fp, pre, cfg, src, rows_idx, mask, training, seed, keep, last_rows=None):
         self.rows_idx.copy_(rows_idx.reshape(-1))
         self.mask.copy_(mask)
+        if self.last_rows is not None:
+            self.last_rows.copy_(last_rows)
         if self.fwd_tape is None:
             tape = []
             ops.TAPE = tape
             try:
                 self.held = []
                 self.hidden, self.run = _encode_forward(fp, pre, cfg, src, self.rows_idx, self.R, self.L, self.mask,
-                                                        training, seed, keep, hold=self.held)
+                                                        training, seed, keep, hold=self.held, last_rows=self.last_rows)
             finally:
                 ops.TAPE = None
             self.fwd_tape, self.fwd_seeds = tape, ops.tape_seed_blocks(tape)
@@ -397,12 +401,12 @@ class _EncoderPlan:
                 self.run.seed = seed
             ops.replay(self.fwd_tape)
         self.pending_backward = keep
-        return self.hidden.view(self.R, self.L, self.H)
+        return self.hidden.view(self.hidden.shape)  # a fresh tensor object over the plan-owned buffer
 
     def backward(self, fp, pre, cfg, d_hidden, arena):
         buf = self.grad_buffer()
         if d_hidden.data_ptr() != buf.data_ptr():
-            buf.copy_(d_hidden.reshape(self.T, self.H))
+            buf.copy_(d_hidden.reshape(-1, self.H))
         if self.bwd_tape is None:
             tape = []
             ops.TAPE = tape
@@ -421,7 +425,7 @@ class _EncoderPlan:
 class _EncoderRun:
     """Activations of one encoder pass kept for the backward pass."""
     __slots__ = ("R", "L", "T", "mask", "rows_idx", "src", "src_rows", "ev", "et", "x0", "layers", "seed", "p_hid",
-                 "p_att", "hidden_f32", "tile", "dense_tables")
+                 "p_att", "hidden_f32", "tile", "dense_tables", "last_rows")
 
 
 # dX kernels of the 128 x 128 Linears also produce dW / dbias (one pass over dY); False: separate pmgt_dw_tile launches
@@ -443,12 +447,19 @@ def _tile_path(H: int, I: int) -> bool:
 
 
 def _encode_forward(fp: FlatParams, pre: str, cfg: PMGTConfig, src: List[torch.Tensor], rows_idx, R: int, L: int,
-                    mask: torch.Tensor, training: bool, seed: int, keep: bool, hold: Optional[list] = None):
+                    mask: torch.Tensor, training: bool, seed: int, keep: bool, hold: Optional[list] = None,
+                    last_rows: Optional[torch.Tensor] = None):
     """PMGTModel.forward (modeling_pmgt.py:80-152) on ``R`` sequences of length ``L``.
 
     ``src``: per modality either the bf16 feature table (``rows_idx`` = flat int64
     node ids, fused gather) or a dense bf16 ``[T, D]`` matrix (``rows_idx`` None).
     Returns (hidden_f32 [R, L, H], run-or-None).
+
+    ``last_rows`` (token-tile path only): sorted unique token indices whose final hidden state the caller consumes.
+    Rows are independent after the attention core, so the LAST layer runs its post-attention half (output projection +
+    LayerNorm, FFN, LayerNorm -- and their whole backward) only on those rows; the result is then the compact
+    ``[len(last_rows), H]`` matrix.  In pre-training that is ~30 % of the tokens (all positions of the target and the
+    masked-target rows, position 0 of the pair rows).
     """
     H, I, heads = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
     T = R * L
@@ -498,10 +509,13 @@ def _encode_forward(fp: FlatParams, pre: str, cfg: PMGTConfig, src: List[torch.T
         run.dense_tables = dense_tables
 
     n_layers = cfg.num_hidden_layers
-    hidden_f32 = new(T, H, dtype=torch.float32)
     tile = _tile_path(H, I)
+    compact = last_rows is not None and tile and n_layers > 0
+    Tc = int(last_rows.numel()) if compact else T
+    hidden_f32 = new(Tc, H, dtype=torch.float32)
     if keep:
         run.tile = tile
+        run.last_rows = last_rows if compact else None
     for i in range(n_layers if tile else 0):
         # ---- fast path: persistent tcgen05 token-tile kernels, element-wise work fused into the epilogues
         P = f"{pre}encoder.layer.{i}."
@@ -512,15 +526,22 @@ def _encode_forward(fp: FlatParams, pre: str, cfg: PMGTConfig, src: List[torch.T
                         bias=fp.f32(P + "attention.self.query.bias", 4), tag="lt_qkvc_fwd")
         ctx = new(T, H)
         ops.attn_core_fwd(ops.attn_args(R, L, H, heads, float(cfg.beta), qkvc, mask, p_att, seed, site, ctx=ctx))
-        a, z1 = new(T, H), new(T, H)
+        Tl, x_res = T, x
+        if last and compact:  # the rest of the last layer only for the rows somebody reads
+            Tl = Tc
+            ctx_c, x_res = new(Tc, H), new(Tc, H)
+            ops.gather_rows(ctx, last_rows, ctx_c)
+            ops.gather_rows(x, last_rows, x_res)
+            ctx = ctx_c
+        a, z1 = new(Tl, H), new(Tl, H)
         ops.linear_tile(ctx, fp.bf16(P + "attention.output.dense.weight"), a, ops.LT_RES_LN,
-                        bias=fp.f32(P + "attention.output.dense.bias"), aux_out=z1, e_in=x,
+                        bias=fp.f32(P + "attention.output.dense.bias"), aux_out=z1, e_in=x_res,
                         ln_g=fp.f32(P + "attention.output.LayerNorm.weight"), ln_b=fp.f32(P + "attention.output.LayerNorm.bias"),
                         ln_eps=cfg.layer_norm_eps, p=p_hid, seed=seed, site=site + 3, tag="lt_res_ln_fwd")
-        h_pre, h = new(T, I), new(T, I)
+        h_pre, h = new(Tl, I), new(Tl, I)
         ops.linear_tile(a, fp.bf16(P + "intermediate.dense.weight"), h, ops.LT_GELU,
                         bias=fp.f32(P + "intermediate.dense.bias"), aux_out=h_pre, tag="lt_gelu_fwd")
-        y, z2 = new(T, H), new(T, H)
+        y, z2 = new(Tl, H), new(Tl, H)
         ops.linear_tile(h, fp.bf16(P + "output.dense.weight"), y, ops.LT_RES_LN, bias=fp.f32(P + "output.dense.bias"),
                         aux_out=z2, e_in=a, ln_g=fp.f32(P + "output.LayerNorm.weight"),
                         ln_b=fp.f32(P + "output.LayerNorm.bias"), ln_eps=cfg.layer_norm_eps, p=p_hid, seed=seed,
@@ -557,7 +578,7 @@ def _encode_forward(fp: FlatParams, pre: str, cfg: PMGTConfig, src: List[torch.T
         x = y
     if n_layers == 0:
         hidden_f32 = x.float()
-    return hidden_f32.view(R, L, H), run
+    return (hidden_f32 if compact else hidden_f32.view(R, L, H)), run
 
 
 def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun, d_hidden: torch.Tensor,
@@ -579,7 +600,9 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
             pool.release(*ts)
 
     G = arena.view
-    dy_f32 = d_hidden.contiguous().view(T, H)
+    last_rows = run.last_rows
+    dy_f32 = d_hidden.contiguous().view(-1, H)
+    top = cfg.num_hidden_layers - 1
     dy = None
     dy_b = None  # second gradient term of the layer input (the LayerNorm residual branch), tile path only
     deferred_dw = []
@@ -587,15 +610,18 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
         P = f"{pre}encoder.layer.{i}."
         site = 10 * (i + 1)
         x, qkvc, ctx, z1, a, h_pre, h, z2 = run.layers[i]
+        # the last layer's post-attention half ran on the compact row set (ctx is then the gathered [Tc, H] matrix)
+        compact = i == top and last_rows is not None
+        Tl = int(last_rows.numel()) if compact else T
         # ---- BertOutput: LayerNorm(dropout(dense(h)) + a)
-        dz2 = new(T, H)
-        do2 = new(T, H) if p_hid > 0 else dz2
-        ops.ln_bwd(T, H, z2, fp.f32(P + "output.LayerNorm.weight"), cfg.layer_norm_eps, p_hid, seed, site + 4, dz2, do2,
+        dz2 = new(Tl, H)
+        do2 = new(Tl, H) if p_hid > 0 else dz2
+        ops.ln_bwd(Tl, H, z2, fp.f32(P + "output.LayerNorm.weight"), cfg.layer_norm_eps, p_hid, seed, site + 4, dz2, do2,
                    G(P + "output.LayerNorm.weight"), G(P + "output.LayerNorm.bias"), dy_a=dy, dy_b=dy_b, dy_f32=dy_f32)
         dy_f32 = None
         # each dX kernel of a 128 x 128 Linear also forms that Linear's dW / dbias from the dY tile it already holds
         fused = FUSED_DW and H == 128 and I == 128
-        dh_pre = new(T, I)
+        dh_pre = new(Tl, I)
         if fused:
             ops.linear_tile(do2, fp.bf16(P + "output.dense.weight"), dh_pre, ops.LT_GELU_BWD, w_mn=True, e_in=h_pre,
                             dw_x=h, dw=G(P + "output.dense.weight"), dbias=G(P + "output.dense.bias"), tag="lt_dxdw_gelu")
@@ -604,7 +630,7 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
             ops.linear_tile(do2, fp.bf16(P + "output.dense.weight"), dh_pre, ops.LT_GELU_BWD, w_mn=True, e_in=h_pre,
                             tag="lt_dx_gelu")
         # ---- BertIntermediate
-        da = new(T, H)
+        da = new(Tl, H)
         if fused:
             ops.linear_tile(dh_pre, fp.bf16(P + "intermediate.dense.weight"), da, ops.LT_PLAIN, w_mn=True, dw_x=a,
                             dw=G(P + "intermediate.dense.weight"), dbias=G(P + "intermediate.dense.bias"), tag="lt_dxdw")
@@ -612,12 +638,12 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
             ops.dw_tile(dh_pre, a, G(P + "intermediate.dense.weight"), G(P + "intermediate.dense.bias"))
             ops.linear_tile(dh_pre, fp.bf16(P + "intermediate.dense.weight"), da, ops.LT_PLAIN, w_mn=True, tag="lt_dx")
         # ---- BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x); d a = da (FFN branch) + dz2 (residual branch)
-        dz1 = new(T, H)
-        do1 = new(T, H) if p_hid > 0 else dz1
-        ops.ln_bwd(T, H, z1, fp.f32(P + "attention.output.LayerNorm.weight"), cfg.layer_norm_eps, p_hid, seed, site + 3,
+        dz1 = new(Tl, H)
+        do1 = new(Tl, H) if p_hid > 0 else dz1
+        ops.ln_bwd(Tl, H, z1, fp.f32(P + "attention.output.LayerNorm.weight"), cfg.layer_norm_eps, p_hid, seed, site + 3,
                    dz1, do1, G(P + "attention.output.LayerNorm.weight"), G(P + "attention.output.LayerNorm.bias"),
                    dy_a=da, dy_b=dz2)
-        dctx = new(T, H)
+        dctx = new(Tl, H)
         if fused:
             ops.linear_tile(do1, fp.bf16(P + "attention.output.dense.weight"), dctx, ops.LT_PLAIN, w_mn=True, dw_x=ctx,
                             dw=G(P + "attention.output.dense.weight"), dbias=G(P + "attention.output.dense.bias"),
@@ -625,6 +651,17 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
         else:
             ops.dw_tile(do1, ctx, G(P + "attention.output.dense.weight"), G(P + "attention.output.dense.bias"))
             ops.linear_tile(do1, fp.bf16(P + "attention.output.dense.weight"), dctx, ops.LT_PLAIN, w_mn=True, tag="lt_dx")
+        if compact:
+            # back to the full token set: rows outside `last_rows` carry no gradient from this layer's second half
+            dctx_c, dz1_c = dctx, dz1
+            dctx, dz1 = new(T, H), new(T, H)
+            ops.zero_(dctx)
+            ops.zero_(dz1)
+            ops.scatter_rows(dctx_c, last_rows, dctx)
+            ops.scatter_rows(dz1_c, last_rows, dz1)
+            done(dctx_c, dz1_c)  # their last readers (the scatters; the dX kernel that read do1) are enqueued
+            if do1 is dz1_c:
+                do1 = dz1  # no dropout: do1 aliased the compact dz1, which has just been released
         # ---- dual-softmax attention core, then the fused Q/K/V/C projection
         dqkvc = new(T, 4 * H)
         ops.attn_core_bwd(ops.attn_args(R, L, H, heads, float(cfg.beta), qkvc, run.mask, p_att, seed, site, dctx=dctx,
@@ -718,14 +755,15 @@ class _EncodeFn(torch.autograd.Function):
     that autograd routes their gradients; the data is read from ``fp``."""
 
     @staticmethod
-    def forward(ctx, host, src_v, src_t, rows_idx, mask, R, L, training, seed, arena, keep, *params):
+    def forward(ctx, host, src_v, src_t, rows_idx, mask, R, L, training, seed, arena, keep, last_rows, *params):
         fp, pre, cfg = host._fp, host._fp_prefix, host.config
-        plan = host._plan_for(fp, [src_v, src_t], rows_idx, R, L, training, keep, arena)
+        plan = host._plan_for(fp, [src_v, src_t], rows_idx, R, L, training, keep, arena, last_rows)
         host._active_plan = plan
         if plan is not None:
-            hidden, run = plan.forward(fp, pre, cfg, [src_v, src_t], rows_idx, mask, training, seed, keep), None
+            hidden, run = plan.forward(fp, pre, cfg, [src_v, src_t], rows_idx, mask, training, seed, keep, last_rows), None
         else:
-            hidden, run = _encode_forward(fp, pre, cfg, [src_v, src_t], rows_idx, R, L, mask, training, seed, keep)
+            hidden, run = _encode_forward(fp, pre, cfg, [src_v, src_t], rows_idx, R, L, mask, training, seed, keep,
+                                          last_rows=last_rows)
         ctx.host, ctx.run, ctx.arena, ctx.n_params, ctx.plan, ctx.keep = host, run, arena, len(params), plan, keep
         return hidden
 
@@ -743,7 +781,7 @@ class _EncodeFn(torch.autograd.Function):
             _encode_backward(fp, pre, cfg, run, d_hidden, arena)
             ctx.run = None
         grads = tuple(arena.view(n) for n in host._encoder_param_names)
-        return (None,) * 11 + grads
+        return (None,) * 12 + grads
 
 
 class PMGTPretrainedModel(nn.Module):
@@ -808,7 +846,7 @@ class PMGTModel(PMGTPretrainedModel):
         self._plans = {}
         self._active_plan = None
 
-    def _plan_for(self, fp, src, rows_idx, R, L, training, keep, arena) -> Optional["_EncoderPlan"]:
+    def _plan_for(self, fp, src, rows_idx, R, L, training, keep, arena, last_rows=None) -> Optional["_EncoderPlan"]:
         """The launch plan for this call, or None when plans are off or the call is not plannable (dense inputs,
         a transient gradient arena, or a forward whose backward is still outstanding on the same plan)."""
         if not self.use_launch_plans or rows_idx is None or (keep and not getattr(arena, "persistent", False)):
@@ -816,12 +854,14 @@ class PMGTModel(PMGTPretrainedModel):
         cfg = self.config
         key = (R, L, bool(training), bool(keep), float(cfg.hidden_dropout_prob), float(cfg.attention_probs_dropout_prob),
                tuple((t.data_ptr(), tuple(t.shape)) for t in src), fp.flat.data_ptr(), fp.flat_bf16.data_ptr(),
-               arena.get().data_ptr() if keep else 0, ops.cur_stream(), PROJECTION_MODE)
+               arena.get().data_ptr() if keep else 0, ops.cur_stream(), PROJECTION_MODE,
+               int(last_rows.numel()) if last_rows is not None else -1)
         plan = self._plans.get(key)
         if plan is None:
             if len(self._plans) >= 4:  # e.g. full batch, tail batch, eval batch; drop the oldest beyond that
                 self._plans.pop(next(iter(self._plans)))
-            plan = _EncoderPlan(key, R, L, cfg.hidden_size, rows_idx.device)
+            plan = _EncoderPlan(key, R, L, cfg.hidden_size, rows_idx.device,
+                                n_last=int(last_rows.numel()) if last_rows is not None else 0)
             self._plans[key] = plan
         elif plan.pending_backward:
             return None
@@ -844,7 +884,10 @@ class PMGTModel(PMGTPretrainedModel):
             self.__dict__["_encoder_params_cache"] = ps
         return ps
 
-    def encode(self, src_v, src_t, rows_idx, mask, R, L, arena=None, refresh=True):
+    def encode(self, src_v, src_t, rows_idx, mask, R, L, arena=None, refresh=True, last_rows=None):
+        """``last_rows`` (sorted unique token indices): return only those rows of the final hidden state, as a
+        ``[len(last_rows), H]`` matrix; on the token-tile path the last layer's post-attention half is then computed for
+        those rows only (see ``_encode_forward``)."""
         fp = self._flat()
         if refresh:
             fp.refresh_bf16()
@@ -854,7 +897,15 @@ class PMGTModel(PMGTPretrainedModel):
         mask = mask.to(torch.float32).contiguous()
         params = self._encoder_params()
         keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        return _EncodeFn.apply(self, src_v, src_t, rows_idx, mask, R, L, self.training, seed, arena, keep, *params)
+        cfg = self.config
+        in_kernel = (last_rows is not None and cfg.num_hidden_layers > 0
+                     and _tile_path(cfg.hidden_size, cfg.intermediate_size))
+        out = _EncodeFn.apply(self, src_v, src_t, rows_idx, mask, R, L, self.training, seed, arena, keep,
+                              last_rows if in_kernel else None, *params)
+        if last_rows is not None and not in_kernel:  # other widths: encode everything, then pick the rows
+            self._active_plan = None  # the gradient of the picked rows does not line up with the plan's buffer
+            out = out.reshape(R * L, -1).index_select(0, last_rows)
+        return out
 
     def forward(self, *input_feat_embeds, attention_mask=None, head_mask=None, output_attentions=None,
                 output_hidden_states=None, return_dict=None):

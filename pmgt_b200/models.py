@@ -131,6 +131,21 @@ class PMGT(PMGTPretrainedModel):
             self._tables_bf16, self._tables_key = out, key
         return self._tables_bf16
 
+    def _last_rows(self, B: int, SP: int, L: int, with_masked: bool, dev) -> torch.Tensor:
+        """Token indices (in the batched [targets | pairs | masked targets] order) whose final state is consumed."""
+        key = (B, SP, L, with_masked, str(dev))
+        cache = self.__dict__.setdefault("_last_rows_cache", {})
+        sel = cache.get(key)
+        if sel is None:
+            parts = [torch.arange(B * L, device=dev), B * L + torch.arange(SP, device=dev) * L]
+            if with_masked:
+                parts.append((B + SP) * L + torch.arange(B * L, device=dev))
+            sel = torch.cat(parts).contiguous()
+            if len(cache) > 8:
+                cache.clear()
+            cache[key] = sel
+        return sel
+
     def mask_nodes(self, node_ids: torch.Tensor, with_positions: bool = False):
         """models.py:131-151, same RNG consumption order (rand, randint, rand).  ``with_positions`` appends the
         (row, position-1) index pairs of the masked slots, so that ``forward`` needs no host sync of its own."""
@@ -205,21 +220,31 @@ class PMGT(PMGTPretrainedModel):
         ids_all = ids[0] if len(ids) == 1 else torch.cat(ids, dim=0)
         mask_all = masks[0] if len(masks) == 1 else torch.cat(masks, dim=0)
         R = ids_all.shape[0]
-        hidden = self.bert.encode(tables[0], tables[1], ids_all.reshape(-1).contiguous(), mask_all, R, L,
-                                  arena=arena, refresh=False)  # (R, L, H) fp32
-        H = hidden.shape[-1]
-        last_hidden_state = hidden[:B]
+        if pair_node_inputs is None:
+            hidden = self.bert.encode(tables[0], tables[1], ids_all.reshape(-1).contiguous(), mask_all, R, L,
+                                      arena=arena, refresh=False)  # (R, L, H) fp32
+            H = hidden.shape[-1]
+            last_hidden_state = hidden[:B]
+        else:
+            # Only these token rows of the final hidden state are consumed: every position of the targets (returned as
+            # last_hidden_state), position 0 of the pairs (GSR), every position of the masked targets (NFR reads the
+            # masked ones).  The encoder prunes its last layer to them and returns the compact [Tc, H] matrix.
+            dev = t_ids.device
+            sel = self._last_rows(B, SP, L, nfr_on, dev)
+            hidden = self.bert.encode(tables[0], tables[1], ids_all.reshape(-1).contiguous(), mask_all, R, L,
+                                      arena=arena, refresh=False, last_rows=sel)  # (Tc, H) fp32
+            H = hidden.shape[-1]
+            last_hidden_state = hidden[:B * L].view(B, L, H)
 
         loss = None
         prediction_logits = None
         if pair_node_inputs is not None:
-            dev = hidden.device
-            # tokens the losses read: position 0 of targets and pairs, masked positions of the masked rows
-            tok = [torch.arange(0, (B + SP) * L, L, device=dev)]
+            # compact row numbers of what the losses read: position 0 of targets and pairs, masked positions
+            tok = [torch.arange(0, B * L, L, device=dev), B * L + torch.arange(SP, device=dev)]
             if nfr_on:
-                tok.append((B + SP + m_pos[:, 0]) * L + m_pos[:, 1] + 1)
+                tok.append(B * L + SP + m_pos[:, 0] * L + m_pos[:, 1] + 1)
             plan = self.bert._active_plan
-            rows = _TakeRows.apply(hidden.view(R * L, H), torch.cat(tok) if len(tok) > 1 else tok[0],
+            rows = _TakeRows.apply(hidden, torch.cat(tok),
                                    plan.grad_buffer() if plan is not None and hidden.requires_grad else None)
             pair_off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
             torch.cumsum(num_pairs.to(dev), 0, out=pair_off[1:])

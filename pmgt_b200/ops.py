@@ -350,6 +350,13 @@ def gather_rows(src, idx, out):
          4 * idx.numel() * src.shape[1])
 
 
+def scatter_rows(src, idx, dst):
+    """dst[idx[r]] = src[r] (bf16 rows; idx unique)."""
+    _run("scatter_rows", _lib.lib().pmgt_scatter_rows_bf16, (ptr(src), src.stride(0), ptr(idx), idx.numel(), src.shape[1],
+                                                             ptr(dst), dst.stride(0), cur_stream()), 1,
+         4 * idx.numel() * src.shape[1])
+
+
 def adamw_step(p, g, m, v, decay_mask, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, grad_scale_dev=None):
     _run("adamw", _lib.lib().pmgt_adamw_step, (ptr(p), ptr(g), ptr(m), ptr(v), ptr(decay_mask), p.numel(), lr, beta1, beta2,
                                                eps, weight_decay, step, grad_scale, ptr(grad_scale_dev), cur_stream()),
