@@ -453,11 +453,10 @@ static int launch_mma(const pmgt_attn_args* a, cudaStream_t st) {
   constexpr int kWarps = AttnRing<L, DH, (BWD ? 5 : 4)>::kWarps;
   constexpr int smem = kWarps * AttnRing<L, DH, (BWD ? 5 : 4)>::kPerWarp;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) {
     if (BWD) PMGT_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel<L, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     else PMGT_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_fwd_kernel<L, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   const long long items = a->rows * a->heads;
   long long ctas = (items + kWarps - 1) / kWarps;

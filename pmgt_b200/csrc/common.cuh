@@ -41,6 +41,16 @@ void set_error(const char* fmt, ...);
 
 int num_sms();  // SM count of the current device (cached)
 
+// Per-kernel one-time setup (cudaFuncSetAttribute for > 48 KiB of dynamic shared memory) is per DEVICE: `mask` is the
+// call site's static bit set of devices already configured.  Returns true when the current device still needs it.
+inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if ((mask >> dev) & 1ull) return false;
+  mask |= 1ull << dev;
+  return true;
+}
+
 // ---------------------------------------------------------------------------
 // Programmatic dependent launch.  The encoder is a chain of ~170 short persistent kernels; launched the ordinary
 // way, each one pays launch latency + its own prologue (barrier init, TMEM allocation, tensor-map fetch) + the idle

@@ -340,11 +340,10 @@ int embed128_fwd(const pmgt_embed_args* a, cudaStream_t st) {
 
 int embed128_bwd(const pmgt_embed_args* a, cudaStream_t st) {
   const size_t smem = ((size_t)(8 + a->L) * 128 + 2) * sizeof(float);
-  static bool cfg = false;
-  if (!cfg) {
+  static unsigned long long cfg = 0;
+  if (first_use_on_device(cfg)) {
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    cfg = true;
   }
   const int grid = grid_for(a->rows, 1);
   if (a->row_idx)

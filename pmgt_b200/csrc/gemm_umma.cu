@@ -337,10 +337,9 @@ template <bool A_MN, bool B_MN, bool GA, bool GB, int STAGES>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelArgs& ka, dim3 grid, cudaStream_t st) {
   auto kern = umma_gemm_kernel<A_MN, B_MN, GA, GB, STAGES>;
   const int smem = 2 * STAGES * kOperandStageBytes + (int)sizeof(GemmSmem) + 1024;
-  static bool configured = false;  // one flag per instantiation
-  if (!configured) {
+  static unsigned long long configured = 0;  // one flag per instantiation
+  if (first_use_on_device(configured)) {
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, ka);
   PMGT_LAUNCH_CHECK();

@@ -712,10 +712,9 @@ static int launch_lt(const pmgt_linear_tile_args* a, cudaStream_t st) {
   using Lay = LtLayout<NC, KC, EPI, SA, SE, NSTG, SX>;
   static_assert(Lay::kTotal <= 232448, "shared memory budget (227 KiB)");
   auto kern = linear_tile_kernel<NC, KC, B_MN, EPI, SA, SE, NSTG, SX>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) {
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay::kTotal));
-    configured = true;
   }
   CUtensorMap tx, tw, te, to, ta;
   memset(&te, 0, sizeof(te));
@@ -752,10 +751,9 @@ static int launch_dw(const pmgt_dw_tile_args* a, int n, cudaStream_t st) {
   static_assert(smem <= 232448, "shared memory budget (227 KiB)");
   static_assert(sizeof(DwBatch) <= 4000, "kernel parameter space");
   auto kern = dw_tile_kernel<NC, SX, SD>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) {
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   DwBatch b;
   memset(&b, 0, sizeof(b));

@@ -208,10 +208,9 @@ int launch(const pmgt_lnbwd_args* a, const uint16_t* g0, const uint16_t* g1, cud
   constexpr int smem = kStages * kStageBytes + (int)sizeof(LnBars);
   static_assert(smem >= 32 * 2 * 128 * 4, "the ring doubles as the column-sum scratch");
   auto kern = ln_bwd_stream_kernel<NB, F32>;
-  static bool cfg = false;
-  if (!cfg) {
+  static unsigned long long cfg = 0;
+  if (first_use_on_device(cfg)) {
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    cfg = true;
   }
   long long chunks = (a->T + kRows - 1) / kRows;
   int grid = num_sms();

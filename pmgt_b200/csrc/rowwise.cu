@@ -809,10 +809,9 @@ int pmgt_embed_fuse_bwd(const pmgt_embed_args* a, void* stream) {
   if (a->H <= 128) {
     embed_fuse_bwd_kernel<1><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(*a);
   } else {
-    static bool cfg = false;
-    if (!cfg) {
+    static unsigned long long cfg = 0;
+    if (first_use_on_device(cfg)) {
       PMGT_CHECK_CUDA(cudaFuncSetAttribute(embed_fuse_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      cfg = true;
     }
     PMGT_REQUIRE(smem <= 227 * 1024, "pmgt_embed_fuse_bwd: H too large for shared-memory accumulators");
     embed_fuse_bwd_kernel<8><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(*a);
@@ -843,17 +842,15 @@ int pmgt_res_ln_bwd(const pmgt_resln_args* a, void* stream) {
   if (a->H <= 128) {
     res_ln_bwd_kernel<1><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(*a);
   } else if (a->H <= 768) {
-    static bool cfg6 = false;
-    if (!cfg6) {
+    static unsigned long long cfg6 = 0;
+    if (first_use_on_device(cfg6)) {
       PMGT_CHECK_CUDA(cudaFuncSetAttribute(res_ln_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      cfg6 = true;
     }
     res_ln_bwd_kernel<6><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(*a);
   } else {
-    static bool cfg = false;
-    if (!cfg) {
+    static unsigned long long cfg = 0;
+    if (first_use_on_device(cfg)) {
       PMGT_CHECK_CUDA(cudaFuncSetAttribute(res_ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      cfg = true;
     }
     res_ln_bwd_kernel<8><<<grid, kRowThreads, smem, (cudaStream_t)stream>>>(*a);
   }
