@@ -39,7 +39,7 @@ typedef enum pmgt_status {
 } pmgt_status;
 
 /* ABI version of this header; bumped on any signature change. */
-#define PMGT_B200_ABI_VERSION 7
+#define PMGT_B200_ABI_VERSION 8
 int pmgt_abi_version(void);
 const char* pmgt_last_error(void);
 
@@ -341,6 +341,35 @@ int pmgt_dw_tile(const pmgt_dw_tile_args* a, void* stream);
  * receives ~SMs / n partial sums instead of SMs and the fixed cost of the accumulator flush is paid once (used for the
  * Q/K/V/C weight gradients of all encoder layers, deferred to the end of the backward pass). */
 int pmgt_dw_tile_batch(const pmgt_dw_tile_args* a, int n, void* stream);
+
+/*
+ * Fused feed-forward block of one encoder layer, H = I = 128 (BertIntermediate + BertOutput as composed by
+ * PMGTLayer.feed_forward_chunk, pmgt/pmgt/modeling_pmgt.py:296-325):
+ *   pmgt_ffn_fwd   out = LayerNorm(dropout(gelu(a w1^T + b1) w2^T + b2) + a)      (optional fp32 copy out_f32)
+ *   pmgt_ffn_bwd   da = d(loss)/d(a) (feed-forward branch + residual branch) from dy (+ dy_b) = d(loss)/d(out);
+ *                  dw1, dw2, db1, db2, d_ln_g, d_ln_b are ACCUMULATED (fp32).  h_pre, h and the pre-LayerNorm sum are
+ *                  recomputed from `a` with the same arithmetic as the forward kernel (same dropout stream), nothing
+ *                  else is saved between the two calls.
+ * One persistent tcgen05 kernel each; intermediate activations stay in shared / tensor memory.
+ */
+typedef struct pmgt_ffn_args {
+  int64_t T;
+  const uint16_t* a; int64_t ld_a;          /* [T][128] bf16 */
+  const uint16_t* w1; const uint16_t* w2;   /* [128][128] bf16, contiguous: intermediate.dense.weight, output.dense.weight */
+  const float* b1; const float* b2;         /* [128] fp32 */
+  const float* ln_g; const float* ln_b; float ln_eps;
+  float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
+  uint16_t* out; int64_t ld_out;            /* fwd: [T][128] bf16 */
+  float* out_f32;                           /* fwd, optional: [T][128] fp32 */
+  const uint16_t* dy; int64_t ld_dy;        /* bwd: [T][128] bf16 */
+  const uint16_t* dy_b; int64_t ld_dy_b;    /* bwd, optional second term of the incoming gradient */
+  uint16_t* da; int64_t ld_da;              /* bwd: [T][128] bf16 */
+  float* dw1; float* dw2;                   /* bwd: [128][128] fp32 */
+  float* db1; float* db2; float* d_ln_g; float* d_ln_b;   /* bwd: [128] fp32, each may be NULL */
+} pmgt_ffn_args;
+
+int pmgt_ffn_fwd(const pmgt_ffn_args* a, void* stream);
+int pmgt_ffn_bwd(const pmgt_ffn_args* a, void* stream);
 
 /*
  * LayerNorm backward from the saved pre-LayerNorm input z (PMGT_LT_RES_LN's aux_out): dy = dy_a + dy_b +

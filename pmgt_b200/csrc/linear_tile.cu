@@ -19,12 +19,10 @@
 //                        vector reductions; four extra warps form the column sums from the staged images.
 //
 // Everything here is HBM-bound by construction (<= 128 FLOP/B); the roofline is the measured copy bandwidth.
-#include "umma.cuh"
+#include "tile.cuh"
 
 namespace pmgt {
 
-constexpr int kImgBytes = 32768;
-constexpr int kSlabBytes = 16384;
 constexpr int kAccSlots = 4;
 constexpr int kEpiWarps = 16;                     // 4 TMEM lane quarters x 4 column quarters (32 columns per thread)
 constexpr int kLtThreads = 96 + 32 * kEpiWarps;   // producer | MMA | store | 16 epilogue warps
@@ -48,28 +46,6 @@ struct LtParams {
   float* dbias;       // [N] fp32, accumulated, may be NULL
   int reverse;        // walk the token tiles in descending order (see next_tile_order)
 };
-
-// 16-byte chunk c8 (8 columns) of row r of an image
-__device__ __forceinline__ uint32_t img_off(int r, int c8) {
-  return (uint32_t)((c8 >> 3) * kSlabBytes + r * 128 + (((c8 & 7) ^ (r & 7)) << 4));
-}
-
-__device__ __forceinline__ void mma_128x128x128(uint32_t tmem_d, uint32_t a_img, bool a_mn, uint32_t b_img, bool b_mn,
-                                                uint32_t idesc, bool accumulate_first) {
-#pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
-    const uint64_t da = a_mn ? umma_desc(a_img + ks * 2048, kSlabBytes, 1024)
-                             : umma_desc(a_img + (ks >> 2) * kSlabBytes + (ks & 3) * 32, 16, 1024);
-    const uint64_t db = b_mn ? umma_desc(b_img + ks * 2048, kSlabBytes, 1024)
-                             : umma_desc(b_img + (ks >> 2) * kSlabBytes + (ks & 3) * 32, 16, 1024);
-    umma_bf16(tmem_d, da, db, idesc, (accumulate_first || ks > 0) ? 1u : 0u);
-  }
-}
-
-__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
 
 template <int NC, int KC, int EPI, int SA, int SE, int NSTG, int SX = 0>
 struct LtLayout {
@@ -95,22 +71,6 @@ struct LtBars {
   uint32_t tmem_base;
 };
 static_assert(sizeof(LtBars) <= 256, "barrier block");
-
-__device__ __forceinline__ void ld8f(const float* __restrict__ p, float (&v)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ uint4 pack8f(const float* v) {
-  uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-  return o;
-}
-__device__ __forceinline__ void unpack8f(const uint4& u, float* v) {
-  unpack_bf16x2(u.x, v[0], v[1]); unpack_bf16x2(u.y, v[2], v[3]);
-  unpack_bf16x2(u.z, v[4], v[5]); unpack_bf16x2(u.w, v[6], v[7]);
-}
 
 // Work item = one 128-token x 128-column output block.  Roles:
 //   warp 0      TMA producer: weights once, then activation (A) and epilogue-input (E) images, SA / SE deep
@@ -523,10 +483,6 @@ struct DwParams {
   long long ld_dw;
   float* dbias;
 };
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 constexpr int kDwBatchMax = 8;
 

@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AttnArgs, DwTileArgs, EmbedArgs, GemmArgs, GsrArgs, LinearTileArgs, LnBwdArgs, NfrArgs, ResLnArgs, check,
+from ._lib import (AttnArgs, DwTileArgs, EmbedArgs, FfnArgs, GemmArgs, GsrArgs, LinearTileArgs, LnBwdArgs, NfrArgs, ResLnArgs, check,
                    cur_stream, ptr)
 
 EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_ADDEND, EPI_OUT_F32, EPI_ATOMIC = 1, 2, 4, 8, 16, 32
@@ -207,6 +207,41 @@ def linear_tile(x, w, out, epi, *, w_mn=False, bias=None, aux_out=None, e_in=Non
     if out_f32 is not None:
         nbytes += 4 * T * N
     _run(tag or "linear_tile", _lib.lib().pmgt_linear_tile, (C.byref(a), cur_stream()), 1, nbytes, flops)
+
+
+def ffn_args(a, w1, b1, w2, b2, ln_g, ln_b, eps, p, seed, site):
+    """Argument block shared by ``ffn_fwd`` / ``ffn_bwd`` (fused feed-forward block, H = I = 128)."""
+    _require_cuda(a, "a")
+    f = FfnArgs()
+    f.T = a.shape[0]
+    f.a, f.ld_a = ptr(a), a.stride(0)
+    f.w1, f.w2, f.b1, f.b2 = ptr(w1), ptr(w2), ptr(b1), ptr(b2)
+    f.ln_g, f.ln_b, f.ln_eps = ptr(ln_g), ptr(ln_b), eps
+    f.dropout_p, f.dropout_seed, f.dropout_site = p, seed, site
+    return f
+
+
+def ffn_supported(H, I) -> bool:
+    return H == 128 and I == 128
+
+
+def ffn_fwd(f: FfnArgs, out, out_f32=None):
+    """out = LayerNorm(dropout(gelu(a w1^T + b1) w2^T + b2) + a): one persistent tcgen05 kernel, 2 rows per token."""
+    f.out, f.ld_out, f.out_f32 = ptr(out), out.stride(0), ptr(out_f32)
+    T = f.T
+    _run("ffn_fwd", _lib.lib().pmgt_ffn_fwd, (C.byref(f), cur_stream()), 1,
+         2 * T * 128 * (2 + (2 if out_f32 is not None else 0)) + 4 * 128 * 128, 4 * T * 128 * 128)
+
+
+def ffn_bwd(f: FfnArgs, dy, da, dw1, dw2, db1, db2, d_ln_g, d_ln_b, dy_b=None):
+    """da, dW1, dW2, db1, db2, d_gamma, d_beta of the fused feed-forward block from (a, dy [+ dy_b]); recomputes h / z."""
+    f.dy, f.ld_dy = ptr(dy), dy.stride(0)
+    f.dy_b, f.ld_dy_b = ptr(dy_b), (dy_b.stride(0) if dy_b is not None else 0)
+    f.da, f.ld_da = ptr(da), da.stride(0)
+    f.dw1, f.dw2, f.db1, f.db2, f.d_ln_g, f.d_ln_b = ptr(dw1), ptr(dw2), ptr(db1), ptr(db2), ptr(d_ln_g), ptr(d_ln_b)
+    T = f.T
+    _run("ffn_bwd", _lib.lib().pmgt_ffn_bwd, (C.byref(f), cur_stream()), 1,
+         2 * T * 128 * (3 + (1 if dy_b is not None else 0)) + 12 * 128 * 128, 12 * T * 128 * 128)
 
 
 def dw_tile(dy, x, dw_f32, dbias=None, tag="dw_tile"):
