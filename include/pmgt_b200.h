@@ -347,10 +347,11 @@ int pmgt_dw_tile_batch(const pmgt_dw_tile_args* a, int n, void* stream);
  * PMGTLayer.feed_forward_chunk, pmgt/pmgt/modeling_pmgt.py:296-325):
  *   pmgt_ffn_fwd   out = LayerNorm(dropout(gelu(a w1^T + b1) w2^T + b2) + a)      (optional fp32 copy out_f32)
  *   pmgt_ffn_bwd   da = d(loss)/d(a) (feed-forward branch + residual branch) from dy (+ dy_b) = d(loss)/d(out);
- *                  dw1, dw2, db1, db2, d_ln_g, d_ln_b are ACCUMULATED (fp32).  h_pre, h and the pre-LayerNorm sum are
- *                  recomputed from `a` with the same arithmetic as the forward kernel (same dropout stream), nothing
- *                  else is saved between the two calls.
- * One persistent tcgen05 kernel each; intermediate activations stay in shared / tensor memory.
+ *                  dw1, dw2, db1, db2, d_ln_g, d_ln_b are ACCUMULATED (fp32).  The forward call saves h = gelu(h_pre)
+ *                  and gelu'(h_pre) (bf16, `h` / `gp`, optional: pass both or neither); the backward call reads them
+ *                  back and recomputes the pre-LayerNorm sum from h with the forward kernel's arithmetic (same
+ *                  dropout stream), so neither h_pre nor the pre-LayerNorm sum is ever stored.
+ * One persistent tcgen05 kernel each; everything else stays in shared / tensor memory.
  */
 typedef struct pmgt_ffn_args {
   int64_t T;
@@ -361,6 +362,7 @@ typedef struct pmgt_ffn_args {
   float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
   uint16_t* out; int64_t ld_out;            /* fwd: [T][128] bf16 */
   float* out_f32;                           /* fwd, optional: [T][128] fp32 */
+  uint16_t* h; uint16_t* gp; int64_t ld_h;  /* [T][128] bf16 each (same pitch): written by fwd (optional), read by bwd */
   const uint16_t* dy; int64_t ld_dy;        /* bwd: [T][128] bf16 */
   const uint16_t* dy_b; int64_t ld_dy_b;    /* bwd, optional second term of the incoming gradient */
   uint16_t* da; int64_t ld_da;              /* bwd: [T][128] bf16 */

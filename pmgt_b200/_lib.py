@@ -123,6 +123,7 @@ class FfnArgs(C.Structure):
         ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("dropout_site", C.c_uint32),
         ("out", c_vp), ("ld_out", C.c_int64),
         ("out_f32", c_vp),
+        ("h", c_vp), ("gp", c_vp), ("ld_h", C.c_int64),
         ("dy", c_vp), ("ld_dy", C.c_int64),
         ("dy_b", c_vp), ("ld_dy_b", C.c_int64),
         ("da", c_vp), ("ld_da", C.c_int64),

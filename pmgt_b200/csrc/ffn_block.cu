@@ -6,11 +6,12 @@
 //
 // Both are persistent tcgen05 token-tile kernels (one CTA per SM, 128-token tiles, W1 and W2 resident in shared memory
 // as swizzled images that serve as K-major operands of the forward products and as MN-major operands of the dX
-// products).  The intermediate activations h_pre / h / z never leave the SM: forward keeps only `a` (which the
-// attention block wrote anyway) and the backward kernel RECOMPUTES h_pre, h and z from it -- two more 128^3 products
-// on an otherwise idle tensor pipe instead of 3 rows written + 4 rows read per token.
+// products).  Forward saves h = gelu(h_pre) and gelu'(h_pre) (both cost nothing extra to form: the erf and the
+// Gaussian density share one exponential); the backward kernel re-forms the pre-LayerNorm sum z from h with one more
+// 128^3 product on an otherwise idle tensor pipe, so neither h_pre nor z is ever stored and the backward epilogues do
+// no transcendental work at all -- both kernels are bound by instruction issue, not by HBM.
 //
-// HBM rows (256-byte bf16 token rows) per token: forward 2 (was 7 as GELU + RES_LN token-tile kernels), backward 3-4
+// HBM rows (256-byte bf16 token rows) per token: forward 4 (was 7 as GELU + RES_LN token-tile kernels), backward 5-6
 // (was 12 as LayerNorm backward + two fused dX+dW kernels).
 #include "tile.cuh"
 
@@ -29,8 +30,13 @@ struct FfnParams {
   uint64_t seed;
   uint32_t site;
   float* out_f32;
+  const uint16_t* a;      // the block input again: the residual rows are re-read in the accumulator layout
+  long long ld_a;
+  int save_act;           // forward: write h and gelu'(h_pre) for the backward kernel
   // backward
-  const uint16_t* dy_b;   // optional second gradient term, read straight from global memory
+  const uint16_t* dy;     // gradient terms, read straight from global memory in the accumulator layout
+  long long ld_dy;
+  const uint16_t* dy_b;   // optional second term
   long long ld_dy_b;
   float *dw1, *dw2, *db1, *db2, *dg, *dbeta;
 };
@@ -58,55 +64,92 @@ __device__ __forceinline__ void store_image(const CUtensorMap* tm, uint32_t src,
 // ---------------------------------------------------------------------------------------------------
 struct FfnFwdLayout {
   static constexpr int kW1 = 0, kW2 = kImgBytes;
-  static constexpr int kA = 2 * kImgBytes;          // 3 stages: a(n) -> (in place) z(n) -> y(n) -> TMA store
-  static constexpr int kHH = kA + 3 * kImgBytes;    // 2 stages: gelu output, K-major operand of the second product
-  static constexpr int kBar = kHH + 2 * kImgBytes;
+  static constexpr int kA = 2 * kImgBytes;          // a(n): operand of the first product only (the residual is re-read from L2)
+  static constexpr int kHH = 3 * kImgBytes;         // 2 stages: gelu output = operand of the second product + TMA store source
+  static constexpr int kGP = 5 * kImgBytes;         // gelu'(h_pre): TMA store source
+  static constexpr int kYS = 6 * kImgBytes;         // LayerNorm output: TMA store source
+  static constexpr int kBar = 7 * kImgBytes;
   static constexpr int kTotal = kBar + 256 + 1024;
 };
 
 struct FfnFwdBars {
   uint64_t w_full;
-  uint64_t a_full[3], a_empty[3], y_full[3];
+  uint64_t a_full, a_empty;
   uint64_t sh_full[2], sh_empty[2];
   uint64_t hh_full[2], hh_empty[2];
+  uint64_t gp_empty;
   uint64_t sz_full, sz_empty;
+  uint64_t y_full, y_empty;
   uint32_t tmem_base;
 };
 static_assert(sizeof(FfnFwdBars) <= 256, "barrier block");
 
-// warp 0: TMA producer | warp 1: MMA issuer | warp 2: store warp | warps 3..18: epilogue.
+__device__ __forceinline__ void tmem_st_x2(uint32_t taddr, float a, float b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float (&r)[8]) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+}
+
+// Row statistics of a 128-column row whose four 32-column quarters live in four different warps (the TMEM accumulator
+// layout): Chan's combination of (mean, M2) partials of equal weight.
+__device__ __forceinline__ void combine_stats(const float (&q)[8], float eps, float& mean, float& rstd) {
+  mean = 0.25f * (q[0] + q[2] + q[4] + q[6]);
+  const float d0 = q[0] - mean, d1 = q[2] - mean, d2 = q[4] - mean, d3 = q[6] - mean;
+  const float m2 = q[1] + q[3] + q[5] + q[7] + 32.f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+  rstd = rsqrtf(m2 * (1.f / 128.f) + eps);
+}
+
+// warp 0: TMA producer | warp 1: MMA issuer | warp 2: store warp | warps 3..18: epilogue (TMEM lane quarter x 32-column
+// quarter per warp: one row x 32 columns per thread).
 // Epilogue order is software-pipelined: gelu(n + 1) runs BEFORE layernorm(n), so the second product of tile n has the
-// whole gelu epilogue of tile n + 1 to complete and neither epilogue ever waits for the tensor pipe.
+// whole gelu epilogue of tile n + 1 to complete and neither epilogue waits for the tensor pipe.  LayerNorm stays in the
+// accumulator layout: the four warps that share a row exchange (mean, M2) partials through 8 spare TMEM columns.
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w1,
-               const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_out, const FfnParams p) {
+               const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_out,
+               const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_gp, const FfnParams p) {
   using Lay = FfnFwdLayout;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   FfnFwdBars* bars = reinterpret_cast<FfnFwdBars*>(smem + Lay::kBar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool save = p.save_act != 0;   // h and gelu' are written out for the backward kernel
   pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     mbar_init(&bars->w_full, 1);
-    for (int s = 0; s < 3; ++s) {
-      mbar_init(&bars->a_full[s], 1);
-      mbar_init(&bars->a_empty[s], 1);
-      mbar_init(&bars->y_full[s], kFfnEpiWarps);
-    }
+    mbar_init(&bars->a_full, 1);
+    mbar_init(&bars->a_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->sh_full[s], 1);
       mbar_init(&bars->sh_empty[s], kFfnEpiWarps);
       mbar_init(&bars->hh_full[s], kFfnEpiWarps);
-      mbar_init(&bars->hh_empty[s], 1);
+      mbar_init(&bars->hh_empty[s], save ? 2 : 1);   // second product done (+ the store of h has read it)
     }
+    mbar_init(&bars->gp_empty, 1);
     mbar_init(&bars->sz_full, 1);
     mbar_init(&bars->sz_empty, kFfnEpiWarps);
+    mbar_init(&bars->y_full, kFfnEpiWarps);
+    mbar_init(&bars->y_empty, 1);
     fence_barrier_init();
     prefetch_tmap(&tm_a);
     prefetch_tmap(&tm_w1);
     prefetch_tmap(&tm_w2);
     prefetch_tmap(&tm_out);
+    if (save) {
+      prefetch_tmap(&tm_h);
+      prefetch_tmap(&tm_gp);
+    }
     // weights are never written by the preceding kernels of the chain: request them before the dependency wait
     mbar_arrive_expect_tx(&bars->w_full, 2u * kImgBytes);
     load_image(smem_u32(smem + Lay::kW1), &tm_w1, &bars->w_full, 0, 0);
@@ -124,10 +167,9 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     if (lane == 0) {
       for (int n = 0; n < n_local; ++n) {
         const int tile = ffn_tile(p, blockIdx.x + n * gridDim.x);
-        const int s = n % 3;
-        mbar_wait(&bars->a_empty[s], ((n / 3) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&bars->a_full[s], (uint32_t)kImgBytes);
-        load_image(smem_u32(smem + Lay::kA + s * kImgBytes), &tm_a, &bars->a_full[s], 0, tile * 128);
+        mbar_wait(&bars->a_empty, (n & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&bars->a_full, (uint32_t)kImgBytes);
+        load_image(smem_u32(smem + Lay::kA), &tm_a, &bars->a_full, 0, tile * 128);
       }
     }
   } else if (warp == 1) {
@@ -137,12 +179,13 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       tcgen05_fence_after();
       const uint32_t w1 = smem_u32(smem + Lay::kW1), w2 = smem_u32(smem + Lay::kW2);
       auto mma1 = [&](int n) {  // S_h[n % 2] = a(n) W1^T
-        const int s = n % 3, sl = n & 1;
-        mbar_wait(&bars->a_full[s], (n / 3) & 1u);
+        const int sl = n & 1;
+        mbar_wait(&bars->a_full, n & 1u);
         mbar_wait(&bars->sh_empty[sl], ((n >> 1) & 1u) ^ 1u);
         tcgen05_fence_after();
-        mma_128x128x128(tmem_base + sl * 128u, smem_u32(smem + Lay::kA + s * kImgBytes), false, w1, false, idesc, false);
+        mma_128x128x128(tmem_base + sl * 128u, smem_u32(smem + Lay::kA), false, w1, false, idesc, false);
         umma_commit(&bars->sh_full[sl]);
+        umma_commit(&bars->a_empty);
       };
       mma1(0);
       for (int n = 0; n < n_local; ++n) {
@@ -158,14 +201,27 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   } else if (warp == 2) {
     if (lane == 0) {
-      for (int n = 0; n < n_local; ++n) {
+      auto store_act = [&](int n) {
+        if (!save) return;
         const int tile = ffn_tile(p, blockIdx.x + n * gridDim.x);
-        const int s = n % 3;
-        mbar_wait(&bars->y_full[s], (n / 3) & 1u);
-        store_image(&tm_out, smem_u32(smem + Lay::kA + s * kImgBytes), 0, tile * 128);
+        const int hb = n & 1;
+        mbar_wait(&bars->hh_full[hb], (n >> 1) & 1u);
+        store_image(&tm_h, smem_u32(smem + Lay::kHH + hb * kImgBytes), 0, tile * 128);
+        store_image(&tm_gp, smem_u32(smem + Lay::kGP), 0, tile * 128);
         tma_store_commit();
         tma_store_wait_read0();
-        mbar_arrive(&bars->a_empty[s]);
+        mbar_arrive(&bars->hh_empty[hb]);
+        mbar_arrive(&bars->gp_empty);
+      };
+      store_act(0);
+      for (int n = 0; n < n_local; ++n) {
+        if (n + 1 < n_local) store_act(n + 1);
+        const int tile = ffn_tile(p, blockIdx.x + n * gridDim.x);
+        mbar_wait(&bars->y_full, n & 1u);
+        store_image(&tm_out, smem_u32(smem + Lay::kYS), 0, tile * 128);
+        tma_store_commit();
+        tma_store_wait_read0();
+        mbar_arrive(&bars->y_empty);
       }
       tma_store_wait_all0();
     }
@@ -175,11 +231,9 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int cq = ew >> 2;         // column quarter
     const int r = quarter * 32 + lane;
     const int c0 = cq * 32;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t lane_addr = lane_base + (uint32_t)c0;
     const float ks = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
-    float ln_gm[8], ln_bt[8];  // LayerNorm affine of the 8 columns this lane owns in phase B
-    ld8f(p.ln_g + (lane & 15) * 8, ln_gm);
-    ld8f(p.ln_b + (lane & 15) * 8, ln_bt);
 
     auto epi_gelu = [&](int n) {
       const int sl = n & 1;
@@ -197,14 +251,23 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->sh_empty[sl]);
       mbar_wait(&bars->hh_empty[sl], ((n >> 1) & 1u) ^ 1u);
+      if (save) mbar_wait(&bars->gp_empty, (n & 1u) ^ 1u);
       unsigned char* hh = smem + Lay::kHH + sl * kImgBytes;
+      unsigned char* gpi = smem + Lay::kGP;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float b[8], h[8];
+        float b[8], h[8], gp[8];
         ld8f(p.b1 + c0 + g * 8, b);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) h[j] = gelu_erf(v[g * 8 + j] + b[j]);
+        for (int j = 0; j < 8; ++j) {
+          const float x = v[g * 8 + j] + b[j];
+          float cdf, pdf_x;
+          gelu_parts(x, cdf, pdf_x);
+          h[j] = x * cdf;
+          gp[j] = cdf + pdf_x;
+        }
         *reinterpret_cast<uint4*>(hh + img_off(r, cq * 4 + g)) = pack8f(h);
+        if (save) *reinterpret_cast<uint4*>(gpi + img_off(r, cq * 4 + g)) = pack8f(gp);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -213,7 +276,17 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
     auto epi_ln = [&](int n) {
       const int tile = ffn_tile(p, blockIdx.x + n * gridDim.x);
-      const int s = n % 3;
+      const long long tok = (long long)tile * 128 + r;
+      // the residual row comes straight from L2 (the tile was loaded by TMA a moment ago); issue before the wait
+      uint4 res[4];
+      if (tok < p.T) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.a + tok * p.ld_a + c0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) res[g] = __ldg(src + g);
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) res[g] = make_uint4(0, 0, 0, 0);
+      }
       mbar_wait(&bars->sz_full, n & 1u);
       tcgen05_fence_after();
       float v[32];
@@ -227,13 +300,11 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->sz_empty);
-      unsigned char* aimg = smem + Lay::kA + s * kImgBytes;
-      const long long tok = (long long)tile * 128 + r;
-      // phase A (row x 32 columns per thread, the TMEM layout): z = dropout(acc + b2) + a, rounded to bf16, written
-      // over the residual image in place
+      // z = bf16(dropout(acc + b2) + a): the backward kernel forms the same z the same way
+      float lsum = 0.f;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float b[8];
+        float b[8], x[8];
         ld8f(p.b2 + c0 + g * 8, b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[g * 8 + j] += b[j];
@@ -243,49 +314,50 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[g * 8 + j] = (k8 >> j) & 1u ? v[g * 8 + j] * ks : 0.f;
         }
-        uint4* zp = reinterpret_cast<uint4*>(aimg + img_off(r, cq * 4 + g));
-        float x[8];
-        unpack8f(*zp, x);
+        unpack8f(res[g], x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] += v[g * 8 + j];
-        *zp = pack8f(x);
-      }
-      named_bar_sync(1, 32 * kFfnEpiWarps);
-      // phase B (half-warp per row, 8 rows per warp): LayerNorm over the bf16-rounded z -- the backward kernel forms the
-      // same z the same way -- with the row statistics in four shuffles; y overwrites z in place and leaves by TMA
-      const int hl = lane & 15, sub = lane >> 4;
-#pragma unroll
-      for (int i2 = 0; i2 < 4; ++i2) {
-        const int row = ew * 8 + i2 * 2 + sub;
-        uint4* zp = reinterpret_cast<uint4*>(aimg + img_off(row, hl));
-        float zf[8];
-        unpack8f(*zp, zf);
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sum += zf[j];
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum * (1.f / 128.f);
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { zf[j] -= mean; q = fmaf(zf[j], zf[j], q); }
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-        const float rstd = rsqrtf(q * (1.f / 128.f) + p.ln_eps);
-        float y[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = zf[j] * rstd * ln_gm[j] + ln_bt[j];
-        *zp = pack8f(y);
-        const long long trow = (long long)tile * 128 + row;
-        if (p.out_f32 != nullptr && trow < p.T) {
-          float* o32 = p.out_f32 + trow * 128 + hl * 8;
-          *reinterpret_cast<float4*>(o32) = make_float4(y[0], y[1], y[2], y[3]);
-          *reinterpret_cast<float4*>(o32 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        for (int j = 0; j < 8; j += 2) {
+          float lo, hi;
+          unpack_bf16x2(pack_bf16x2(x[j] + v[g * 8 + j], x[j + 1] + v[g * 8 + j + 1]), lo, hi);
+          v[g * 8 + j] = lo;
+          v[g * 8 + j + 1] = hi;
+          lsum += lo + hi;
         }
+      }
+      const float lmean = lsum * (1.f / 32.f);
+      float m2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float d = v[j] - lmean; m2 = fmaf(d, d, m2); }
+      // exchange through 8 spare TMEM columns (two sets, alternating per tile: a fast warp's next write never lands on a
+      // set a slow warp is still reading)
+      const uint32_t xcol = lane_base + 384u + (uint32_t)((n & 1) * 8);
+      tmem_st_x2(xcol + (uint32_t)(cq * 2), lmean, m2);
+      tmem_wait_st();
+      tcgen05_fence_before();
+      named_bar_sync(1, 32 * kFfnEpiWarps);
+      tcgen05_fence_after();
+      float q[8], mean, rstd;
+      tmem_ld_x8(xcol, q);
+      combine_stats(q, p.ln_eps, mean, rstd);
+      mbar_wait(&bars->y_empty, (n & 1u) ^ 1u);
+      unsigned char* ys = smem + Lay::kYS;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float gm[8], bt[8];
+        ld8f(p.ln_g + c0 + g * 8, gm);
+        ld8f(p.ln_b + c0 + g * 8, bt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[g * 8 + j] = (v[g * 8 + j] - mean) * rstd * gm[j] + bt[j];
+        *reinterpret_cast<uint4*>(ys + img_off(r, cq * 4 + g)) = pack8f(v + g * 8);
+      }
+      if (p.out_f32 != nullptr && tok < p.T) {
+        float4* o32 = reinterpret_cast<float4*>(p.out_f32 + tok * 128 + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o32[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->y_full[s]);
+      if (lane == 0) mbar_arrive(&bars->y_full);
     };
 
     epi_gelu(0);
@@ -324,12 +396,12 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 
 struct FfnBwdLayout {
   static constexpr int kW1 = 0, kW2 = kImgBytes;
-  static constexpr int kXY = 2 * kImgBytes;        // two buffers alternating between the roles "a" and "h" (see below)
-  static constexpr int kDY = 4 * kImgBytes;        // dy -> (in place) d_o -> staging of d_a
-  static constexpr int kGP = 5 * kImgBytes;        // gelu'(h_pre) -> (in place) d h_pre
+  static constexpr int kX = 2 * kImgBytes;         // a(n): MN-major operand of the dW1 product (last product of the tile)
+  static constexpr int kY = 3 * kImgBytes;         // h(n): operand of the z product and of the dW2 product
+  static constexpr int kDO = 4 * kImgBytes;        // d_o: dropout-masked LayerNorm input gradient (operand of d_h, dW2)
+  static constexpr int kGP = 5 * kImgBytes;        // gelu'(h_pre) -> (in place) d h_pre -> (in place) staging of d_a
   static constexpr int kExch = 6 * kImgBytes;      // 2 x float2 [128 rows][4 column quarters]: row-statistic partials
-  static constexpr int kRed = kExch + 8192;        // end-of-kernel reduction of the bias / LayerNorm gradients
-  static constexpr int kBar = kRed + 8192;
+  static constexpr int kBar = kExch + 8192;        // (the exchange area doubles as the end-of-kernel reduction scratch)
   static constexpr int kTotal = kBar + 256 + 1024;
 };
 static_assert(FfnBwdLayout::kTotal <= 232448, "shared memory budget (227 KiB)");
@@ -337,32 +409,32 @@ static_assert(FfnFwdLayout::kTotal <= 232448, "shared memory budget (227 KiB)");
 
 struct FfnBwdBars {
   uint64_t w_full;
-  uint64_t a_full[2];      // a(n) landed in XY[n % 2]
-  uint64_t y_free[2];      // XY[s] no longer read by the tensor pipe (it held h(n): free after the dW2 product)
-  uint64_t dy_full, dy_free;
-  uint64_t c1, c2, c3, c4;             // tensor-pipe commits: h_pre | z | d_h + dW2 | d_a + dW1
-  uint64_t e1, e2, e3, e4;             // epilogue hand-offs (one arrival per epilogue warp)
+  uint64_t x_full, y_full, gp_full;
+  uint64_t y_free;           // h(n) no longer read by the tensor pipe (after the dW2 product)
+  uint64_t xg_free;          // a(n) and d h_pre(n) no longer read by the tensor pipe (after the dW1 product)
+  uint64_t st_free;          // the store of d_a(n) has read its staging (the GP buffer)
+  uint64_t c2, c3, c4;       // tensor-pipe commits: z | d_h + dW2 | d_a + dW1
+  uint64_t e2, e3, e4;       // epilogue hand-offs (one arrival per epilogue warp)
   uint64_t dw_done;
   uint32_t tmem_base;
 };
 static_assert(sizeof(FfnBwdBars) <= 256, "barrier block");
 
-// Per tile n (X = XY[n % 2] holds a(n), Y = XY[(n + 1) % 2] receives h(n); Sa = TMEM slot n % 2, Sb = the other one):
-//   MMA1  Sa  = a W1^T                               (issued one tile early, right after the last products of tile n - 1)
-//   E1    h = gelu(Sa + b1) -> Y, gelu'(.) -> GP
-//   MMA2  Sb  = h W2^T
-//   E2    z = bf16(dropout(Sb + b2) + a); LayerNorm backward with dy: dz -> Sa (fp32, tcgen05.st: the accumulator of
-//         the d_a product starts from the residual-branch gradient), d_o = dropout-masked dz -> DY in place;
-//         d_gamma, d_beta, d_b2 column sums
-//   MMA3  Sb  = d_o W2        MMA4  dW2 += d_o^T h        (then Y is free: a(n + 1) is loaded into it)
+// Per tile n (Sa = TMEM columns 0..127, Sb = 128..255, dW1 = 256..383, dW2 = 384..511):
+//   TMA   h(n) -> Y, gelu'(n) -> GP, a(n) -> X          (h one tile ahead: Y is free after the dW2 product)
+//   MMA2  Sb  = h W2^T                                   (issued as soon as E3 of tile n - 1 has drained Sb)
+//   E2    z = bf16(dropout(Sb + b2) + a)   [a, dy, dy_b read from global memory in the accumulator layout];
+//         LayerNorm backward: dz -> Sa (fp32, tcgen05.st: the accumulator of the d_a product starts from the
+//         residual-branch gradient), d_o = dropout-masked dz -> DO; d_gamma, d_beta, d_b2 column sums
+//   MMA3  Sb  = d_o W2        MMA4  dW2 += d_o^T h
 //   E3    d h_pre = Sb * gelu' -> GP in place; d_b1 column sums
 //   MMA5  Sa += d h_pre W1    MMA6  dW1 += d h_pre^T a
-//   E4    d_a = Sa -> bf16 -> DY (staging) -> TMA store   (then dy(n + 1) is loaded into DY)
-// dW1 / dW2 live in TMEM columns 256..511 for the whole kernel and are flushed once with vector reductions.
+//   E4    d_a = Sa -> bf16 -> GP (staging) -> TMA store
+// dW1 / dW2 live in TMEM for the whole kernel and are flushed once with vector reductions.
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w1,
-               const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_dy,
-               const __grid_constant__ CUtensorMap tm_da, const FfnParams p) {
+               const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_h,
+               const __grid_constant__ CUtensorMap tm_gp, const __grid_constant__ CUtensorMap tm_da, const FfnParams p) {
   using Lay = FfnBwdLayout;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -372,17 +444,15 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   if (threadIdx.x == 0) {
     mbar_init(&bars->w_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars->a_full[s], 1);
-      mbar_init(&bars->y_free[s], 1);
-    }
-    mbar_init(&bars->dy_full, 1);
-    mbar_init(&bars->dy_free, 1);
-    mbar_init(&bars->c1, 1);
+    mbar_init(&bars->x_full, 1);
+    mbar_init(&bars->y_full, 1);
+    mbar_init(&bars->gp_full, 1);
+    mbar_init(&bars->y_free, 1);
+    mbar_init(&bars->xg_free, 1);
+    mbar_init(&bars->st_free, 1);
     mbar_init(&bars->c2, 1);
     mbar_init(&bars->c3, 1);
     mbar_init(&bars->c4, 1);
-    mbar_init(&bars->e1, kFfnEpiWarps);
     mbar_init(&bars->e2, kFfnEpiWarps);
     mbar_init(&bars->e3, kFfnEpiWarps);
     mbar_init(&bars->e4, kFfnEpiWarps);
@@ -391,7 +461,8 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     prefetch_tmap(&tm_a);
     prefetch_tmap(&tm_w1);
     prefetch_tmap(&tm_w2);
-    prefetch_tmap(&tm_dy);
+    prefetch_tmap(&tm_h);
+    prefetch_tmap(&tm_gp);
     prefetch_tmap(&tm_da);
     mbar_arrive_expect_tx(&bars->w_full, 2u * kImgBytes);
     load_image(smem_u32(smem + Lay::kW1), &tm_w1, &bars->w_full, 0, 0);
@@ -409,16 +480,16 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       for (int n = 0; n < n_local; ++n) {
-        const int tile = ffn_tile(p, blockIdx.x + n * gridDim.x);
-        const int s = n & 1;
-        // a(n) goes into XY[n % 2], which held h(n - 1): free once the dW2 product of tile n - 1 has completed
-        if (n > 0) mbar_wait(&bars->y_free[s], ((n - 1) >> 1) & 1u);
-        mbar_arrive_expect_tx(&bars->a_full[s], (uint32_t)kImgBytes);
-        load_image(smem_u32(smem + Lay::kXY + s * kImgBytes), &tm_a, &bars->a_full[s], 0, tile * 128);
-        // dy(n) goes into DY once the store of d_a(n - 1) has read it
-        if (n > 0) mbar_wait(&bars->dy_free, (n - 1) & 1u);
-        mbar_arrive_expect_tx(&bars->dy_full, (uint32_t)kImgBytes);
-        load_image(smem_u32(smem + Lay::kDY), &tm_dy, &bars->dy_full, 0, tile * 128);
+        const int row0 = ffn_tile(p, blockIdx.x + n * gridDim.x) * 128;
+        if (n > 0) mbar_wait(&bars->y_free, (n - 1) & 1u);
+        mbar_arrive_expect_tx(&bars->y_full, (uint32_t)kImgBytes);
+        load_image(smem_u32(smem + Lay::kY), &tm_h, &bars->y_full, 0, row0);
+        if (n > 0) mbar_wait(&bars->xg_free, (n - 1) & 1u);
+        mbar_arrive_expect_tx(&bars->x_full, (uint32_t)kImgBytes);
+        load_image(smem_u32(smem + Lay::kX), &tm_a, &bars->x_full, 0, row0);
+        if (n > 0) mbar_wait(&bars->st_free, (n - 1) & 1u);
+        mbar_arrive_expect_tx(&bars->gp_full, (uint32_t)kImgBytes);
+        load_image(smem_u32(smem + Lay::kGP), &tm_gp, &bars->gp_full, 0, row0);
       }
     }
   } else if (warp == 1) {
@@ -430,37 +501,32 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_wait(&bars->w_full, 0u);
       tcgen05_fence_after();
       const uint32_t w1 = smem_u32(smem + Lay::kW1), w2 = smem_u32(smem + Lay::kW2);
-      const uint32_t dyi = smem_u32(smem + Lay::kDY), gpi = smem_u32(smem + Lay::kGP);
-      const uint32_t t_dw1 = tmem_base + 256u, t_dw2 = tmem_base + 384u;
-      auto mma1 = [&](int n) {
-        const int s = n & 1;
-        mbar_wait(&bars->a_full[s], (n >> 1) & 1u);
+      const uint32_t xi = smem_u32(smem + Lay::kX), yi = smem_u32(smem + Lay::kY);
+      const uint32_t doi = smem_u32(smem + Lay::kDO), gpi = smem_u32(smem + Lay::kGP);
+      const uint32_t sa = tmem_base, sb = tmem_base + 128u, t_dw1 = tmem_base + 256u, t_dw2 = tmem_base + 384u;
+      auto mma2 = [&](int n) {
+        mbar_wait(&bars->y_full, n & 1u);
         tcgen05_fence_after();
-        mma_128x128x128(tmem_base + s * 128u, smem_u32(smem + Lay::kXY + s * kImgBytes), false, w1, false, id_kk, false);
-        umma_commit(&bars->c1);
+        mma_128x128x128(sb, yi, false, w2, false, id_kk, false);
+        umma_commit(&bars->c2);
       };
-      mma1(0);
+      mma2(0);
       for (int n = 0; n < n_local; ++n) {
         const uint32_t ph = n & 1u;
-        const int s = n & 1;
-        const uint32_t x_img = smem_u32(smem + Lay::kXY + s * kImgBytes), y_img = smem_u32(smem + Lay::kXY + (s ^ 1) * kImgBytes);
-        const uint32_t sa = tmem_base + s * 128u, sb = tmem_base + (s ^ 1) * 128u;
-        mbar_wait(&bars->e1, ph);
-        tcgen05_fence_after();
-        mma_128x128x128(sb, y_img, false, w2, false, id_kk, false);
-        umma_commit(&bars->c2);
         mbar_wait(&bars->e2, ph);
         tcgen05_fence_after();
-        mma_128x128x128(sb, dyi, false, w2, true, id_kn, false);
-        mma_128x128x128(t_dw2, dyi, true, y_img, true, id_nn, n > 0);
+        mma_128x128x128(sb, doi, false, w2, true, id_kn, false);
+        mma_128x128x128(t_dw2, doi, true, yi, true, id_nn, n > 0);
         umma_commit(&bars->c3);
-        umma_commit(&bars->y_free[s ^ 1]);
-        mbar_wait(&bars->e3, ph);
+        umma_commit(&bars->y_free);
+        mbar_wait(&bars->e3, ph);       // d h_pre sits in GP, Sb has been drained
+        mbar_wait(&bars->x_full, ph);
         tcgen05_fence_after();
         mma_128x128x128(sa, gpi, false, w1, true, id_kn, true);   // accumulates onto the dz the epilogue stored
-        mma_128x128x128(t_dw1, gpi, true, x_img, true, id_nn, n > 0);
+        mma_128x128x128(t_dw1, gpi, true, xi, true, id_nn, n > 0);
         umma_commit(&bars->c4);
-        if (n + 1 < n_local) mma1(n + 1);   // Sb was drained by E3; a(n + 1) sits in Y
+        umma_commit(&bars->xg_free);
+        if (n + 1 < n_local) mma2(n + 1);
       }
       umma_commit(&bars->dw_done);
     }
@@ -470,10 +536,10 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       for (int n = 0; n < n_local; ++n) {
         const int tile = ffn_tile(p, blockIdx.x + n * gridDim.x);
         mbar_wait(&bars->e4, n & 1u);
-        store_image(&tm_da, smem_u32(smem + Lay::kDY), 0, tile * 128);
+        store_image(&tm_da, smem_u32(smem + Lay::kGP), 0, tile * 128);
         tma_store_commit();
         tma_store_wait_read0();
-        mbar_arrive(&bars->dy_free);
+        mbar_arrive(&bars->st_free);
       }
       tma_store_wait_all0();
     }
@@ -485,64 +551,49 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int r = quarter * 32 + lane;
     const int c0 = cq * 32;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+    const uint32_t t_sa = lane_addr, t_sb = lane_addr + 128u;
     const float ks = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
     float2* exch = reinterpret_cast<float2*>(smem + Lay::kExch);
-    unsigned char* dyimg = smem + Lay::kDY;
+    unsigned char* doimg = smem + Lay::kDO;
     unsigned char* gpimg = smem + Lay::kGP;
     float acc_dg = 0.f, acc_dbeta = 0.f, acc_db2 = 0.f, acc_db1 = 0.f;   // column c0 + lane, rows of this warp, all tiles
 
     for (int n = 0; n < n_local; ++n) {
       const int tile = ffn_tile(p, blockIdx.x + n * gridDim.x);
       const uint32_t ph = n & 1u;
-      const int s = n & 1;
-      const uint32_t t_sa = lane_addr + s * 128u, t_sb = lane_addr + (s ^ 1) * 128u;
-      unsigned char* ximg = smem + Lay::kXY + s * kImgBytes;         // a(n)
-      unsigned char* yimg = smem + Lay::kXY + (s ^ 1) * kImgBytes;   // h(n)
       const long long tok = (long long)tile * 128 + r;
       float v[32];
+      uint32_t dyp[16];   // dy of this thread's 32 columns, packed bf16x2 (dy + dy_b summed)
 
-      // ---- E1: h = gelu(h_pre), gelu'(h_pre)
-      mbar_wait(&bars->c1, ph);
-      tcgen05_fence_after();
-      {
-        uint32_t acc[32];
-        tmem_ld_x32(t_sa, acc);
-        tmem_wait_ld();
+      // ---- E2: recompute z, LayerNorm backward.  a / dy / dy_b rows come from global memory in the accumulator
+      // layout (64 contiguous bytes per thread); the loads are issued before the wait for the z product.
+      uint4 res[4];
+      if (tok < p.T) {
+        const uint4* sa_ = reinterpret_cast<const uint4*>(p.a + tok * p.ld_a + c0);
+        const uint4* sd_ = reinterpret_cast<const uint4*>(p.dy + tok * p.ld_dy + c0);
+        uint4 d[4];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-      }
+        for (int g = 0; g < 4; ++g) { res[g] = __ldg(sa_ + g); d[g] = __ldg(sd_ + g); }
+        if (p.dy_b != nullptr) {
+          const uint4* sb_ = reinterpret_cast<const uint4*>(p.dy_b + tok * p.ld_dy_b + c0);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float b[8], h[8], gp[8];
-        ld8f(p.b1 + c0 + g * 8, b);
+          for (int g = 0; g < 4; ++g) {
+            const uint4 e = __ldg(sb_ + g);
+            float x[8], y[8];
+            unpack8f(d[g], x);
+            unpack8f(e, y);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float x = v[g * 8 + j] + b[j];
-          float cdf, pdf_x;
-          gelu_parts(x, cdf, pdf_x);
-          h[j] = x * cdf;
-          gp[j] = cdf + pdf_x;
+            for (int j = 0; j < 8; ++j) x[j] += y[j];
+            d[g] = pack8f(x);
+          }
         }
-        *reinterpret_cast<uint4*>(yimg + img_off(r, cq * 4 + g)) = pack8f(h);
-        *reinterpret_cast<uint4*>(gpimg + img_off(r, cq * 4 + g)) = pack8f(gp);
-      }
-      tcgen05_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->e1);
-
-      // ---- E2: recompute z, LayerNorm backward
-      // the optional second gradient term comes straight from global memory; issue its loads before the wait
-      uint4 dyb[4];
-      if (p.dy_b != nullptr) {
-        if (tok < p.T) {
-          const uint4* src = reinterpret_cast<const uint4*>(p.dy_b + tok * p.ld_dy_b + c0);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) dyb[g] = __ldg(src + g);
-        } else {
+        for (int g = 0; g < 4; ++g) { dyp[4 * g] = d[g].x; dyp[4 * g + 1] = d[g].y; dyp[4 * g + 2] = d[g].z; dyp[4 * g + 3] = d[g].w; }
+      } else {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) dyb[g] = make_uint4(0, 0, 0, 0);
-        }
+        for (int g = 0; g < 4; ++g) res[g] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dyp[j] = 0u;
       }
       mbar_wait(&bars->c2, ph);
       tcgen05_fence_after();
@@ -568,8 +619,8 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[g * 8 + j] = (k8 >> j) & 1u ? v[g * 8 + j] * ks : 0.f;
         }
-        unpack8f(*reinterpret_cast<const uint4*>(ximg + img_off(r, cq * 4 + g)), x);
-        // z rounded to bf16 exactly as the forward kernel stores it before its LayerNorm
+        unpack8f(res[g], x);
+        // z rounded to bf16 exactly as the forward kernel rounds it before its LayerNorm
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
           float lo, hi;
@@ -586,43 +637,36 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int j = 0; j < 32; ++j) { const float d = v[j] - lmean; m2 = fmaf(d, d, m2); }
         exch[r * 4 + cq] = make_float2(lmean, m2);
       }
-      mbar_wait(&bars->dy_full, ph);   // dy(n) landed (long ago; acquire for the generic-proxy reads below)
       named_bar_sync(1, 32 * kFfnEpiWarps);
       float mean, rstd;
       {
+        float q[8];
         const float4 p01 = *reinterpret_cast<const float4*>(&exch[r * 4]);
         const float4 p23 = *reinterpret_cast<const float4*>(&exch[r * 4 + 2]);
-        mean = 0.25f * (p01.x + p01.z + p23.x + p23.z);
-        const float d0 = p01.x - mean, d1 = p01.z - mean, d2 = p23.x - mean, d3 = p23.z - mean;
-        const float m2 = p01.y + p01.w + p23.y + p23.w + 32.f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
-        rstd = rsqrtf(m2 * (1.f / 128.f) + p.ln_eps);
+        q[0] = p01.x; q[1] = p01.y; q[2] = p01.z; q[3] = p01.w; q[4] = p23.x; q[5] = p23.y; q[6] = p23.z; q[7] = p23.w;
+        combine_stats(q, p.ln_eps, mean, rstd);
       }
-      uint32_t dyp[16];   // dy of this thread's 32 columns, packed bf16x2 (dy_a + dy_b already summed)
       float s1 = 0.f, s2 = 0.f;
       {
         float pg[32];   // dy * xhat: the d_gamma terms
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float d[8], gm[8];
-          unpack8f(*reinterpret_cast<const uint4*>(dyimg + img_off(r, cq * 4 + g)), d);
-          if (p.dy_b != nullptr) {
-            float e[8];
-            unpack8f(dyb[g], e);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) d[j] += e[j];
-          }
+          float gm[8];
           ld8f(p.ln_g + c0 + g * 8, gm);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float xh = (v[g * 8 + j] - mean) * rstd;
-            v[g * 8 + j] = xh;
-            const float gg = d[j] * gm[j];
-            s1 += gg;
-            s2 = fmaf(gg, xh, s2);
-            pg[g * 8 + j] = d[j] * xh;
+          for (int j = 0; j < 8; j += 2) {
+            float d0, d1;
+            unpack_bf16x2(dyp[g * 4 + (j >> 1)], d0, d1);
+            const int c = g * 8 + j;
+            const float x0 = (v[c] - mean) * rstd, x1 = (v[c + 1] - mean) * rstd;
+            v[c] = x0;
+            v[c + 1] = x1;
+            const float g0 = d0 * gm[j], g1 = d1 * gm[j + 1];
+            s1 += g0 + g1;
+            s2 = fmaf(g0, x0, fmaf(g1, x1, s2));
+            pg[c] = d0 * x0;
+            pg[c + 1] = d1 * x1;
           }
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) dyp[g * 4 + (j >> 1)] = pack_bf16x2(d[j], d[j + 1]);
         }
         // second exchange in the other half of the exchange area: slow readers of the first one are not disturbed
         exch[512 + r * 4 + cq] = make_float2(s1, s2);
@@ -657,18 +701,19 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             v[c] = (kbits >> c) & 1u ? z0 * ks : 0.f;         // d_o: gradient wrt the dense output
             v[c + 1] = (kbits >> (c + 1)) & 1u ? z1 * ks : 0.f;
           }
-          *reinterpret_cast<uint4*>(dyimg + img_off(r, cq * 4 + g)) = pack8f(v + g * 8);
+          *reinterpret_cast<uint4*>(doimg + img_off(r, cq * 4 + g)) = pack8f(v + g * 8);
         }
         tmem_st_x32(t_sa, dzb);   // residual-branch gradient: the d_a accumulator starts from it
         tmem_wait_st();
       }
-      acc_db2 += warp_colsum32(v, lane);
       tcgen05_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->e2);
+      acc_db2 += warp_colsum32(v, lane);
 
       // ---- E3: d h_pre = d_h * gelu'(h_pre)
+      mbar_wait(&bars->gp_full, ph);
       mbar_wait(&bars->c3, ph);
       tcgen05_fence_after();
       {
@@ -704,7 +749,7 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
       }
 #pragma unroll
-      for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dyimg + img_off(r, cq * 4 + g)) = pack8f(v + g * 8);
+      for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(gpimg + img_off(r, cq * 4 + g)) = pack8f(v + g * 8);
       tcgen05_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
@@ -713,7 +758,8 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
     // ---- bias / LayerNorm parameter gradients: reduce the four lane quarters in shared memory, one atomic per column
     {
-      float* red = reinterpret_cast<float*>(smem + Lay::kRed);   // [4 quantities][4 quarters][128 columns]
+      named_bar_sync(1, 32 * kFfnEpiWarps);   // every reader of the exchange area is done: reuse it
+      float* red = reinterpret_cast<float*>(smem + Lay::kExch);   // [4 quantities][4 quarters][128 columns]
       red[(0 * 4 + quarter) * 128 + c0 + lane] = acc_dg;
       red[(1 * 4 + quarter) * 128 + c0 + lane] = acc_dbeta;
       red[(2 * 4 + quarter) * 128 + c0 + lane] = acc_db2;
@@ -726,7 +772,7 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       float* dst = qn == 0 ? p.dg : (qn == 1 ? p.dbeta : (qn == 2 ? p.db2 : p.db1));
       if (dst != nullptr && sum != 0.f) atomicAdd(dst + col, sum);
     }
-    // ---- dW1 / dW2 flush (rotated chunk order per CTA: 148 CTAs add into the same 2 x 64 KB)
+    // ---- dW1 / dW2 flush (rotated order per CTA: 148 CTAs add into the same 2 x 64 KB)
     mbar_wait(&bars->dw_done, 0u);
     tcgen05_fence_after();
 #pragma unroll 1
@@ -758,11 +804,13 @@ static int check_ffn(const pmgt_ffn_args* a, bool bwd) {
   PMGT_REQUIRE((((uintptr_t)a->w1 | (uintptr_t)a->w2 | (uintptr_t)a->b1 | (uintptr_t)a->b2 | (uintptr_t)a->ln_g |
                  (uintptr_t)a->ln_b) & 15) == 0, "pmgt_ffn: parameter alignment");
   PMGT_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "pmgt_ffn: bad dropout_p");
+  PMGT_REQUIRE((((uintptr_t)a->h | (uintptr_t)a->gp) & 15) == 0 && a->ld_h % 8 == 0, "pmgt_ffn: h / gp alignment");
   if (!bwd) {
     PMGT_REQUIRE(a->out && a->ld_out % 8 == 0 && ((uintptr_t)a->out & 15) == 0, "pmgt_ffn_fwd: out alignment");
     PMGT_REQUIRE(((uintptr_t)a->out_f32 & 15) == 0, "pmgt_ffn_fwd: out_f32 alignment");
+    PMGT_REQUIRE((a->h == nullptr) == (a->gp == nullptr), "pmgt_ffn_fwd: pass both h and gp, or neither");
   } else {
-    PMGT_REQUIRE(a->dy && a->da && a->dw1 && a->dw2, "pmgt_ffn_bwd: dy, da, dw1, dw2 required");
+    PMGT_REQUIRE(a->dy && a->da && a->dw1 && a->dw2 && a->h && a->gp, "pmgt_ffn_bwd: h, gp, dy, da, dw1, dw2 required");
     PMGT_REQUIRE(a->ld_dy % 8 == 0 && a->ld_da % 8 == 0 && a->ld_dy_b % 8 == 0 &&
                  (((uintptr_t)a->dy | (uintptr_t)a->da | (uintptr_t)a->dy_b | (uintptr_t)a->dw1 | (uintptr_t)a->dw2) & 15) == 0,
                  "pmgt_ffn_bwd: gradient buffer alignment");
@@ -778,6 +826,9 @@ static void fill_params(const pmgt_ffn_args* a, FfnParams& p) {
   p.b1 = a->b1; p.b2 = a->b2; p.ln_g = a->ln_g; p.ln_b = a->ln_b; p.ln_eps = a->ln_eps;
   p.dropout_p = a->dropout_p; p.seed = a->dropout_seed; p.site = a->dropout_site;
   p.out_f32 = a->out_f32;
+  p.a = a->a; p.ld_a = a->ld_a;
+  p.save_act = a->h != nullptr;
+  p.dy = a->dy; p.ld_dy = a->ld_dy;
   p.dy_b = a->dy_b; p.ld_dy_b = a->ld_dy_b;
   p.dw1 = a->dw1; p.dw2 = a->dw2; p.db1 = a->db1; p.db2 = a->db2; p.dg = a->d_ln_g; p.dbeta = a->d_ln_b;
 }
@@ -795,17 +846,23 @@ int pmgt_ffn_fwd(const pmgt_ffn_args* a, void* stream) {
   static unsigned long long configured = 0;
   if (first_use_on_device(configured))
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnFwdLayout::kTotal));
-  CUtensorMap ta, tw1, tw2, to;
+  CUtensorMap ta, tw1, tw2, to, th, tg;
   if ((rc = make_tmap(&ta, a->a, 128, a->T, a->ld_a, 64, 128))) return rc;
   if ((rc = make_tmap(&tw1, a->w1, 128, 128, 128, 64, 128))) return rc;
   if ((rc = make_tmap(&tw2, a->w2, 128, 128, 128, 64, 128))) return rc;
   if ((rc = make_tmap(&to, a->out, 128, a->T, a->ld_out, 64, 128))) return rc;
+  th = to;
+  tg = to;
+  if (a->h != nullptr) {
+    if ((rc = make_tmap(&th, a->h, 128, a->T, a->ld_h, 64, 128))) return rc;
+    if ((rc = make_tmap(&tg, a->gp, 128, a->T, a->ld_h, 64, 128))) return rc;
+  }
   FfnParams p;
   fill_params(a, p);
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   PMGT_CHECK_CUDA(launch_kernel(true, ffn_fwd_kernel, dim3(grid), dim3(kFfnThreads), FfnFwdLayout::kTotal,
-                                (cudaStream_t)stream, ta, tw1, tw2, to, p));
+                                (cudaStream_t)stream, ta, tw1, tw2, to, th, tg, p));
   return PMGT_OK;
 }
 
@@ -816,18 +873,19 @@ int pmgt_ffn_bwd(const pmgt_ffn_args* a, void* stream) {
   static unsigned long long configured = 0;
   if (first_use_on_device(configured))
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(ffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnBwdLayout::kTotal));
-  CUtensorMap ta, tw1, tw2, tdy, tda;
+  CUtensorMap ta, tw1, tw2, th, tg, tda;
   if ((rc = make_tmap(&ta, a->a, 128, a->T, a->ld_a, 64, 128))) return rc;
   if ((rc = make_tmap(&tw1, a->w1, 128, 128, 128, 64, 128))) return rc;
   if ((rc = make_tmap(&tw2, a->w2, 128, 128, 128, 64, 128))) return rc;
-  if ((rc = make_tmap(&tdy, a->dy, 128, a->T, a->ld_dy, 64, 128))) return rc;
+  if ((rc = make_tmap(&th, a->h, 128, a->T, a->ld_h, 64, 128))) return rc;
+  if ((rc = make_tmap(&tg, a->gp, 128, a->T, a->ld_h, 64, 128))) return rc;
   if ((rc = make_tmap(&tda, a->da, 128, a->T, a->ld_da, 64, 128))) return rc;
   FfnParams p;
   fill_params(a, p);
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   PMGT_CHECK_CUDA(launch_kernel(true, ffn_bwd_kernel, dim3(grid), dim3(kFfnThreads), FfnBwdLayout::kTotal,
-                                (cudaStream_t)stream, ta, tw1, tw2, tdy, tda, p));
+                                (cudaStream_t)stream, ta, tw1, tw2, th, tg, tda, p));
   return PMGT_OK;
 }
 

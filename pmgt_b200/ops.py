@@ -225,23 +225,27 @@ def ffn_supported(H, I) -> bool:
     return H == 128 and I == 128
 
 
-def ffn_fwd(f: FfnArgs, out, out_f32=None):
-    """out = LayerNorm(dropout(gelu(a w1^T + b1) w2^T + b2) + a): one persistent tcgen05 kernel, 2 rows per token."""
+def ffn_fwd(f: FfnArgs, out, out_f32=None, h=None, gp=None):
+    """out = LayerNorm(dropout(gelu(a w1^T + b1) w2^T + b2) + a): one persistent tcgen05 kernel; ``h`` / ``gp``
+    (gelu output and gelu'(h_pre), both or neither) are saved for ``ffn_bwd``."""
     f.out, f.ld_out, f.out_f32 = ptr(out), out.stride(0), ptr(out_f32)
+    f.h, f.gp, f.ld_h = ptr(h), ptr(gp), (h.stride(0) if h is not None else 0)
     T = f.T
-    _run("ffn_fwd", _lib.lib().pmgt_ffn_fwd, (C.byref(f), cur_stream()), 1,
-         2 * T * 128 * (2 + (2 if out_f32 is not None else 0)) + 4 * 128 * 128, 4 * T * 128 * 128)
+    rows = 2 + (2 if out_f32 is not None else 0) + (2 if h is not None else 0)
+    _run("ffn_fwd", _lib.lib().pmgt_ffn_fwd, (C.byref(f), cur_stream()), 1, 2 * T * 128 * rows + 4 * 128 * 128,
+         4 * T * 128 * 128)
 
 
-def ffn_bwd(f: FfnArgs, dy, da, dw1, dw2, db1, db2, d_ln_g, d_ln_b, dy_b=None):
-    """da, dW1, dW2, db1, db2, d_gamma, d_beta of the fused feed-forward block from (a, dy [+ dy_b]); recomputes h / z."""
+def ffn_bwd(f: FfnArgs, h, gp, dy, da, dw1, dw2, db1, db2, d_ln_g, d_ln_b, dy_b=None):
+    """da, dW1, dW2, db1, db2, d_gamma, d_beta of the fused feed-forward block from (a, h, gp, dy [+ dy_b])."""
+    f.h, f.gp, f.ld_h = ptr(h), ptr(gp), h.stride(0)
     f.dy, f.ld_dy = ptr(dy), dy.stride(0)
     f.dy_b, f.ld_dy_b = ptr(dy_b), (dy_b.stride(0) if dy_b is not None else 0)
     f.da, f.ld_da = ptr(da), da.stride(0)
     f.dw1, f.dw2, f.db1, f.db2, f.d_ln_g, f.d_ln_b = ptr(dw1), ptr(dw2), ptr(db1), ptr(db2), ptr(d_ln_g), ptr(d_ln_b)
     T = f.T
     _run("ffn_bwd", _lib.lib().pmgt_ffn_bwd, (C.byref(f), cur_stream()), 1,
-         2 * T * 128 * (3 + (1 if dy_b is not None else 0)) + 12 * 128 * 128, 12 * T * 128 * 128)
+         2 * T * 128 * (5 + (1 if dy_b is not None else 0)) + 12 * 128 * 128, 10 * T * 128 * 128)
 
 
 def dw_tile(dy, x, dw_f32, dbias=None, tag="dw_tile"):

@@ -78,7 +78,10 @@ def test_ffn_bwd(T, two_terms):
     dw2 = torch.full((128, 128), -0.5, device="cuda")
     db1, db2 = torch.ones(128, device="cuda"), torch.ones(128, device="cuda")
     dg, dbe = torch.ones(128, device="cuda"), torch.ones(128, device="cuda")
-    ops.ffn_bwd(ops.ffn_args(a, w1, b1, w2, b2, g, be, EPS, 0.0, 0, 0), dy, da, dw1, dw2, db1, db2, dg, dbe, dy_b=dy_b)
+    fa = ops.ffn_args(a, w1, b1, w2, b2, g, be, EPS, 0.0, 0, 0)
+    out, h, gp = (torch.empty(T, 128, device="cuda", dtype=BF16) for _ in range(3))
+    ops.ffn_fwd(fa, out, None, h, gp)
+    ops.ffn_bwd(fa, h, gp, dy, da, dw1, dw2, db1, db2, dg, dbe, dy_b=dy_b)
     a32 = a.float().requires_grad_(True)
     ps = [t.float().clone().requires_grad_(True) for t in (w1, b1, w2, b2, g, be)]
     h = F.gelu(F.linear(a32, ps[0], ps[1]))
@@ -102,12 +105,17 @@ def test_ffn_dropout_matches_the_unfused_chain(T):
     p, seed, site = 0.1, 0x1234567890ABCDEF, 14
     out = torch.empty(T, 128, device="cuda", dtype=BF16)
     fa = ops.ffn_args(a, w1, b1, w2, b2, g, be, EPS, p, seed, site)
-    ops.ffn_fwd(fa, out)
+    hs, gps = torch.empty_like(out), torch.empty_like(out)
+    ops.ffn_fwd(fa, out, None, hs, gps)
     # unfused chain
     h_pre, h, z, y = (torch.empty(T, 128, device="cuda", dtype=BF16) for _ in range(4))
     ops.linear_tile(a, w1, h, ops.LT_GELU, bias=b1, aux_out=h_pre)
     ops.linear_tile(h, w2, y, ops.LT_RES_LN, bias=b2, aux_out=z, e_in=a, ln_g=g, ln_b=be, ln_eps=EPS, p=p, seed=seed, site=site)
     _close(out, y.float(), 1e-2, name="out vs unfused")
+    _close(hs, h.float(), 1e-2, name="h vs unfused")
+    p32 = h_pre.float().requires_grad_(True)
+    F.gelu(p32).sum().backward()
+    _close(gps, p32.grad, 1e-2, name="gelu' vs autograd")
     # without dropout the result differs: the mask is really applied
     out0 = torch.empty_like(out)
     ops.ffn_fwd(ops.ffn_args(a, w1, b1, w2, b2, g, be, EPS, 0.0, seed, site), out0)
@@ -115,7 +123,7 @@ def test_ffn_dropout_matches_the_unfused_chain(T):
     # backward
     da = torch.empty(T, 128, device="cuda", dtype=BF16)
     grads = [torch.zeros(128, 128, device="cuda"), torch.zeros(128, 128, device="cuda")] + [torch.zeros(128, device="cuda") for _ in range(4)]
-    ops.ffn_bwd(fa, dy, da, *grads)
+    ops.ffn_bwd(fa, hs, gps, dy, da, *grads)
     dz, do = torch.empty(T, 128, device="cuda", dtype=BF16), torch.empty(T, 128, device="cuda", dtype=BF16)
     rg = [torch.zeros(128, 128, device="cuda"), torch.zeros(128, 128, device="cuda")] + [torch.zeros(128, device="cuda") for _ in range(4)]
     ops.ln_bwd(T, 128, z, g, EPS, p, seed, site, dz, do, rg[4], rg[5], dy_a=dy)

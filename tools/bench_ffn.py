@@ -13,7 +13,7 @@ w1, w2 = r(128, 128, k=0.1), r(128, 128, k=0.1)
 b1, b2 = torch.randn(128, device="cuda") * 0.3, torch.randn(128, device="cuda") * 0.3
 g, be = 1 + 0.1 * torch.randn(128, device="cuda"), 0.1 * torch.randn(128, device="cuda")
 a, dy = r(T, 128), r(T, 128, k=0.5)
-out, da = torch.empty_like(a), torch.empty_like(a)
+out, da, hs, gps = (torch.empty_like(a) for _ in range(4))
 h_pre, h, z, y, dz, do, dh_pre, da2 = (torch.empty_like(a) for _ in range(8))
 G = [torch.zeros(128, 128, device="cuda"), torch.zeros(128, 128, device="cuda")] + [torch.zeros(128, device="cuda") for _ in range(4)]
 ops.set_pdl(False)
@@ -21,11 +21,11 @@ fa = ops.ffn_args(a, w1, b1, w2, b2, g, be, 1e-12, p, 77, 14)
 
 
 def fused_fwd():
-    ops.ffn_fwd(fa, out)
+    ops.ffn_fwd(fa, out, None, hs, gps)
 
 
 def fused_bwd():
-    ops.ffn_bwd(fa, dy, da, *G)
+    ops.ffn_bwd(fa, hs, gps, dy, da, *G)
 
 
 def chain_fwd():
