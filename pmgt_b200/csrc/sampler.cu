@@ -11,6 +11,11 @@
 //          key = (score << 32) | ~first  (score desc, first appearance asc --
 //          Python's stable sorted(..., reverse=True) over dict insertion order).
 // The CPU replay of the same stream is oracle/philox_sampler.c.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
 #include "common.cuh"
 
 namespace pmgt {
@@ -22,6 +27,9 @@ struct pmgt_graph_impl {
   int64_t* indptr;
   int32_t* indices;
   float* cdf;
+  // Inverse-CDF acceleration, built once in pmgt_graph_create (see find_neighbour):
+  uint2* ec;         // [E] (cdf bits, neighbour id) interleaved: the probe that ends the search also delivers the id
+  uint16_t* guide;   // [E] guide[rs + j] = #{i : cdf[rs + i] <= j / deg}; NULL when some row has more than 65535 entries
 };
 
 constexpr int kSamplerThreads = 128;
@@ -31,6 +39,8 @@ struct SamplerParams {
   const int64_t* indptr;
   const int32_t* indices;
   const float* cdf;
+  const uint2* ec;
+  const uint16_t* guide;
   const int64_t* roots;
   const int64_t* keys;
   int64_t n_ctx;
@@ -55,6 +65,28 @@ __device__ __forceinline__ int upper_bound_cdf(const float* __restrict__ cdf, in
     if (__ldg(cdf + mid) <= u) lo = mid + 1; else hi = mid;
   }
   return lo < n ? lo : n - 1;
+}
+
+// Inverse-CDF draw with a guide table (Chen & Asau 1974): numpy's legacy choice() returns
+// searchsorted(cdf, u, side="right") -- the number of entries <= u -- clamped to deg - 1.  With u = u24 / 2^24 and
+// j = floor(u24 * deg / 2^24) (exact integer arithmetic) we have j / deg <= u, so guide[j] = #{cdf <= j / deg} is a lower
+// bound of the answer and a forward scan from there ends after ~1 entry on average: the dependent-load chain of a
+// draw shrinks from 2 + ceil(log2 deg) (row pointers, binary search, neighbour id) to ~4 (row pointers, guide entry,
+// one or two (cdf, id) pairs) -- on graphs that spill out of L2 every link of that chain is an HBM round trip, and the
+// kernel is bound by exactly that latency.  The result is identical to the binary search, entry for entry.
+__device__ __forceinline__ int32_t find_neighbour(const SamplerParams& p, int64_t rs, int deg, uint32_t word) {
+  const uint32_t u24 = word >> 8;
+  const float u = (float)u24 * (1.0f / 16777216.0f);
+  if (p.guide == nullptr) return __ldg(p.indices + rs + upper_bound_cdf(p.cdf + rs, deg, u));
+  const uint32_t j = (uint32_t)(((uint64_t)u24 * (uint64_t)(uint32_t)deg) >> 24);
+  int pos = (int)__ldg(p.guide + rs + j);
+  pos = pos < deg - 1 ? pos : deg - 1;
+  uint2 e = __ldg(p.ec + rs + pos);
+  while (pos < deg - 1 && __uint_as_float(e.x) <= u) {
+    ++pos;
+    e = __ldg(p.ec + rs + pos);
+  }
+  return (int32_t)e.y;
 }
 
 // SPT > 0: table_cap == SPT * 128 and max_ctx <= 8 -- the top-k keeps every thread's slots in registers, each warp
@@ -116,11 +148,7 @@ sample_contexts_kernel(const SamplerParams p) {
           const int64_t rs = __ldg(p.indptr + parent);
           const int deg = (int)(__ldg(p.indptr + parent + 1) - rs);
           if (d - ppos * s == 0) my_deg += (unsigned long long)deg;
-          if (deg > 0) {
-            const float u = (float)(word >> 8) * (1.0f / 16777216.0f);
-            const int pos = upper_bound_cdf(p.cdf + rs, deg, u);
-            nb = __ldg(p.indices + rs + pos);
-          }
+          if (deg > 0) nb = find_neighbour(p, rs, deg, word);
         }
         if (store) cur[d] = nb;
         if (nb != 0 && nb != root) {
@@ -180,6 +208,47 @@ sample_contexts_kernel(const SamplerParams p) {
             lo[w] = 0;
             hi[w] = dg[w];
           }
+          int32_t nb[4];
+          if (p.guide != nullptr) {
+            // guide entry -> first (cdf, id) pair -> forward scan, the four draws in lock-step
+            uint2 e[4];
+            int pos[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              pos[w] = 0;
+              if (dg[w] > 0) {
+                const uint32_t u24 = philox_word(r, w) >> 8;
+                const uint32_t j = (uint32_t)(((uint64_t)u24 * (uint64_t)(uint32_t)dg[w]) >> 24);
+                pos[w] = (int)__ldg(p.guide + rs[w] + j);
+              }
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              e[w] = make_uint2(0x7f800000u, 0u);  // +inf: an inactive draw never advances
+              if (dg[w] > 0) {
+                pos[w] = pos[w] < dg[w] - 1 ? pos[w] : dg[w] - 1;
+                e[w] = __ldg(p.ec + rs[w] + pos[w]);
+              }
+            }
+            while (true) {
+              bool adv[4];
+              bool any = false;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                adv[w] = dg[w] > 0 && pos[w] < dg[w] - 1 && __uint_as_float(e[w].x) <= uu[w];
+                any |= adv[w];
+              }
+              if (!any) break;
+#pragma unroll
+              for (int w = 0; w < 4; ++w)
+                if (adv[w]) {
+                  ++pos[w];
+                  e[w] = __ldg(p.ec + rs[w] + pos[w]);
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w) nb[w] = dg[w] > 0 ? (int32_t)e[w].y : 0;
+          } else {
           while ((lo[0] < hi[0]) | (lo[1] < hi[1]) | (lo[2] < hi[2]) | (lo[3] < hi[3])) {
             float cv[4];
             int mid[4];
@@ -194,10 +263,10 @@ sample_contexts_kernel(const SamplerParams p) {
                 if (cv[w] <= uu[w]) lo[w] = mid[w] + 1; else hi[w] = mid[w];
               }
           }
-          int32_t nb[4];
 #pragma unroll
           for (int w = 0; w < 4; ++w)
             nb[w] = dg[w] > 0 ? __ldg(p.indices + rs[w] + (lo[w] < dg[w] ? lo[w] : dg[w] - 1)) : 0;
+          }
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             if (!act[w]) continue;
@@ -439,8 +508,32 @@ int pmgt_graph_create(pmgt_graph** out, int device, int64_t num_nodes, int64_t n
   PMGT_CHECK_CUDA(cudaSetDevice(device));
   pmgt_graph_impl* g = new pmgt_graph_impl();
   g->device = device; g->num_nodes = num_nodes; g->num_edges = num_edges;
-  g->indptr = nullptr; g->indices = nullptr; g->cdf = nullptr;
+  g->indptr = nullptr; g->indices = nullptr; g->cdf = nullptr; g->ec = nullptr; g->guide = nullptr;
+  // host-side build of the interleaved (cdf, id) array and the guide table (one pass over the edges)
+  std::vector<uint2> ec((size_t)(num_edges > 0 ? num_edges : 1));
+  std::vector<uint16_t> guide((size_t)(num_edges > 0 ? num_edges : 1));
+  bool guide_ok = true;
+  for (int64_t row = 0; row < num_nodes + 2; ++row) {
+    const int64_t rs = indptr_host[row], m = indptr_host[row + 1] - rs;
+    if (m > 65535) guide_ok = false;
+    int64_t i = 0;
+    for (int64_t j = 0; j < m; ++j) {
+      uint32_t bits;
+      memcpy(&bits, &cdf_host[rs + j], 4);
+      ec[(size_t)(rs + j)] = make_uint2(bits, (uint32_t)indices_host[rs + j]);
+      const double thr = (double)j / (double)m;
+      while (i < m && (double)cdf_host[rs + i] <= thr) ++i;
+      guide[(size_t)(rs + j)] = (uint16_t)(i > 65535 ? 65535 : i);
+    }
+  }
   cudaError_t e = cudaMalloc(&g->indptr, sizeof(int64_t) * (num_nodes + 3));
+  if (e == cudaSuccess) e = cudaMalloc(&g->ec, sizeof(uint2) * ec.size());
+  if (e == cudaSuccess && num_edges) e = cudaMemcpy(g->ec, ec.data(), sizeof(uint2) * (size_t)num_edges, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && guide_ok) {
+    e = cudaMalloc(&g->guide, sizeof(uint16_t) * guide.size());
+    if (e == cudaSuccess && num_edges)
+      e = cudaMemcpy(g->guide, guide.data(), sizeof(uint16_t) * (size_t)num_edges, cudaMemcpyHostToDevice);
+  }
   if (e == cudaSuccess) e = cudaMalloc(&g->indices, sizeof(int32_t) * (num_edges > 0 ? num_edges : 1));
   if (e == cudaSuccess) e = cudaMalloc(&g->cdf, sizeof(float) * (num_edges > 0 ? num_edges : 1));
   if (e == cudaSuccess) e = cudaMemcpy(g->indptr, indptr_host, sizeof(int64_t) * (num_nodes + 3), cudaMemcpyHostToDevice);
@@ -448,7 +541,7 @@ int pmgt_graph_create(pmgt_graph** out, int device, int64_t num_nodes, int64_t n
   if (e == cudaSuccess && num_edges) e = cudaMemcpy(g->cdf, cdf_host, sizeof(float) * num_edges, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     set_error("pmgt_graph_create: %s", cudaGetErrorString(e));
-    cudaFree(g->indptr); cudaFree(g->indices); cudaFree(g->cdf);
+    cudaFree(g->indptr); cudaFree(g->indices); cudaFree(g->cdf); cudaFree(g->ec); cudaFree(g->guide);
     delete g;
     return PMGT_ERR_CUDA;
   }
@@ -459,7 +552,7 @@ int pmgt_graph_create(pmgt_graph** out, int device, int64_t num_nodes, int64_t n
 int pmgt_graph_destroy(pmgt_graph* gh) {
   if (!gh) return PMGT_OK;
   pmgt_graph_impl* g = reinterpret_cast<pmgt_graph_impl*>(gh);
-  cudaFree(g->indptr); cudaFree(g->indices); cudaFree(g->cdf);
+  cudaFree(g->indptr); cudaFree(g->indices); cudaFree(g->cdf); cudaFree(g->ec); cudaFree(g->guide);
   delete g;
   return PMGT_OK;
 }
@@ -483,6 +576,15 @@ int pmgt_sample_contexts(const pmgt_graph* gh, const int64_t* roots, const int64
   const pmgt_graph_impl* g = reinterpret_cast<const pmgt_graph_impl*>(gh);
   SamplerParams p{};
   p.indptr = g->indptr; p.indices = g->indices; p.cdf = g->cdf;
+  p.ec = g->ec;
+  {
+    static int use_guide = -1;  // PMGT_SAMPLER_GUIDE=0: plain binary search (A/B measurements)
+    if (use_guide < 0) {
+      const char* ev = getenv("PMGT_SAMPLER_GUIDE");
+      use_guide = (ev && ev[0] == '0') ? 0 : 1;
+    }
+    p.guide = use_guide ? g->guide : nullptr;
+  }
   p.roots = roots; p.keys = ctx_keys; p.n_ctx = n_ctx; p.n_node_ids = g->num_nodes + 2;
   p.depth = depth; p.max_ctx = max_ctx;
   int64_t level = 1, total = 0, stored = 1;

@@ -48,6 +48,7 @@ class ItemGraph:
                  weights: np.ndarray, cdf: Optional[np.ndarray] = None):
         indptr = np.ascontiguousarray(indptr, dtype=np.int64)
         indices = np.ascontiguousarray(indices, dtype=np.int32)
+        weights_in = np.asarray(weights)  # the softmax CDF is formed from the weights at the precision they arrive in
         weights = np.ascontiguousarray(weights, dtype=np.float32)
         if indptr.shape != (num_nodes + 3,):
             raise ValueError(f"indptr must have num_nodes+3={num_nodes + 3} entries, got {indptr.shape}")
@@ -63,7 +64,8 @@ class ItemGraph:
         self.indptr = indptr
         self.indices = indices
         self.weights = weights
-        self.cdf = np.ascontiguousarray(cdf, dtype=np.float32) if cdf is not None else _row_softmax_cdf(indptr, weights)
+        self.cdf = (np.ascontiguousarray(cdf, dtype=np.float32) if cdf is not None
+                    else _row_softmax_cdf(indptr, weights_in))  # fp64 math on fp64 weights like ss.softmax (datasets.py:27-29)
         self._handles = {}  # device index -> opaque pmgt_graph*
 
     # -- nx.Graph-like surface used by the reference's callers -----------------
@@ -95,7 +97,7 @@ class ItemGraph:
             idx.extend(adj.keys())
             wts.extend(d["weight"] for d in adj.values())
             indptr[node + 1] = len(idx)
-        return cls(n, indptr, np.asarray(idx, dtype=np.int32), np.asarray(wts, dtype=np.float32))
+        return cls(n, indptr, np.asarray(idx, dtype=np.int32), np.asarray(wts, dtype=np.float64))
 
     @classmethod
     def from_edge_list(cls, num_nodes: int, src: np.ndarray, dst: np.ndarray, weight: np.ndarray) -> "ItemGraph":
@@ -104,7 +106,18 @@ class ItemGraph:
         (edge i appends dst to src's row and src to dst's row, in edge order)."""
         src = np.asarray(src, dtype=np.int64)
         dst = np.asarray(dst, dtype=np.int64)
-        weight = np.asarray(weight, dtype=np.float32)
+        weight = np.asarray(weight)
+        # nx.Graph keeps ONE edge per unordered pair: a repeated (u, v) updates the weight of the existing edge and
+        # leaves its position in both adjacency lists where the first occurrence put it
+        code = np.minimum(src, dst) << 32 | np.maximum(src, dst)
+        uniq, first, inverse = np.unique(code, return_index=True, return_inverse=True)
+        if len(uniq) != len(code):
+            last = np.zeros(len(uniq), dtype=np.int64)
+            np.maximum.at(last, inverse, np.arange(len(code)))       # last occurrence carries the surviving weight
+            keep = np.sort(first)
+            w_last = weight[last]
+            weight = w_last[inverse[keep]]
+            src, dst = src[keep], dst[keep]
         m = len(src)
         order = np.arange(m, dtype=np.int64)
         rows = np.concatenate([src, dst])

@@ -60,6 +60,12 @@ class PMGT(PMGTPretrainedModel):
     ) -> None:
         config = config if config is not None else PMGTConfig()
         super().__init__(config)
+        if feat_init_emb is None:
+            # the reference would TRAIN randomly initialised tables in this case (models.py:49-54 freezes them only when
+            # feat_init_emb is given); the bf16 gather path here treats the tables as a frozen feature store
+            import warnings
+            warnings.warn("PMGT(feat_init_emb=None): feature tables are randomly initialised and stay frozen; the "
+                          "reference would train them. Pass the visual / textual feature matrices.", stacklevel=2)
         self.node_size = node_size
         self.random_node_ratio = random_node_ratio
         self.mask_node_ratio = mask_node_ratio

@@ -107,8 +107,17 @@ class DenseSparseAdamW(Optimizer):
             return None
         return self._flat["p"], self._flat_grad(self._flat)
 
+    def load_state_dict(self, state_dict):
+        """``torch.optim.Optimizer.load_state_dict`` + rebuild of the flat moment buffers: the flat fast path caches its
+        own ``m`` / ``v`` vectors, so after a resume they are re-derived from the loaded per-parameter state."""
+        super().load_state_dict(state_dict)
+        self._flat = None
+
     @torch.no_grad()
-    def step(self, closure=None, grad_scale: float = 1.0, grad_scale_dev=None):
+    def step(self, closure=None, grad_scale: float = 1.0, grad_scale_dev=None, flat_grad=None):
+        """``flat_grad``: the flat gradient vector to step with (as returned by ``flat_views()[1]``, e.g. after an
+        allreduce).  Passing it makes the step use exactly the reduced buffer even when ``flat_views`` had to COPY the
+        per-parameter gradients into a temporary (gradients that are not zero-copy views of one arena)."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -118,9 +127,16 @@ class DenseSparseAdamW(Optimizer):
                 if p.grad is not None and p.grad.is_sparse:
                     raise NotImplementedError("sparse gradients: PMGT's embeddings are frozen, the sparse branch of "
                                               "the reference optimizer is outside the pre-training path")
-        fv = self.flat_views()
+        if flat_grad is not None:
+            if self._flat is None:
+                self.flat_views()
+            fv = (self._flat["p"], flat_grad) if self._flat is not None else None
+        else:
+            fv = self.flat_views()
         if fv is not None and fv[1] is not None:
             fl = self._flat
+            if fv[1].numel() != fl["span"]:
+                raise ValueError("flat_grad does not match the flat parameter buffer")
             g0 = self.param_groups[0]
             step = self.state[fl["params"][0]]["step"] + 1
             for p in fl["params"]:

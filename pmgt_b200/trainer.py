@@ -97,6 +97,13 @@ def check_args(args: AttrDict) -> None:
         raise ValueError(f"Optimizer {args.optim} is not supported")
     if args.scheduler_type is not None:
         raise ValueError("LR schedulers are not wired in the reference's PMGT path (base_trainer.py:71-90 recurses)")
+    if args.mp_enabled:
+        # the reference's --mp-enabled is fp16 autocast + GradScaler (base_trainer.py:312); this implementation always
+        # computes in bf16 with fp32 accumulation / statistics, there is no fp16 path to switch on
+        raise ValueError("mp_enabled (fp16 autocast) is not supported: pmgt_b200 always runs bf16 tensor-core math with "
+                         "fp32 accumulation")
+    if int(args.accumulation_step or 1) < 1:
+        raise ValueError("accumulation_step must be >= 1")
 
 
 def init_run(args: AttrDict) -> None:
@@ -192,6 +199,9 @@ class PMGTTrainerModel:
         self._prefetched = None  # (dataset, indices, epoch, batch, masked, ready-event)
         self._loss_pin = None    # pinned host scalar the step's loss is copied into right after the forward pass
         self._loss_event = None
+        self._micro = 0          # micro-batches accumulated since the last optimizer step
+        self.epoch = 0           # next epoch to train (saved in checkpoints; Lightning's current_epoch)
+        self.best, self.bad_epochs, self.best_path = None, 0, None
 
     # -- inference: net(x)[0][:, 0] (trainer.py:153-154)
     def forward(self, x):
@@ -246,12 +256,18 @@ class PMGTTrainerModel:
 
     # -- one optimisation step on a sampled batch (sample -> fwd -> bwd -> allreduce -> AdamW)
     def train_on_indices(self, dataset: PMGTDataset, indices, epoch: int) -> torch.Tensor:
+        """One micro-batch: forward + backward, and -- every ``accumulation_step`` calls (pl.Trainer's
+        ``accumulate_grad_batches``, base_trainer.py:315) -- gradient allreduce, clipping and the AdamW step."""
         args = self.args
         if not self.net.training:
             self.net.train()
-        self.net.bert.use_launch_plans = True  # fixed-shape steps: record the encoder's launch list once, then replay
+        accum = max(1, int(args.accumulation_step or 1))
+        # fixed-shape steps: record the encoder's launch list once, then replay.  Launch plans write the gradients of
+        # every pass into the same arena, so with gradient accumulation (which must ADD passes) they stay off.
+        self.net.bert.use_launch_plans = accum == 1
         pf = self._take_prefetched(dataset, indices, epoch)
-        self.optimizer.zero_grad(set_to_none=True)
+        if self._micro == 0:
+            self.optimizer.zero_grad(set_to_none=True)
         if pf is not None:
             batch, masked = pf
             loss = self.net(*batch, masked_inputs=masked)[0]
@@ -266,14 +282,18 @@ class PMGTTrainerModel:
         self._loss_pin.copy_(loss.detach(), non_blocking=True)
         self._loss_event.record()
         loss.backward()
+        self._micro += 1
+        if self._micro < accum:
+            return loss.detach()
+        self._micro = 0
         rank, ws = world()
-        scale = 1.0
+        scale = 1.0 / accum
         fv = self.optimizer.flat_views()
         if ws > 1:
             if fv is None or fv[1] is None:
                 raise RuntimeError("data-parallel training needs the flat gradient buffer")
             dist.all_reduce(fv[1])  # ONE allreduce of the flat gradient (sum); mean folded into the step
-            scale = 1.0 / ws
+            scale = scale / ws
         scale_dev = None
         if args.gradient_max_norm:
             # torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)), on the averaged gradient
@@ -288,7 +308,10 @@ class PMGTTrainerModel:
                         ops.sumsq(p.grad.contiguous().view(-1), self._sumsq)
             norm = self._sumsq.sqrt() * scale
             scale_dev = (scale * torch.clamp(args.gradient_max_norm / (norm + 1e-6), max=1.0)).to(torch.float32)
-        self.optimizer.step(grad_scale=scale, grad_scale_dev=scale_dev)
+        # step with exactly the buffer that was reduced / measured above (it is a temporary when the gradients are not
+        # zero-copy views of the arena: a second flat_views() call would rebuild it from the un-reduced p.grad)
+        self.optimizer.step(grad_scale=scale, grad_scale_dev=scale_dev,
+                            flat_grad=fv[1] if fv is not None else None)
         self.global_step += 1
         return loss.detach()
 
@@ -315,7 +338,8 @@ class PMGTTrainerModel:
             preds.append(p)
             labels.append(l)
             losses.append(float(loss))
-        preds, labels = np.concatenate(preds), np.concatenate(labels)
+        preds = np.concatenate(preds) if preds else np.zeros(0, dtype=np.float32)   # a rank's shard may be empty
+        labels = np.concatenate(labels) if labels else np.zeros(0, dtype=np.float32)
         if ws > 1:
             gathered = [None] * ws
             dist.all_gather_object(gathered, (preds, labels, losses))
@@ -326,11 +350,23 @@ class PMGTTrainerModel:
 
     def state_dict(self):
         return {"state_dict": {"net." + k: v for k, v in self.net.state_dict().items()},  # Lightning's "net." prefix
-                "optimizer": self.optimizer.state_dict(), "global_step": self.global_step}
+                "optimizer": self.optimizer.state_dict(), "global_step": self.global_step, "epoch": self.epoch,
+                "early_stopping": {"best": self.best, "bad_epochs": self.bad_epochs, "best_path": self.best_path}}
 
-    def load_state_dict(self, ckpt):
+    def load_state_dict(self, ckpt, weights_only: bool = False):
+        """Restore a checkpoint.  Like Lightning's ``fit(ckpt_path=...)`` (base_trainer.py:324-332) this brings back the
+        weights, the optimizer state (AdamW moments and step count), the epoch counter and the early-stopping
+        bookkeeping; ``weights_only`` restores just the weights (evaluation / inference of a best checkpoint)."""
         self.net.load_state_dict({k[len("net."):]: v for k, v in ckpt["state_dict"].items()})
+        self.net._tables_bf16 = None
+        if weights_only:
+            return
         self.global_step = ckpt.get("global_step", 0)
+        self.epoch = ckpt.get("epoch", 0)
+        es = ckpt.get("early_stopping") or {}
+        self.best, self.bad_epochs, self.best_path = es.get("best"), es.get("bad_epochs", 0), es.get("best_path")
+        if ckpt.get("optimizer") is not None:
+            self.optimizer.load_state_dict(ckpt["optimizer"])
 
 
 def _ckpt_dir(args: AttrDict) -> str:
@@ -339,30 +375,51 @@ def _ckpt_dir(args: AttrDict) -> str:
     return d
 
 
+def _barrier():
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def epoch_batches(n: int, batch: int, rank: int, ws: int, perm: np.ndarray) -> List[np.ndarray]:
+    """Index batches of ``rank`` for one epoch: every full global batch of ``batch * ws`` targets, then the tail
+    (the reference's DataLoader keeps the partial last batch: shuffle=True, drop_last=False, trainer.py:90-103), split
+    evenly over the ranks; ranks whose tail share would be empty re-use the first tail targets so that every rank runs
+    the same number of steps (the allreduce is collective)."""
+    per = batch * ws
+    full = n // per
+    out = [shard_indices(perm, step, batch, rank, ws) for step in range(full)]
+    tail = perm[full * per:]
+    if len(tail):
+        share = -(-len(tail) // ws)
+        mine = tail[rank * share: (rank + 1) * share]
+        if len(mine) == 0:
+            mine = tail[:1]
+        out.append(mine)
+    return out
+
+
 def train(args: AttrDict, is_hptuning: bool = False, trial=None, enable_trial_pruning: bool = False):
     """base_trainer.py:266-341: fit with early stopping + last/best checkpoints.  Returns (best_score, trainer)."""
     tm = PMGTTrainerModel(args)
     rank, ws = world()
     ds: PMGTDataset = args.train_dataset
     B = args.train_batch_size
-    steps_per_epoch = len(ds) // (B * ws)
-    if steps_per_epoch == 0:
-        raise ValueError("train_batch_size x world_size exceeds the number of training nodes")
     monitor = "loss" if args.early_criterion == "loss" else "auc"
-    best, bad_epochs, best_path = None, 0, None
     ckpt_dir = _ckpt_dir(args)
     last_path = os.path.join(ckpt_dir, "last.ckpt")
     if args.run_id is not None and os.path.exists(last_path):  # resume (base_trainer.py:324-332)
         tm.load_state_dict(torch.load(last_path, map_location=args.device, weights_only=False))
     args.history = []
-    for epoch in range(args.num_epochs):
+    for epoch in range(tm.epoch, args.num_epochs):
+        if args.early and tm.bad_epochs >= args.early:
+            break
         perm = epoch_permutation(len(ds), args.seed, epoch)
         t0 = time.time()
         running = []
-        shards = [shard_indices(perm, step, B, rank, ws) for step in range(steps_per_epoch)]
-        for step in range(steps_per_epoch):
+        shards = epoch_batches(len(ds), B, rank, ws, perm)
+        for step in range(len(shards)):
             loss = tm.train_on_indices(ds, shards[step], epoch)
-            if step + 1 < steps_per_epoch:
+            if step + 1 < len(shards):
                 tm.prefetch(ds, shards[step + 1], epoch)  # sampling + corruption of the next batch overlap this step
             running.append(loss)
         train_loss = float(torch.stack(running).mean())
@@ -370,27 +427,36 @@ def train(args: AttrDict, is_hptuning: bool = False, trial=None, enable_trial_pr
         args.history.append({"epoch": epoch, "loss/train": train_loss, "loss/val": val["loss"], "val/auc": val["auc"],
                              "sec": time.time() - t0})
         score = val[monitor]
-        improved = best is None or (score < best if monitor == "loss" else score > best)
+        improved = tm.best is None or (score < tm.best if monitor == "loss" else score > tm.best)
+        tm.epoch = epoch + 1
+        if improved:
+            tm.best, tm.bad_epochs = score, 0
+            tm.best_path = os.path.join(ckpt_dir, f"epoch={epoch}.ckpt")
+            if rank == 0:
+                torch.save(tm.state_dict(), tm.best_path)
+        else:
+            tm.bad_epochs += 1
         if rank == 0:
             torch.save(tm.state_dict(), last_path)
-        if improved:
-            best, bad_epochs = score, 0
-            best_path = os.path.join(ckpt_dir, f"epoch={epoch}.ckpt")
-            if rank == 0:
-                torch.save(tm.state_dict(), best_path)
-        else:
-            bad_epochs += 1
-            if args.early and bad_epochs >= args.early:
-                break
-    args.best_model_path = best_path
-    return best, tm
+        _barrier()  # no rank reads a checkpoint that rank 0 is still writing
+    args.best_model_path = tm.best_path
+    return tm.best, tm
+
+
+def _load_best(tm: "PMGTTrainerModel", args: AttrDict) -> None:
+    """Weights of the best checkpoint (base_trainer.py get_ckpt_path): loud when the path is set but the file is not there."""
+    if not args.best_model_path:
+        return
+    _barrier()
+    if not os.path.exists(args.best_model_path):
+        raise FileNotFoundError(f"best_model_path is set but missing: {args.best_model_path}")
+    tm.load_state_dict(torch.load(args.best_model_path, map_location=args.device, weights_only=False), weights_only=True)
 
 
 def test(args: AttrDict, trainer: Optional[PMGTTrainerModel] = None, is_hptuning: bool = False) -> Dict[str, float]:
     """base_trainer.py test(): AUC on the test split with the best checkpoint."""
     tm = trainer or PMGTTrainerModel(args)
-    if args.best_model_path and os.path.exists(args.best_model_path):
-        tm.load_state_dict(torch.load(args.best_model_path, map_location=args.device, weights_only=False))
+    _load_best(tm, args)
     res = tm.evaluate(args.test_dataset, args.test_batch_size)
     return {"test/auc": res["auc"]}
 
@@ -400,8 +466,7 @@ def inference(args: AttrDict) -> np.ndarray:
     """trainer.py:259-275 + base_trainer.py:382-409: (N, H) float32 embeddings, row i <-> node id i+2,
     node range sharded contiguously across ranks; rank 0 saves ``inference_result_path`` (.npy)."""
     tm = PMGTTrainerModel(args)
-    if args.best_model_path and os.path.exists(args.best_model_path):
-        tm.load_state_dict(torch.load(args.best_model_path, map_location=args.device, weights_only=False))
+    _load_best(tm, args)
     tm.net.eval()
     ds = PMGTDataset(args.graph, max_ctx_neigh=args.max_ctx_neigh, hop_sampling_sizes=args.hop_sampling_sizes,
                      is_training=False, is_inference=True, seed=args.seed)

@@ -119,3 +119,20 @@ def test_remap_node_embeddings_like_load_node_init_emb():
     assert np.allclose(out[0], emb[1] / np.linalg.norm(emb[1])) and np.allclose(out[2], emb[0] / np.linalg.norm(emb[0]))
     assert np.isclose(np.linalg.norm(out[1]), 1.0)               # missing item: random row, normalised
     assert out.dtype == np.float32
+
+
+def test_edge_list_duplicates_follow_networkx_semantics():
+    """nx.Graph keeps one edge per unordered pair: a repeated (u, v) updates the weight in place (first position in the
+    adjacency lists, last weight) -- ItemGraph.from_edge_list must build the same CSR."""
+    import networkx as nx
+    import numpy as np
+    from pmgt_b200.graph import ItemGraph
+    edges = [(2, 3, 0.5), (3, 4, 1.0), (3, 2, 0.9), (4, 5, 0.2), (2, 3, 0.1), (5, 2, 0.7), (4, 3, 0.3)]
+    g = nx.Graph()
+    g.add_nodes_from(range(2, 6))
+    g.add_weighted_edges_from(edges)
+    a = ItemGraph.from_networkx(g)
+    b = ItemGraph.from_edge_list(4, np.array([e[0] for e in edges]), np.array([e[1] for e in edges]),
+                                 np.array([e[2] for e in edges]))
+    assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+    assert np.allclose(a.weights, b.weights) and np.array_equal(a.cdf, b.cdf)

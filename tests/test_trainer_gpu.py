@@ -106,3 +106,65 @@ def test_prefetch_and_early_loss_readback(tmp_path):
     # -> the two runs are the same computation up to fp32 atomic ordering
     for a, b in zip(losses[False], losses[True]):
         assert abs(a - b) <= 1e-4 * abs(a), (losses[False], losses[True])
+
+
+def test_resume_restores_optimizer_state_and_epoch(tmp_path):
+    """Lightning's fit(ckpt_path=last.ckpt) semantics (base_trainer.py:324-332): weights, AdamW moments + step count,
+    epoch counter and early-stopping bookkeeping come back, and training continues at the next epoch."""
+    from pmgt_b200 import trainer
+    args = _args(tmp_path, run_id="resume_me", num_epochs=2)
+    trainer.check_args(args)
+    trainer.init_run(args)
+    trainer.init_dataloader(args)
+    trainer.init_model(args)
+    best, tm = trainer.train(args)
+    last = os.path.join(str(tmp_path), "resume_me", "checkpoints", "last.ckpt")
+    ckpt = torch.load(last, map_location="cpu", weights_only=False)
+    assert ckpt["epoch"] == 2 and ckpt["global_step"] == tm.global_step > 0
+    fl = tm.optimizer._flat
+    m_saved, v_saved = fl["m"].clone(), fl["v"].clone()
+    step_saved = tm.optimizer.state[fl["params"][0]]["step"]
+    assert step_saved == tm.global_step and float(m_saved.abs().max()) > 0
+
+    args2 = _args(tmp_path, run_id="resume_me", num_epochs=3)
+    trainer.init_run(args2)
+    trainer.init_dataloader(args2)
+    trainer.init_model(args2)
+    tm2 = trainer.PMGTTrainerModel(args2)
+    tm2.load_state_dict(torch.load(last, map_location=args2.device, weights_only=False))
+    assert tm2.epoch == 2 and tm2.global_step == tm.global_step and tm2.best == tm.best
+    fv = tm2.optimizer.flat_views()          # rebuilds the flat moment buffers from the loaded per-parameter state
+    assert fv is not None
+    fl2 = tm2.optimizer._flat
+    assert torch.equal(fl2["m"], m_saved) and torch.equal(fl2["v"], v_saved)
+    assert tm2.optimizer.state[fl2["params"][0]]["step"] == step_saved
+    # train() with the same run_id resumes: exactly ONE more epoch (epoch index 2) is run
+    best3, tm3 = trainer.train(args2)
+    assert [h["epoch"] for h in args2.history] == [2]
+    assert tm3.global_step > tm.global_step and tm3.epoch == 3
+
+
+def test_gradient_accumulation_and_rejected_flags(tmp_path):
+    """--accumulation-step (base_trainer.py:315): the optimizer steps every k micro-batches on the mean gradient;
+    --mp-enabled (fp16 autocast, base_trainer.py:312) is refused instead of being silently ignored."""
+    from pmgt_b200 import trainer
+    with pytest.raises(ValueError):
+        trainer.check_args(_args(tmp_path, mp_enabled=True))
+    args = _args(tmp_path, accumulation_step=2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    trainer.check_args(args)
+    trainer.init_run(args)
+    trainer.init_dataloader(args)
+    trainer.init_model(args)
+    tm = trainer.PMGTTrainerModel(args)
+    ds = args.train_dataset
+    flat = lambda: torch.cat([p.detach().reshape(-1) for p in tm.net.parameters() if p.requires_grad]).clone()
+    p0 = flat()
+    tm.train_on_indices(ds, np.arange(0, 64), 0)
+    assert tm.global_step == 0 and torch.equal(flat(), p0)          # first micro-batch: gradients only
+    g1 = tm.optimizer.flat_views()[1].clone()
+    tm.train_on_indices(ds, np.arange(64, 128), 0)
+    assert tm.global_step == 1 and not torch.equal(flat(), p0)      # second one: the step
+    g2 = tm.optimizer.flat_views()[1]
+    assert float((g2 - g1).abs().max()) > 0 and float(g2.norm()) > 0.5 * float(g1.norm())   # accumulated, not replaced
+    tm.train_on_indices(ds, np.arange(128, 192), 0)
+    assert tm.global_step == 1                                      # gradients were reset, a new cycle started
