@@ -182,6 +182,9 @@ class FlatParams:
         self.total = off
         self.flat = None
         self.flat_bf16 = None
+        # called as hook(arena) from the encoder backward once every gradient EXCEPT those of the embedding block is
+        # final (data-parallel training starts the allreduce of that part here, overlapping the embedding backward)
+        self.after_layers_hook = None
         self._views32 = {}
         self._views16 = {}
 
@@ -721,6 +724,8 @@ def _encode_backward(fp: FlatParams, pre: str, cfg: PMGTConfig, run: _EncoderRun
     if dy is None:  # zero layers
         dy = dy_f32.to(BF16)
         dy_b = None
+    if fp.after_layers_hook is not None:
+        ops.host_hook(fp.after_layers_hook, arena)
     # ---- embeddings
     E = pre + "embeddings."
     common = dict(dx=dy, dx_b=dy_b, d_w_att=G(E + "attention.1.weight"), d_b_att=G(E + "attention.1.bias"),

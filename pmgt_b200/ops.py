@@ -76,6 +76,15 @@ def zero_(t):
     _run("memset", fn, (), 0, t.numel() * t.element_size(), 0)
 
 
+def host_hook(fn, *args):
+    """A host-side callback at this point of the launch sequence (replayed with the tape): e.g. the trainer starts the
+    gradient allreduce of the encoder layers here, while the embedding backward is still to be enqueued."""
+    def call():
+        fn(*args)
+        return 0
+    _run("host_hook", call, (), 0, 0, 0)
+
+
 def tape_seed_blocks(tape):
     """The argument blocks of a tape that carry a dropout seed (patched before every replay)."""
     out = []

@@ -199,6 +199,9 @@ class PMGTTrainerModel:
         self._prefetched = None  # (dataset, indices, epoch, batch, masked, ready-event)
         self._loss_pin = None    # pinned host scalar the step's loss is copied into right after the forward pass
         self._loss_event = None
+        self._work = None        # in-flight allreduce of the encoder-layer gradients (started inside the backward pass)
+        self._work_buf = None
+        self.max_run_ahead = 1   # the host enqueues at most this many steps beyond the one whose forward pass is running
         self._micro = 0          # micro-batches accumulated since the last optimizer step
         self.epoch = 0           # next epoch to train (saved in checkpoints; Lightning's current_epoch)
         self.best, self.bad_epochs, self.best_path = None, 0, None
@@ -262,6 +265,11 @@ class PMGTTrainerModel:
         if not self.net.training:
             self.net.train()
         accum = max(1, int(args.accumulation_step or 1))
+        # Bound the host's run-ahead: wait until the PREVIOUS step's forward pass has finished (its loss event) before
+        # enqueueing this step.  An unthrottled loop queues several steps of side-stream sampling next to the main
+        # stream's kernels, which measurably slows both (round 1: the loop that read the loss every step was faster).
+        if self.max_run_ahead and self._loss_event is not None:
+            self._loss_event.synchronize()
         # fixed-shape steps: record the encoder's launch list once, then replay.  Launch plans write the gradients of
         # every pass into the same arena, so with gradient accumulation (which must ADD passes) they stay off.
         self.net.bert.use_launch_plans = accum == 1
@@ -281,18 +289,30 @@ class PMGTTrainerModel:
             self._loss_event = torch.cuda.Event()
         self._loss_pin.copy_(loss.detach(), non_blocking=True)
         self._loss_event.record()
+        rank, ws = world()
+        fp = self.net._flat()
+        fp.after_layers_hook = self._reduce_layers_early if (ws > 1 and self._micro + 1 >= accum) else None
+        self._work = None
         loss.backward()
         self._micro += 1
         if self._micro < accum:
             return loss.detach()
         self._micro = 0
-        rank, ws = world()
         scale = 1.0 / accum
         fv = self.optimizer.flat_views()
         if ws > 1:
             if fv is None or fv[1] is None:
                 raise RuntimeError("data-parallel training needs the flat gradient buffer")
-            dist.all_reduce(fv[1])  # ONE allreduce of the flat gradient (sum); mean folded into the step
+            if self._work is not None:
+                # the encoder-layer (+ NFR) part of the flat gradient has been in flight since the middle of the backward
+                # pass; only the embedding block -- whose backward ran meanwhile -- is reduced here
+                if fv[1].data_ptr() != self._work_buf.data_ptr():
+                    raise RuntimeError("the gradient that was reduced early is not the buffer the optimizer steps with")
+                self._work.wait()
+                dist.all_reduce(fv[1][: self._layers_lo(fp)])
+                self._work = None
+            else:
+                dist.all_reduce(fv[1])  # ONE allreduce of the flat gradient (sum); mean folded into the step
             scale = scale / ws
         scale_dev = None
         if args.gradient_max_norm:
@@ -314,6 +334,28 @@ class PMGTTrainerModel:
                             flat_grad=fv[1] if fv is not None else None)
         self.global_step += 1
         return loss.detach()
+
+    # -- data parallel: the flat gradient is reduced in two pieces, the big one overlapped with the embedding backward
+    @staticmethod
+    def _layers_lo(fp) -> int:
+        """Offset in the flat parameter order where the encoder layers start (everything before it is the embedding
+        block, whose gradients are produced LAST by the backward pass)."""
+        for n in fp.names:
+            if ".encoder.layer." in n or n.startswith("nfr_loss."):
+                return fp.offsets[n]
+        return fp.total
+
+    def _reduce_layers_early(self, arena) -> None:
+        """Called from inside the encoder backward (ops.host_hook) when all gradients except the embedding block's are
+        final.  Only for the persistent step arena, whose buffer is what the optimizer steps with (zero-copy)."""
+        if not getattr(arena, "persistent", False):
+            return
+        buf = arena.get()
+        lo = self._layers_lo(arena.fp)
+        if lo >= buf.numel():
+            return
+        self._work_buf = buf
+        self._work = dist.all_reduce(buf[lo:], async_op=True)
 
     def last_loss(self) -> float:
         """Host value of the most recent ``train_on_indices`` loss (device -> pinned-host copy issued right after the

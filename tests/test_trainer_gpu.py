@@ -133,6 +133,7 @@ def test_resume_restores_optimizer_state_and_epoch(tmp_path):
     tm2 = trainer.PMGTTrainerModel(args2)
     tm2.load_state_dict(torch.load(last, map_location=args2.device, weights_only=False))
     assert tm2.epoch == 2 and tm2.global_step == tm.global_step and tm2.best == tm.best
+    tm2.net.flat_parameters()                # parameters become views of the flat buffer (normally on the first forward)
     fv = tm2.optimizer.flat_views()          # rebuilds the flat moment buffers from the loaded per-parameter state
     assert fv is not None
     fl2 = tm2.optimizer._flat
