@@ -79,6 +79,15 @@ typedef struct pmgt_graph pmgt_graph;
 int pmgt_graph_create(pmgt_graph** out, int device, int64_t num_nodes, int64_t num_edges_directed,
                       const int64_t* indptr_host, const int32_t* indices_host,
                       const float* cdf_host);
+/*
+ * The same handle built ON the device from device-resident arrays: `indptr_dev` / `indices_dev` as above (rows already
+ * in adjacency insertion order) and the fp64 edge weights; the per-row softmax CDF (fp64 math, stored fp32, last entry 1)
+ * and the sampler's lookup structures are computed by kernels (replaces the networkx ingestion of
+ * pmgt/pmgt/trainer.py:34-41 for graphs whose host-side construction is the start-up bottleneck).  Synchronises `stream`.
+ */
+int pmgt_graph_create_device(pmgt_graph** out, int device, int64_t num_nodes, int64_t num_edges_directed,
+                             const int64_t* indptr_dev, const int32_t* indices_dev, const double* weights_dev,
+                             void* stream);
 int pmgt_graph_destroy(pmgt_graph* g);
 int64_t pmgt_graph_num_nodes(const pmgt_graph* g);
 int64_t pmgt_graph_num_edges(const pmgt_graph* g);

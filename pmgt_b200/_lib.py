@@ -172,6 +172,7 @@ SIGNATURES = {
     "pmgt_set_alternate_order": (C.c_int, [C.c_int]),
     "pmgt_last_error": (C.c_char_p, []),
     "pmgt_graph_create": (C.c_int, [C.POINTER(c_vp), C.c_int, C.c_int64, C.c_int64, c_i64p, c_i32p, c_f32p]),
+    "pmgt_graph_create_device": (C.c_int, [C.POINTER(c_vp), C.c_int, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp]),
     "pmgt_graph_destroy": (C.c_int, [c_vp]),
     "pmgt_graph_num_nodes": (C.c_int64, [c_vp]),
     "pmgt_graph_num_edges": (C.c_int64, [c_vp]),
@@ -262,6 +263,15 @@ def graph_create(device_index: int, num_nodes: int, indptr: np.ndarray, indices:
         C.byref(h), device_index, num_nodes, len(indices),
         indptr.ctypes.data_as(c_i64p), indices.ctypes.data_as(c_i32p), cdf.ctypes.data_as(c_f32p))
     check(rc, "pmgt_graph_create")
+    return h
+
+
+def graph_create_device(device_index: int, num_nodes: int, indptr_dev, indices_dev, weights_dev):
+    """``pmgt_graph_create_device``: torch CUDA tensors (int64 / int32 / float64) -> opaque handle."""
+    h = c_vp()
+    rc = lib().pmgt_graph_create_device(C.byref(h), device_index, num_nodes, indices_dev.numel(), ptr(indptr_dev),
+                                        ptr(indices_dev), ptr(weights_dev), cur_stream())
+    check(rc, "pmgt_graph_create_device")
     return h
 
 

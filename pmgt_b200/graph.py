@@ -41,6 +41,20 @@ def _row_softmax_cdf(indptr: np.ndarray, weights: np.ndarray) -> np.ndarray:
     return cdf
 
 
+def _device_array_as_tensor(ptr: int, n: int, dtype, device):
+    """A torch view of ``n`` elements of library-owned device memory (``__cuda_array_interface__``)."""
+    import torch
+
+    itemsize = torch.empty((), dtype=dtype).element_size()
+    typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8"}[dtype]
+
+    class _Wrap:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2,
+                                    "strides": (itemsize,)}
+
+    return torch.as_tensor(_Wrap(), device=device)
+
+
 class ItemGraph:
     """CSR item graph + per-row softmax CDF; optionally resident on a GPU."""
 
@@ -134,6 +148,47 @@ class ItemGraph:
         indptr = np.zeros(num_nodes + 3, dtype=np.int64)
         np.cumsum(counts, out=indptr[1:])
         return cls(num_nodes, indptr, cols.astype(np.int32), wts)
+
+    @classmethod
+    def from_edge_list_device(cls, num_nodes: int, src, dst, weight, device=None) -> "ItemGraph":
+        """``from_edge_list`` on the GPU: the doubled edge list is sorted by (row, insertion sequence) with one stable
+        device sort, and the softmax CDF plus the sampler's lookup tables are built by kernels
+        (``pmgt_graph_create_device``).  Same CSR, same neighbour order; the CDF agrees with the host builder to fp32
+        rounding (the host copy kept in ``self.cdf`` is the device result, so CPU replays see the same values).
+        Edge lists with self loops or repeated pairs take the host path (networkx de-duplication semantics)."""
+        import torch
+
+        from . import _lib
+
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        src = torch.as_tensor(src, dtype=torch.int64, device=dev)
+        dst = torch.as_tensor(dst, dtype=torch.int64, device=dev)
+        w = torch.as_tensor(weight, dtype=torch.float64, device=dev)
+        m = src.numel()
+        code = torch.minimum(src, dst) << 32 | torch.maximum(src, dst)
+        if bool((src == dst).any()) or torch.unique(code).numel() != m:
+            return cls.from_edge_list(num_nodes, src.cpu().numpy(), dst.cpu().numpy(), w.cpu().numpy())
+        del code
+        rows = torch.cat([src, dst])
+        # key = (row, 2 * edge + side): edge i appends dst to src's row and then src to dst's row
+        seq = torch.cat([2 * torch.arange(m, device=dev), 2 * torch.arange(m, device=dev) + 1])
+        key = rows * (2 * m) + seq
+        del seq
+        perm = torch.argsort(key)
+        del key
+        cols = torch.cat([dst, src])[perm].to(torch.int32)
+        wts = torch.cat([w, w])[perm]
+        counts = torch.bincount(rows, minlength=num_nodes + 2)
+        del rows, perm
+        indptr = torch.zeros(num_nodes + 3, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=indptr[1:])
+        h = _lib.graph_create_device(dev.index, num_nodes, indptr, cols, wts)
+        cdf = torch.empty(cols.numel(), dtype=torch.float32, device=dev)
+        if cols.numel():
+            cdf = _device_array_as_tensor(_lib.lib().pmgt_graph_cdf(h), cols.numel(), torch.float32, dev).clone()
+        g = cls(num_nodes, indptr.cpu().numpy(), cols.cpu().numpy(), wts.cpu().numpy(), cdf=cdf.cpu().numpy())
+        g._handles[dev.index] = h
+        return g
 
     # -- device residency ---------------------------------------------------------
     def device_handle(self, device_index: int):

@@ -27,26 +27,89 @@ from .modeling_pmgt import (BF16, FlatParams, GradArena, PMGTForPreTrainingOutpu
 from .utils import get_input_feat_embeds  # noqa: F401  (re-exported like the reference module)
 
 
-class _TakeRows(torch.autograd.Function):
-    """rows = hidden_flat[idx]; backward scatters into one zero buffer (idx unique)."""
+class _PretrainLossFn(torch.autograd.Function):
+    """GSR + NFR losses of one batch straight from the encoder's compact hidden-state matrix, and their gradient
+    written straight into the buffer the encoder's backward pass reads.
+
+    ``hidden`` is ``[B*L + SP (+ B*L), H]`` fp32: every position of the targets, position 0 of the pairs, (training)
+    every position of the masked targets.  The GSR kernel reads the target / pair rows through strides (no gather),
+    NFR gathers its ~0.16 * B * (L - 1) masked rows; backward zeroes the gradient buffer once, the GSR kernel writes
+    its rows through the same strides and the NFR rows are copied in.  This replaces an index_select of ~48k rows,
+    three slice-backward zero-fills / adds and an index_copy per step with two small gathers (models.py:104-162)."""
 
     @staticmethod
-    def forward(ctx, hidden_flat, idx, grad_buf=None):
-        ctx.save_for_backward(idx)
-        ctx.shape = hidden_flat.shape
-        ctx.grad_buf = grad_buf  # launch plans: build the gradient in the buffer the recorded backward pass reads
-        return hidden_flat.index_select(0, idx)
+    def forward(ctx, host, hidden, B, SP, L, pair_off, labels, nfr_rows, target_idx, tables, arena, grad_buf, *params):
+        from . import ops
+        H = hidden.shape[1]
+        dev = hidden.device
+        hidden = hidden if hidden.is_contiguous() else hidden.contiguous()
+        tgt = hidden[: B * L].view(B, L, H)[:, 0]            # stride L * H
+        pair = hidden[B * L: B * L + SP]
+        logits = torch.empty(SP, dtype=torch.float32, device=dev)
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        ops.gsr(True, B, SP, H, tgt, tgt.stride(0), pair, pair.stride(0), pair_off, labels, logits=logits, loss_out=loss)
+        saved = [hidden, pair_off, labels]
+        ctx.n_mod = 0
+        if nfr_rows is not None:
+            nfr = host.nfr_loss
+            fp, pre = nfr._fp, nfr._fp_prefix
+            Mm = int(nfr_rows.numel())
+            hb = hidden.index_select(0, nfr_rows).to(BF16) if Mm > 0 else torch.empty(0, H, dtype=BF16, device=dev)
+            projs = []
+            for m, table in enumerate(tables):
+                D = table.shape[1]
+                proj = torch.empty(Mm, D, dtype=BF16, device=dev)
+                if Mm > 0:
+                    ops.linear_fwd(hb, fp.bf16(f"{pre}projections.{m}.weight"), fp.f32(f"{pre}projections.{m}.bias"), proj)
+                ops.nfr_mse(True, Mm, D, proj, table, target_idx, 1.0 / len(tables), loss_out=loss)   # adds into `loss`
+                projs.append(proj)
+            saved += [nfr_rows, target_idx, hb, *projs]
+            ctx.n_mod = len(tables)
+        ctx.save_for_backward(*saved)
+        ctx.host, ctx.arena, ctx.tables, ctx.grad_buf, ctx.dims = host, arena, tables, grad_buf, (B, SP, L, H)
+        ctx.n_params = len(params)
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
 
     @staticmethod
-    def backward(ctx, g):
-        (idx,) = ctx.saved_tensors
+    def backward(ctx, g_loss, _g_logits):
+        from . import ops
+        host, arena, tables = ctx.host, ctx.arena, ctx.tables
+        B, SP, L, H = ctx.dims
+        hidden, pair_off, labels, *rest = ctx.saved_tensors
         out = ctx.grad_buf
-        if out is not None and out.shape == ctx.shape and out.dtype == g.dtype:
+        if out is not None and out.shape == hidden.shape and out.dtype == torch.float32:
             out.zero_()
         else:
-            out = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
-        out.index_copy_(0, idx, g)
-        return out, None, None
+            out = torch.zeros_like(hidden)
+        g = g_loss.to(torch.float32).contiguous()
+        tgt = hidden[: B * L].view(B, L, H)[:, 0]
+        pair = hidden[B * L: B * L + SP]
+        d_t = out[: B * L].view(B, L, H)[:, 0]
+        d_p = out[B * L: B * L + SP]
+        ops.gsr(False, B, SP, H, tgt, tgt.stride(0), pair, pair.stride(0), pair_off, labels, grad_out=g, d_tgt=d_t, d_pair=d_p)
+        grads = (None,) * ctx.n_params
+        if ctx.n_mod:
+            nfr = host.nfr_loss
+            fp, pre = nfr._fp, nfr._fp_prefix
+            nfr_rows, target_idx, hb, *projs = rest
+            Mm = hb.shape[0]
+            dh = None
+            for m, table in enumerate(tables):
+                if Mm == 0:
+                    continue
+                D = table.shape[1]
+                dproj = torch.empty(Mm, D, dtype=BF16, device=hb.device)
+                ops.nfr_mse(False, Mm, D, projs[m], table, target_idx, 1.0 / len(tables), grad_out=g, dproj=dproj)
+                ops.colsum(dproj, arena.view(f"{pre}projections.{m}.bias"))
+                ops.linear_dw(dproj, hb, arena.view(f"{pre}projections.{m}.weight"))
+                o = torch.empty(Mm, H, dtype=BF16, device=hb.device)
+                ops.linear_dx(dproj, fp.bf16(f"{pre}projections.{m}.weight"), o, addend=dh)
+                dh = o
+            if dh is not None:
+                out.index_copy_(0, nfr_rows, dh.float())     # masked rows: disjoint from the rows GSR wrote
+            grads = tuple(arena.view(n) for n in nfr._param_names)
+        return (None, out) + (None,) * 10 + grads
 
 
 class PMGT(PMGTPretrainedModel):
@@ -245,21 +308,18 @@ class PMGT(PMGTPretrainedModel):
         loss = None
         prediction_logits = None
         if pair_node_inputs is not None:
-            # compact row numbers of what the losses read: position 0 of targets and pairs, masked positions
-            tok = [torch.arange(0, B * L, L, device=dev), B * L + torch.arange(SP, device=dev)]
-            if nfr_on:
-                tok.append(B * L + SP + m_pos[:, 0] * L + m_pos[:, 1] + 1)
             plan = self.bert._active_plan
-            rows = _TakeRows.apply(hidden, torch.cat(tok),
-                                   plan.grad_buffer() if plan is not None and hidden.requires_grad else None)
             pair_off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
             torch.cumsum(num_pairs.to(dev), 0, out=pair_off[1:])
-            gsr_loss, prediction_logits = self.gsr_loss.batched(rows[:B], rows[B: B + SP], pair_off,
-                                                                labels.to(torch.float32).contiguous())
-            loss = gsr_loss
-            if nfr_on:
-                nfr = self.nfr_loss.from_ids(rows[B + SP:], target_idx.contiguous(), tables, arena=arena)
-                loss = gsr_loss + nfr
+            nfr_rows = None
+            target_ids = None
+            if nfr_on:  # compact row numbers of the masked positions (inside the masked-target block)
+                nfr_rows = B * L + SP + m_pos[:, 0] * L + m_pos[:, 1] + 1
+                target_ids = target_idx.contiguous()
+            nfr_params = [p for _, p in self.nfr_loss.param_order()] if nfr_on else []
+            loss, prediction_logits = _PretrainLossFn.apply(
+                self, hidden, B, SP, L, pair_off, labels.to(torch.float32).contiguous(), nfr_rows, target_ids, tables, arena,
+                plan.grad_buffer() if plan is not None and hidden.requires_grad else None, *nfr_params)
 
         if not return_dict:
             return (loss, prediction_logits, last_hidden_state, None)
