@@ -161,6 +161,8 @@ class ItemGraph:
         from . import _lib
 
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         src = torch.as_tensor(src, dtype=torch.int64, device=dev)
         dst = torch.as_tensor(dst, dtype=torch.int64, device=dev)
         w = torch.as_tensor(weight, dtype=torch.float64, device=dev)

@@ -121,7 +121,9 @@ def _load_graph_and_features(args: AttrDict):
         from . import synthetic
 
         name = args.synthetic
-        graph = synthetic.make_item_graph(name)
+        big = isinstance(name, str) and name in synthetic.SHAPES and synthetic.SHAPES[name][0] > 200_000
+        # large graphs are ingested on the device (edge list -> CSR + CDF + lookup tables by kernels)
+        graph = synthetic.make_item_graph(name, device=args.device if (big and args.device is not None) else None)
         seed = synthetic.SHAPES[name][3] if isinstance(name, str) and name in synthetic.SHAPES else 1234
         if graph.num_nodes > 200_000:
             feats = synthetic.make_features_device(graph.num_nodes, seed=seed, device=args.device)

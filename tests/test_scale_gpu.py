@@ -205,7 +205,7 @@ def _dp_worker(rank, ws, port, q):
             assert cos > 0.9995, (n, cos)
             assert abs(float(got.norm()) / wn - 1) < 1e-2, (n, float(got.norm()) / wn)
             off_ok += 1
-        assert off_ok > 50 and len(names) > 50
+        assert off_ok >= 40 and len(names) >= 40, (off_ok, len(names))
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
