@@ -84,13 +84,26 @@ def load_peaks():
 # reference arms: the oracle port on the host cores / eagerly on the GPU, each in a subprocess
 # ---------------------------------------------------------------------------
 def run_cpu_port(workload, steps, warmup, budget_s):
-    cmd = [sys.executable, "-m", "oracle.cpu_baseline", "--workload", workload, "--steps", str(steps), "--warmup",
-           str(warmup), "--budget-s", str(budget_s)]
+    """The reference's CPU path on the host cores, in a CUDA-free subprocess: the UNMODIFIED reference modules when they
+    are available (/root/reference, or the copies oracle/build.py staged under oracle/_ref/ -- kind "reference"), else
+    the oracle port (kind "port")."""
+    from oracle import ref_shim
+    use_ref = ref_shim.available() or ref_shim.staged_available()
+    mod = "oracle.ref_baseline" if use_ref else "oracle.cpu_baseline"
+    cmd = [sys.executable, "-m", mod, "--workload", workload, "--steps", str(steps), "--warmup", str(warmup),
+           "--budget-s", str(budget_s)]
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    if r.returncode != 0 and use_ref:  # never lose the line over the staged copy: fall back to the port, and say so
+        cmd[2] = "oracle.cpu_baseline"
+        r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     if r.returncode != 0:
         raise RuntimeError("cpu baseline failed: " + r.stderr[-2000:])
-    return json.loads(r.stdout.strip().splitlines()[-1])
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    d.setdefault("kind", "port")
+    return d
 
 
 def run_gpu_eager(workload, batch, steps, warmup, device_index=0):
@@ -112,14 +125,16 @@ def reference_arm(a):
         return
     wl = "TG" if a.workload == "1M" else a.workload  # the fp32 host tables of the 1M graph (9.2 GB) are not built for a CPU run
     d = run_cpu_port(wl, a.steps, a.warmup, budget_s=150.0)
+    how = ("the reference's own PMGTDataset in DataLoader worker processes + PMGT.forward (per-target loop) + "
+           "DenseSparseAdamW" if d["kind"] == "reference" else "oracle port: sampler in a process pool, batched pair encode")
     sample = (f"{d['targets_per_step']} targets ({int(d['contexts'] / d['steps'])} contexts) per step x {d['steps']} steps on "
-              f"the {wl} graph; sampler = process pool over {d['cores']} cores, model fp32 torch with {d['cores']} threads")
+              f"the {wl} graph; {how}; {d['cores']} cores")
     line = {
         "impl": "reference", "metric": "pmgt_pretrain_node_contexts_per_s", "value": d["value"], "unit": "contexts/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": d["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(wl, d["targets_per_step"], "cpu"),
-        "cpu_baseline": {"value": d["value"], "unit": "contexts/s", "cores": d["cores"], "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": d["value"], "unit": "contexts/s", "cores": d["cores"], "kind": d["kind"], "sample": sample,
                          "sampler_contexts_per_s": d["sampler_contexts_per_s"], "model_contexts_per_s": d["model_contexts_per_s"]},
         "e2e": {"value": d["value"], "unit": "contexts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -409,11 +424,12 @@ def ours(a):
     if rank == 0 and ws == 1 and not a.no_cpu_baseline:
         wl = "TG" if a.workload == "1M" else a.workload
         d = run_cpu_port(wl, steps=2, warmup=0, budget_s=20.0)
-        cpu = {"value": d["value"], "unit": "contexts/s", "cores": d["cores"], "kind": "port",
+        cpu = {"value": d["value"], "unit": "contexts/s", "cores": d["cores"], "kind": d["kind"],
                "sample": f"{d['targets_per_step']} targets x {d['steps']} steps of the {wl} workload (same encoder / hops / "
                          f"pairs; the graph only changes which rows are touched) "
-                         f"(sampler pool {d['cores']} procs: {d['sampler_contexts_per_s']:.0f} ctx/s; fp32 torch model "
-                         f"{d['cores']} threads: {d['model_contexts_per_s']:.0f} ctx/s)"}
+                         f"(sampler in {d['cores']} worker processes: {d['sampler_contexts_per_s']:.0f} ctx/s; fp32 torch model "
+                         f"{d['cores']} threads: {d['model_contexts_per_s']:.0f} ctx/s; "
+                         + ("unmodified reference modules" if d["kind"] == "reference" else "oracle port") + ")"}
     if rank == 0 and ws == 1 and not a.no_gpu_baseline:
         try:
             g = run_gpu_eager("TG" if a.workload == "1M" else a.workload, 256, steps=2, warmup=1, device_index=local_rank)

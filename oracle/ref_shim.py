@@ -13,21 +13,37 @@ import os
 import sys
 
 REFERENCE_ROOT = os.environ.get("PMGT_REFERENCE_ROOT", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build.py::build_ref()
 
 
 def available() -> bool:
+    """The reference tree itself (build container only): what the parity tests and the golden generator need."""
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "pmgt", "pmgt"))
+
+
+def staged_available() -> bool:
+    """The unmodified hot-path modules staged under oracle/_ref/ (travels to the GPU box; bench CPU arm only)."""
+    return os.path.isdir(os.path.join(STAGED_ROOT, "pmgt", "pmgt"))
+
+
+def load_any():
+    """The reference from /root/reference when present, else from the staged copy."""
+    global REFERENCE_ROOT
+    if not available() and staged_available():
+        REFERENCE_ROOT = STAGED_ROOT
+        return load(_root_ok=True)
+    return load()
 
 
 _loaded = None
 
 
-def load():
+def load(_root_ok: bool = False):
     """Return a namespace with the reference's hot-path symbols."""
     global _loaded
     if _loaded is not None:
         return _loaded
-    if not available():
+    if not _root_ok and not available():
         raise RuntimeError(f"reference tree not present at {REFERENCE_ROOT}")
     sys.dont_write_bytecode = True  # the reference tree is read-only
     if REFERENCE_ROOT not in sys.path:

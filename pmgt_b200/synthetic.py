@@ -64,10 +64,9 @@ def chung_lu_edges(num_nodes: int, num_edges: int, seed: int, exponent: float = 
     return u, v
 
 
-def make_item_graph(name_or_shape, seed=None, device=None) -> ItemGraph:
-    """``"VG"`` / ``"TG"`` / ``"1M"`` or an explicit ``(num_nodes, num_edges)``.  With ``device`` (a CUDA device) the CSR,
-    the softmax CDF and the sampler's lookup tables are built on the GPU (``ItemGraph.from_edge_list_device``: 0.7 s
-    instead of 12 s at 1M nodes / 20M edges); the CDF then agrees with the host build to fp32 rounding."""
+def make_edge_list(name_or_shape, seed=None):
+    """``(num_nodes, src, dst, weight)`` of a synthetic item graph: node ids ``2..N+1``, unique undirected edges in
+    insertion order, fp32-rounded weights per notebook cell 20 (``(ln r + 1) / (ln sqrt(deg_u deg_v) + 1)``, r >= 3)."""
     if isinstance(name_or_shape, str):
         n, m, gseed, _ = SHAPES[name_or_shape]
     else:
@@ -80,9 +79,17 @@ def make_item_graph(name_or_shape, seed=None, device=None) -> ItemGraph:
     deg = (np.bincount(u, minlength=n) + np.bincount(v, minlength=n)).astype(np.float64)
     r = 2.0 + rng.geometric(0.5, size=m)  # co-review counts, >= 3
     weight = (np.log(r) + 1.0) / (np.log(np.sqrt(deg[u] * deg[v])) + 1.0)
+    return n, u + 2, v + 2, weight.astype(np.float32)
+
+
+def make_item_graph(name_or_shape, seed=None, device=None) -> ItemGraph:
+    """``"VG"`` / ``"TG"`` / ``"1M"`` or an explicit ``(num_nodes, num_edges)``.  With ``device`` (a CUDA device) the CSR,
+    the softmax CDF and the sampler's lookup tables are built on the GPU (``ItemGraph.from_edge_list_device``: 0.7 s
+    instead of 12 s at 1M nodes / 20M edges); the CDF then agrees with the host build to fp32 rounding."""
+    n, src, dst, weight = make_edge_list(name_or_shape, seed)
     if device is not None:
-        return ItemGraph.from_edge_list_device(n, u + 2, v + 2, weight.astype(np.float32).astype(np.float64), device=device)
-    return ItemGraph.from_edge_list(n, u + 2, v + 2, weight.astype(np.float32))
+        return ItemGraph.from_edge_list_device(n, src, dst, weight.astype(np.float64), device=device)
+    return ItemGraph.from_edge_list(n, src, dst, weight)
 
 
 def make_features(num_nodes: int, dims=(1536, 768), seed: int = 1234):

@@ -10,7 +10,7 @@ from pmgt_b200.datasets import context_keys, sample_contexts
 wl = sys.argv[1] if len(sys.argv) > 1 else "TG"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 45056
 t0 = time.time()
-g = synthetic.make_item_graph(wl)
+g = synthetic.make_item_graph(wl, device="cuda" if wl == "1M" else None)
 t_graph = time.time() - t0
 dev = torch.device("cuda", 0)
 t0 = time.time()
