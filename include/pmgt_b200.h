@@ -39,7 +39,7 @@ typedef enum pmgt_status {
 } pmgt_status;
 
 /* ABI version of this header; bumped on any signature change. */
-#define PMGT_B200_ABI_VERSION 8
+#define PMGT_B200_ABI_VERSION 9
 int pmgt_abi_version(void);
 const char* pmgt_last_error(void);
 
@@ -352,35 +352,46 @@ int pmgt_dw_tile(const pmgt_dw_tile_args* a, void* stream);
 int pmgt_dw_tile_batch(const pmgt_dw_tile_args* a, int n, void* stream);
 
 /*
- * Fused feed-forward block of one encoder layer, H = I = 128 (BertIntermediate + BertOutput as composed by
- * PMGTLayer.feed_forward_chunk, pmgt/pmgt/modeling_pmgt.py:296-325):
- *   pmgt_ffn_fwd   out = LayerNorm(dropout(gelu(a w1^T + b1) w2^T + b2) + a)      (optional fp32 copy out_f32)
- *   pmgt_ffn_bwd   da = d(loss)/d(a) (feed-forward branch + residual branch) from dy (+ dy_b) = d(loss)/d(out);
- *                  dw1, dw2, db1, db2, d_ln_g, d_ln_b are ACCUMULATED (fp32).  The forward call saves h = gelu(h_pre)
- *                  and gelu'(h_pre) (bf16, `h` / `gp`, optional: pass both or neither); the backward call reads them
- *                  back and recomputes the pre-LayerNorm sum from h with the forward kernel's arithmetic (same
- *                  dropout stream), so neither h_pre nor the pre-LayerNorm sum is ever stored.
- * One persistent tcgen05 kernel each; everything else stays in shared / tensor memory.
+ * Fused post-attention blocks of one encoder layer, H = I = 128 (one persistent tcgen05 kernel per call):
+ *   ffn = 0  BertSelfOutput as composed by PMGTAttention (pmgt/pmgt/modeling_pmgt.py:358-375):
+ *              out = LayerNorm(dropout(in w2^T + b2) + res)
+ *   ffn = 1  BertIntermediate + BertOutput as composed by PMGTLayer.feed_forward_chunk (modeling_pmgt.py:296-325):
+ *              out = LayerNorm(dropout(gelu(in w1^T + b1) w2^T + b2) + in)
+ * pmgt_block_fwd  writes out (optional fp32 copy out_f32) and, when xhat != NULL, what pmgt_block_bwd reads back:
+ *                 xhat (normalised pre-affine LayerNorm value, bf16), rstd (fp32 per row) and -- ffn -- h = gelu(h_pre)
+ *                 and gp = gelu'(h_pre).  The dropout mask is regenerated from (seed, site) in the backward call.
+ * pmgt_block_bwd  dy (+ dy_b) = d(loss)/d(out).  dx = d(loss)/d(in): for ffn = 1 it includes the residual branch
+ *                 (in IS the residual); for ffn = 0 the residual-branch gradient is written to dz instead.
+ *                 dw1, dw2, db1, db2, d_ln_g, d_ln_b are ACCUMULATED (fp32).
+ * All [T][128] bf16 matrices: 32-byte aligned, pitch a multiple of 16 elements.
  */
-typedef struct pmgt_ffn_args {
+typedef struct pmgt_block_args {
   int64_t T;
-  const uint16_t* a; int64_t ld_a;          /* [T][128] bf16 */
-  const uint16_t* w1; const uint16_t* w2;   /* [128][128] bf16, contiguous: intermediate.dense.weight, output.dense.weight */
-  const float* b1; const float* b2;         /* [128] fp32 */
+  int ffn;
+  const uint16_t* in; int64_t ld_in;        /* [T][128] bf16 */
+  const uint16_t* res; int64_t ld_res;      /* ffn = 0: residual rows [T][128] bf16 (ffn = 1: ignored, the residual is `in`) */
+  const uint16_t* w1; const float* b1;      /* ffn = 1: intermediate.dense  [128][128] bf16 contiguous, [128] fp32 */
+  const uint16_t* w2; const float* b2;      /* the dense layer in front of the LayerNorm */
   const float* ln_g; const float* ln_b; float ln_eps;
   float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
   uint16_t* out; int64_t ld_out;            /* fwd: [T][128] bf16 */
-  float* out_f32;                           /* fwd, optional: [T][128] fp32 */
-  uint16_t* h; uint16_t* gp; int64_t ld_h;  /* [T][128] bf16 each (same pitch): written by fwd (optional), read by bwd */
+  float* out_f32;                           /* fwd, optional: [T][128] fp32 contiguous */
+  uint16_t* h; uint16_t* gp; uint16_t* xhat; int64_t ld_save;   /* saved activations, [T][128] bf16 each, same pitch */
+  float* rstd;                              /* [T] fp32 */
   const uint16_t* dy; int64_t ld_dy;        /* bwd: [T][128] bf16 */
   const uint16_t* dy_b; int64_t ld_dy_b;    /* bwd, optional second term of the incoming gradient */
-  uint16_t* da; int64_t ld_da;              /* bwd: [T][128] bf16 */
+  uint16_t* dx; int64_t ld_dx;              /* bwd: [T][128] bf16 */
+  uint16_t* dz; int64_t ld_dz;              /* bwd, ffn = 0: [T][128] bf16 gradient of the residual branch */
   float* dw1; float* dw2;                   /* bwd: [128][128] fp32 */
   float* db1; float* db2; float* d_ln_g; float* d_ln_b;   /* bwd: [128] fp32, each may be NULL */
-} pmgt_ffn_args;
+} pmgt_block_args;
 
-int pmgt_ffn_fwd(const pmgt_ffn_args* a, void* stream);
-int pmgt_ffn_bwd(const pmgt_ffn_args* a, void* stream);
+int pmgt_block_fwd(const pmgt_block_args* a, void* stream);
+int pmgt_block_bwd(const pmgt_block_args* a, void* stream);
+/* Diagnostics: `buf` = device buffer of 8 * 32 * 4 uint64 (or NULL to stop).  While set, CTA 0 of every block kernel
+ * stamps clock64() at its stage boundaries ([role][tile][event]; roles: 0 MMA issuer, then the epilogue groups) --
+ * tools/blk_timeline.py prints the per-stage durations. */
+int pmgt_block_set_trace(void* buf);
 
 /*
  * LayerNorm backward from the saved pre-LayerNorm input z (PMGT_LT_RES_LN's aux_out): dy = dy_a + dy_b +

@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmgt_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _lib = None
 
@@ -113,20 +113,22 @@ class DwTileArgs(C.Structure):
     ]
 
 
-class FfnArgs(C.Structure):
+class BlockArgs(C.Structure):
     _fields_ = [
-        ("T", C.c_int64),
-        ("a", c_vp), ("ld_a", C.c_int64),
-        ("w1", c_vp), ("w2", c_vp),
-        ("b1", c_vp), ("b2", c_vp),
+        ("T", C.c_int64), ("ffn", C.c_int),
+        ("in_", c_vp), ("ld_in", C.c_int64),
+        ("res", c_vp), ("ld_res", C.c_int64),
+        ("w1", c_vp), ("b1", c_vp), ("w2", c_vp), ("b2", c_vp),
         ("ln_g", c_vp), ("ln_b", c_vp), ("ln_eps", C.c_float),
         ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("dropout_site", C.c_uint32),
         ("out", c_vp), ("ld_out", C.c_int64),
         ("out_f32", c_vp),
-        ("h", c_vp), ("gp", c_vp), ("ld_h", C.c_int64),
+        ("h", c_vp), ("gp", c_vp), ("xhat", c_vp), ("ld_save", C.c_int64),
+        ("rstd", c_vp),
         ("dy", c_vp), ("ld_dy", C.c_int64),
         ("dy_b", c_vp), ("ld_dy_b", C.c_int64),
-        ("da", c_vp), ("ld_da", C.c_int64),
+        ("dx", c_vp), ("ld_dx", C.c_int64),
+        ("dz", c_vp), ("ld_dz", C.c_int64),
         ("dw1", c_vp), ("dw2", c_vp),
         ("db1", c_vp), ("db2", c_vp), ("d_ln_g", c_vp), ("d_ln_b", c_vp),
     ]
@@ -195,8 +197,9 @@ SIGNATURES = {
     "pmgt_dw_tile_supported": (C.c_int, [C.c_int64, C.c_int64]),
     "pmgt_dw_tile": (C.c_int, [C.POINTER(DwTileArgs), c_vp]),
     "pmgt_dw_tile_batch": (C.c_int, [C.POINTER(DwTileArgs), C.c_int, c_vp]),
-    "pmgt_ffn_fwd": (C.c_int, [C.POINTER(FfnArgs), c_vp]),
-    "pmgt_ffn_bwd": (C.c_int, [C.POINTER(FfnArgs), c_vp]),
+    "pmgt_block_fwd": (C.c_int, [C.POINTER(BlockArgs), c_vp]),
+    "pmgt_block_bwd": (C.c_int, [C.POINTER(BlockArgs), c_vp]),
+    "pmgt_block_set_trace": (C.c_int, [c_vp]),
     "pmgt_ln_bwd": (C.c_int, [C.POINTER(LnBwdArgs), c_vp]),
     "pmgt_colsum_bf16": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp]),
     "pmgt_gsr_fwd": (C.c_int, [C.POINTER(GsrArgs), c_vp]),

@@ -41,6 +41,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();  // a lost arrival becomes an error, not a hang
   }
 }
+// Wait of a single-thread role (TMA producer, MMA issuer, store warp): these threads spin for most of the kernel, and
+// every spin iteration takes an issue slot from the epilogue warps of the same scheduler -- the try_wait carries a
+// suspend-time hint and failed polls back off with nanosleep.
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(2000u)
+        : "memory");
+    if (done) break;
+    __nanosleep(40);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AttnArgs, DwTileArgs, EmbedArgs, FfnArgs, GemmArgs, GsrArgs, LinearTileArgs, LnBwdArgs, NfrArgs, ResLnArgs, check,
+from ._lib import (AttnArgs, DwTileArgs, EmbedArgs, BlockArgs, GemmArgs, GsrArgs, LinearTileArgs, LnBwdArgs, NfrArgs, ResLnArgs, check,
                    cur_stream, ptr)
 
 EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_ADDEND, EPI_OUT_F32, EPI_ATOMIC = 1, 2, 4, 8, 16, 32
@@ -220,43 +220,73 @@ def linear_tile(x, w, out, epi, *, w_mn=False, bias=None, aux_out=None, e_in=Non
     _run(tag or "linear_tile", _lib.lib().pmgt_linear_tile, (C.byref(a), cur_stream()), 1, nbytes, flops)
 
 
-def ffn_args(a, w1, b1, w2, b2, ln_g, ln_b, eps, p, seed, site):
-    """Argument block shared by ``ffn_fwd`` / ``ffn_bwd`` (fused feed-forward block, H = I = 128)."""
-    _require_cuda(a, "a")
-    f = FfnArgs()
-    f.T = a.shape[0]
-    f.a, f.ld_a = ptr(a), a.stride(0)
-    f.w1, f.w2, f.b1, f.b2 = ptr(w1), ptr(w2), ptr(b1), ptr(b2)
+class BlockSaved:
+    """What ``block_fwd`` leaves for ``block_bwd``: xhat (normalised pre-affine LayerNorm value), rstd and
+    -- FFN block -- h = gelu(h_pre) and gp = gelu'(h_pre)."""
+    __slots__ = ("xhat", "rstd", "h", "gp")
+
+    def __init__(self, T, ffn, p, device, new=None):
+        mk = new if new is not None else (lambda *shape, dtype=torch.bfloat16: torch.empty(shape, dtype=dtype, device=device))
+        self.xhat = mk(T, 128)
+        self.rstd = mk(T, dtype=torch.float32)
+        self.h = mk(T, 128) if ffn else None
+        self.gp = mk(T, 128) if ffn else None
+
+    def tensors(self):
+        return tuple(t for t in (self.xhat, self.rstd, self.h, self.gp) if t is not None)
+
+
+def block_args(x, w2, b2, ln_g, ln_b, eps, p, seed, site, w1=None, b1=None, res=None):
+    """Argument block shared by ``block_fwd`` / ``block_bwd``.  ``w1`` given: the feed-forward block
+    ``LayerNorm(dropout(gelu(x w1^T + b1) w2^T + b2) + x)``; otherwise the dense block
+    ``LayerNorm(dropout(x w2^T + b2) + res)`` (H = I = 128)."""
+    _require_cuda(x, "x")
+    f = BlockArgs()
+    f.T = x.shape[0]
+    f.ffn = 1 if w1 is not None else 0
+    f.in_, f.ld_in = ptr(x), x.stride(0)
+    f.res, f.ld_res = ptr(res), (res.stride(0) if res is not None else 0)
+    f.w1, f.b1, f.w2, f.b2 = ptr(w1), ptr(b1), ptr(w2), ptr(b2)
     f.ln_g, f.ln_b, f.ln_eps = ptr(ln_g), ptr(ln_b), eps
     f.dropout_p, f.dropout_seed, f.dropout_site = p, seed, site
     return f
 
 
-def ffn_supported(H, I) -> bool:
+def block_supported(H, I) -> bool:
     return H == 128 and I == 128
 
 
-def ffn_fwd(f: FfnArgs, out, out_f32=None, h=None, gp=None):
-    """out = LayerNorm(dropout(gelu(a w1^T + b1) w2^T + b2) + a): one persistent tcgen05 kernel; ``h`` / ``gp``
-    (gelu output and gelu'(h_pre), both or neither) are saved for ``ffn_bwd``."""
+def _block_saved(f: BlockArgs, sv):
+    f.xhat, f.rstd = ptr(sv.xhat), ptr(sv.rstd)
+    f.h, f.gp, f.ld_save = ptr(sv.h), ptr(sv.gp), sv.xhat.stride(0)
+
+
+def block_fwd(f: BlockArgs, out, out_f32=None, saved: BlockSaved = None):
+    """One persistent tcgen05 kernel for the whole block; ``saved`` receives the activations ``block_bwd`` needs."""
     f.out, f.ld_out, f.out_f32 = ptr(out), out.stride(0), ptr(out_f32)
-    f.h, f.gp, f.ld_h = ptr(h), ptr(gp), (h.stride(0) if h is not None else 0)
-    T = f.T
-    rows = 2 + (2 if out_f32 is not None else 0) + (2 if h is not None else 0)
-    _run("ffn_fwd", _lib.lib().pmgt_ffn_fwd, (C.byref(f), cur_stream()), 1, 2 * T * 128 * rows + 4 * 128 * 128,
-         4 * T * 128 * 128)
+    if saved is not None:
+        _block_saved(f, saved)
+    else:
+        f.xhat = f.rstd = f.h = f.gp = None
+    T, ffn = f.T, f.ffn
+    rows = (2 if ffn else 3) + (2 if out_f32 is not None else 0) + ((3 if ffn else 1) if saved is not None else 0)
+    _run("ffn_fwd" if ffn else "dense_ln_fwd", _lib.lib().pmgt_block_fwd, (C.byref(f), cur_stream()), 1,
+         2 * T * 128 * rows + 2 * 128 * 128 * (2 if ffn else 1), 2 * T * 128 * 128 * (2 if ffn else 1))
 
 
-def ffn_bwd(f: FfnArgs, h, gp, dy, da, dw1, dw2, db1, db2, d_ln_g, d_ln_b, dy_b=None):
-    """da, dW1, dW2, db1, db2, d_gamma, d_beta of the fused feed-forward block from (a, h, gp, dy [+ dy_b])."""
-    f.h, f.gp, f.ld_h = ptr(h), ptr(gp), h.stride(0)
+def block_bwd(f: BlockArgs, saved: BlockSaved, dy, dx, dw2, db2, d_ln_g, d_ln_b, dy_b=None, dw1=None, db1=None, dz=None):
+    """d(in) and the parameter gradients of the block from (in, saved, dy [+ dy_b]); dense block: ``dz`` receives the
+    residual-branch gradient."""
+    _block_saved(f, saved)
     f.dy, f.ld_dy = ptr(dy), dy.stride(0)
     f.dy_b, f.ld_dy_b = ptr(dy_b), (dy_b.stride(0) if dy_b is not None else 0)
-    f.da, f.ld_da = ptr(da), da.stride(0)
+    f.dx, f.ld_dx = ptr(dx), dx.stride(0)
+    f.dz, f.ld_dz = ptr(dz), (dz.stride(0) if dz is not None else 0)
     f.dw1, f.dw2, f.db1, f.db2, f.d_ln_g, f.d_ln_b = ptr(dw1), ptr(dw2), ptr(db1), ptr(db2), ptr(d_ln_g), ptr(d_ln_b)
-    T = f.T
-    _run("ffn_bwd", _lib.lib().pmgt_ffn_bwd, (C.byref(f), cur_stream()), 1,
-         2 * T * 128 * (5 + (1 if dy_b is not None else 0)) + 12 * 128 * 128, 10 * T * 128 * 128)
+    T, ffn = f.T, f.ffn
+    rows = (6 if ffn else 5) + (1 if dy_b is not None else 0)
+    _run("ffn_bwd" if ffn else "dense_ln_bwd", _lib.lib().pmgt_block_bwd, (C.byref(f), cur_stream()), 1,
+         2 * T * 128 * rows + 6 * 128 * 128 * (2 if ffn else 1), 2 * T * 128 * 128 * (4 if ffn else 2))
 
 
 def dw_tile(dy, x, dw_f32, dbias=None, tag="dw_tile"):
