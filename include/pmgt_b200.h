@@ -39,7 +39,7 @@ typedef enum pmgt_status {
 } pmgt_status;
 
 /* ABI version of this header; bumped on any signature change. */
-#define PMGT_B200_ABI_VERSION 9
+#define PMGT_B200_ABI_VERSION 10
 int pmgt_abi_version(void);
 const char* pmgt_last_error(void);
 
@@ -231,6 +231,30 @@ typedef struct pmgt_embed_args {
 
 int pmgt_embed_fuse_fwd(const pmgt_embed_args* a, void* stream);
 int pmgt_embed_fuse_bwd(const pmgt_embed_args* a, void* stream);
+
+/*
+ * Gather-fused feature projection for large graphs, H = 128 (csrc/gather_proj.cu): persistent tcgen05 kernels whose
+ * shared-memory ring belongs to the gathered operand (>= 256 contiguous bytes of a table row per request, ~160 KB in
+ * flight per SM).  Same contract as pmgt_gemm_bf16 with a_rows / b_rows (get_input_feat_embeds, pmgt/pmgt/utils.py:43-50,
+ * + feat_linear, pmgt/pmgt/modeling_pmgt.py:195-198):
+ *   pmgt_gather_proj_fwd  out[T][128] (bf16) = table[rows[t]][0:K] . w[128][K]^T + bias
+ *   pmgt_gather_proj_dw   dw[128][K] (fp32) += dy[T][128]^T . table[rows[t]][0:K]
+ * rows[t] outside [0, table_rows) reads as a zero row.  pmgt_gather_proj_supported(N, K): N == 128, K a multiple of
+ * 128 and of 256, 384 or 512.
+ */
+typedef struct pmgt_gather_proj_args {
+  int64_t T, K;
+  const uint16_t* table; int64_t ld; int64_t table_rows;   /* [table_rows][K] bf16, row pitch ld elements */
+  const int64_t* rows;                                      /* [T] node ids */
+  const uint16_t* w; int64_t ldw; const float* bias;        /* fwd: [128][K] bf16, [128] fp32 (may be NULL) */
+  uint16_t* out; int64_t ldo;                               /* fwd: [T][128] bf16, 32-byte aligned rows */
+  const uint16_t* dy; int64_t ld_dy;                        /* dw: [T][128] bf16 */
+  float* dw; int64_t ld_dw;                                 /* dw: [128][K] fp32, accumulated */
+} pmgt_gather_proj_args;
+
+int pmgt_gather_proj_supported(int64_t N, int64_t K);
+int pmgt_gather_proj_fwd(const pmgt_gather_proj_args* a, void* stream);
+int pmgt_gather_proj_dw(const pmgt_gather_proj_args* a, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* K3  encoder layer pieces                                                  */

@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmgt_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _lib = None
 
@@ -103,6 +103,18 @@ class LinearTileArgs(C.Structure):
     ]
 
 
+class GatherProjArgs(C.Structure):
+    _fields_ = [
+        ("T", C.c_int64), ("K", C.c_int64),
+        ("table", c_vp), ("ld", C.c_int64), ("table_rows", C.c_int64),
+        ("rows", c_vp),
+        ("w", c_vp), ("ldw", C.c_int64), ("bias", c_vp),
+        ("out", c_vp), ("ldo", C.c_int64),
+        ("dy", c_vp), ("ld_dy", C.c_int64),
+        ("dw", c_vp), ("ld_dw", C.c_int64),
+    ]
+
+
 class DwTileArgs(C.Structure):
     _fields_ = [
         ("T", C.c_int64), ("N", C.c_int), ("K", C.c_int),
@@ -186,6 +198,9 @@ SIGNATURES = {
     "pmgt_sample_pairs": (C.c_int, [c_vp, c_vp, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_uint64, c_vp, c_vp, c_vp, c_vp]),
     "pmgt_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), c_vp]),
+    "pmgt_gather_proj_supported": (C.c_int, [C.c_int64, C.c_int64]),
+    "pmgt_gather_proj_fwd": (C.c_int, [C.POINTER(GatherProjArgs), c_vp]),
+    "pmgt_gather_proj_dw": (C.c_int, [C.POINTER(GatherProjArgs), c_vp]),
     "pmgt_embed_fuse_fwd": (C.c_int, [C.POINTER(EmbedArgs), c_vp]),
     "pmgt_embed_fuse_bwd": (C.c_int, [C.POINTER(EmbedArgs), c_vp]),
     "pmgt_attn_core_fwd": (C.c_int, [C.POINTER(AttnArgs), c_vp]),

@@ -1,0 +1,508 @@
+// Gather-fused feature projections of PMGTEmbeddings on large graphs (H = 128): the rows of a frozen bf16 feature
+// table are fetched through the token -> node-id vector INSIDE the GEMM (replaces get_input_feat_embeds,
+// pmgt/pmgt/utils.py:43-50, + feat_linear, pmgt/pmgt/modeling_pmgt.py:195-198, and the weight gradient of that Linear).
+//
+//   forward   out[T][128]  = table[rows[t]][0:K] . W[128][K]^T + bias                       (gather_proj_fwd_kernel)
+//   backward  dW[128][K]  += dY[T][128]^T . table[rows[t]][0:K]                              (gather_proj_dw_kernel)
+//
+// Both are bound by the random row gather from HBM (3072-byte / 1536-byte rows out of a multi-GB table).  What the
+// memory system rewards (tools/probes/gather_probe.cu, B200): requests that cover >= 256 contiguous bytes of a row at
+// a time (128-byte pieces of a row spread over time cap at ~4.6 TB/s whatever the concurrency; 256-byte pieces reach
+// 6.5+) and ~150-250 KB of requests in flight per SM.  So, unlike the general GEMM (gemm_umma.cu: 64-column stages,
+// two CTAs per SM, 96 KB ring shared by both operands):
+//   * one persistent CTA per SM whose shared memory is almost entirely the ring of the GATHERED operand
+//     (forward 5 x 32 KB: 128 rows x 256 B per stage; backward 5 x 32 KB: 32 rows x 1024 B per stage);
+//   * a warp's 16-byte cp.async copies cover 512 contiguous bytes of ONE row (two rows x 256 B in the forward kernel);
+//   * the dense operand (W from L2, dY) streams through a small TMA ring of its own;
+//   * a gather thread hands over the stage that has landed BEFORE it waits for the next free slot (the other order
+//     chains consume -> issue -> arrive into one serial loop of ~1 us per stage: 4.4 instead of 5.4 TB/s);
+//   * forward: two TMEM accumulators, the epilogue of tile n runs under the gather of tile n + 1;
+//     backward: every CTA owns a [128 x 512] (or 384) slice of dW in TMEM for its whole token range and flushes it once.
+// Measured on B200 (tools/bench_gather.py, 294,912 tokens, 1M-row tables, 75 % unique rows): forward 183 us visual /
+// 105 us text (5.4 / 5.1 TB/s of gathered + written bytes), dW 230 / 124 us (4.3 TB/s); pmgt_gemm_bf16 with a_rows /
+// b_rows: 237 / 160 and 245 / 144 us.  Tried and dropped: cp.async.bulk.prefetch.L2 of the rows of later stages
+// (forward 270 us, dW 378 us: the prefetches compete with the demand fetches instead of running ahead of them).
+#include "umma.cuh"
+
+namespace pmgt {
+
+constexpr int kGpRing = 5;  // stages of the gathered operand in flight
+
+__device__ __forceinline__ unsigned char* gp_align1024(unsigned char* p) {
+  return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+__device__ __forceinline__ void gp_cp_async_8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gp_stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------
+constexpr int kGpFwdThreads = 320;  // warp 0: W TMA producer | 1: MMA issuer | 2-5: gather | 6-9: epilogue
+constexpr int kGpFwdAStage = 32768; // 128 rows x 128 columns: two 64-column slabs
+constexpr int kGpFwdWRing = 3;
+constexpr int kGpFwdWStage = 16384; // W[128][64 columns]
+
+struct GpFwdParams {
+  int T, K, num_tiles;
+  const uint16_t* table;
+  long long ld;
+  const long long* rows;
+  long long src_rows;
+  uint16_t* out;
+  long long ldo;
+  const float* bias;
+};
+
+struct GpFwdShared {
+  uint64_t a_full[kGpRing], a_empty[kGpRing];
+  uint64_t w_full[kGpFwdWRing], w_empty[kGpFwdWRing];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  int ids[4][128];
+};
+
+constexpr int kGpFwdSmem = kGpRing * kGpFwdAStage + kGpFwdWRing * kGpFwdWStage + (int)sizeof(GpFwdShared) + 1024;
+
+__device__ __forceinline__ int gp_row_id(const long long* rows, long long src_rows, int m, int T) {
+  if (m >= T) return -1;
+  const long long r = rows[m];
+  return (r < 0 || r >= src_rows) ? -1 : (int)r;
+}
+
+__global__ void __launch_bounds__(kGpFwdThreads, 1)
+gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const GpFwdParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = gp_align1024(smem_dyn);
+  unsigned char* sA = smem;
+  unsigned char* sW = smem + kGpRing * kGpFwdAStage;
+  GpFwdShared* sh = reinterpret_cast<GpFwdShared*>(sW + kGpFwdWRing * kGpFwdWStage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nstage = p.K >> 7;  // 128-column stages per tile
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGpRing; ++s) { mbar_init(&sh->a_full[s], 128u); mbar_init(&sh->a_empty[s], 1u); }
+    for (int s = 0; s < kGpFwdWRing; ++s) { mbar_init(&sh->w_full[s], 1u); mbar_init(&sh->w_empty[s], 1u); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sh->acc_full[s], 1u); mbar_init(&sh->acc_empty[s], 4u); }
+    fence_barrier_init();
+    prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(256u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    // ===================== W producer: one [128 x 64] k-block per TMA, straight from L2 =====================
+    if (lane == 0) {
+      uint32_t wi = 0;
+      const int nkb = p.K >> 6;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < nkb; ++kb, ++wi) {
+          const uint32_t s = wi % kGpFwdWRing;
+          mbar_wait_idle(&sh->w_empty[s], ((wi / kGpFwdWRing) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&sh->w_full[s], (uint32_t)kGpFwdWStage);
+          tma_load_2d(smem_u32(sW + s * kGpFwdWStage), &tmap_w, &sh->w_full[s], kb * 64, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t ai = 0, wi = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t slot = tl & 1u;
+        mbar_wait(&sh->acc_empty[slot], ((tl >> 1) & 1u) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + slot * 128u;
+        for (int st = 0; st < nstage; ++st, ++ai) {
+          const uint32_t sa = ai % kGpRing;
+          mbar_wait(&sh->a_full[sa], (ai / kGpRing) & 1u);
+          const uint32_t a_base = smem_u32(sA + sa * kGpFwdAStage);
+#pragma unroll
+          for (int h = 0; h < 2; ++h, ++wi) {
+            const uint32_t sw = wi % kGpFwdWRing;
+            mbar_wait(&sh->w_full[sw], (wi / kGpFwdWRing) & 1u);
+            tcgen05_fence_after();
+            const uint32_t w_base = smem_u32(sW + sw * kGpFwdWStage);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(tacc, umma_desc(a_base + h * 16384 + k * 32, 16, 1024), umma_desc(w_base + k * 32, 16, 1024), idesc,
+                        (st > 0 || h > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&sh->w_empty[sw]);
+          }
+          umma_commit(&sh->a_empty[sa]);
+        }
+        umma_commit(&sh->acc_full[slot]);
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== gather: 16 lanes x 16 B = 256 contiguous bytes of one table row =====================
+    const int t = threadIdx.x - 64;
+    const int c16 = t & 15, rb = t >> 4;
+    const uint32_t dst_off = (uint32_t)((c16 >> 3) * 16384 + rb * 128 + (((c16 & 7) ^ rb) << 4));
+    constexpr int LAG = kGpRing - 1;
+    uint32_t g = 0;
+    sh->ids[0][t] = gp_row_id(p.rows, p.src_rows, blockIdx.x * 128 + t, p.T);
+    named_bar_sync(1, 128);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+      const int buf = tl & 3, nbuf = (tl + 1) & 3;
+      const int next = tile + gridDim.x;
+      // the next tile's node ids are requested now and parked in the next buffer after the first stage is on its way
+      const int nid = next < p.num_tiles ? gp_row_id(p.rows, p.src_rows, next * 128 + t, p.T) : -1;
+      int rid[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) rid[i] = sh->ids[buf][rb + 8 * i];
+      for (int st = 0; st < nstage; ++st, ++g) {
+        const uint32_t s = g % kGpRing;
+        // hand over the stage issued LAG iterations ago BEFORE waiting for a free slot: the MMA on it then overlaps the
+        // address arithmetic and issue of this stage (arriving after the issue chained consume -> issue -> arrive ->
+        // consume into one serial loop of ~1 us per stage, whatever the memory latency)
+        if (g >= (uint32_t)LAG) {
+          cp_async_wait<LAG - 1>();
+          fence_proxy_async_smem();
+          mbar_arrive(&sh->a_full[(g - LAG) % kGpRing]);
+        }
+        mbar_wait(&sh->a_empty[s], ((g / kGpRing) & 1u) ^ 1u);
+        const uint32_t base = smem_u32(sA + s * kGpFwdAStage) + dst_off;
+        const int col = st * 128 + c16 * 8;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const bool ok = rid[i] >= 0;
+          const uint16_t* src = ok ? p.table + (long long)rid[i] * p.ld + col : p.table;
+          cp_async_16(base + i * 1024, src, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (st == 0) {
+          sh->ids[nbuf][t] = nid;
+          named_bar_sync(1, 128);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (uint32_t i = (g > (uint32_t)LAG ? g - LAG : 0u); i < g; ++i) mbar_arrive(&sh->a_full[i % kGpRing]);  // the last LAG stages
+  } else {
+    // ===================== epilogue: + bias, bf16, one output row per thread =====================
+    const int quarter = warp & 3;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+      const uint32_t slot = tl & 1u;
+      mbar_wait(&sh->acc_full[slot], (tl >> 1) & 1u);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 128u;
+      const int m = tile * 128 + quarter * 32 + lane;
+      uint16_t* orow = p.out + (long long)m * p.ldo;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(taddr + (uint32_t)c0, r);
+        tmem_wait_ld();
+        if (m < p.T) {
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = c0 + g8 * 16 + 2 * j;
+              const float2 b = p.bias != nullptr ? __ldg(reinterpret_cast<const float2*>(p.bias + c)) : make_float2(0.f, 0.f);
+              o[j] = pack_bf16x2(__uint_as_float(r[g8 * 16 + 2 * j]) + b.x, __uint_as_float(r[g8 * 16 + 2 * j + 1]) + b.y);
+            }
+            gp_stg256(orow + c0 + g8 * 16, o);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->acc_empty[slot]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward (weight gradient)
+// ---------------------------------------------------------------------------------------------------
+constexpr int kGpDwThreads = 192;  // warp 0: dY TMA producer | 1: MMA issuer | 2-5: gather, then the flush
+constexpr int kGpDwTok = 32;       // tokens per stage
+constexpr int kGpDwAStage = 8192;  // dY[32 tokens][128]: two slabs of 32 rows x 128 B
+
+struct GpDwParams {
+  int T, K, tok_per_cta;
+  const uint16_t* table;
+  long long ld;
+  const long long* rows;
+  long long src_rows;
+  float* dw;
+  long long ld_dw;
+};
+
+constexpr int kGpDwIdRing = 16;   // stages of node ids held in shared memory
+constexpr int kGpDwIdAhead = 12;  // ... requested this many stages ahead (8-byte cp.async in the gather's own groups)
+
+struct GpDwShared {
+  uint64_t full[kGpRing], empty[kGpRing];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+  long long ids[kGpDwIdRing][kGpDwTok];
+};
+
+template <int NC>
+constexpr int gp_dw_smem() { return kGpRing * (kGpDwAStage + NC * 4096) + (int)sizeof(GpDwShared) + 1024; }
+
+template <int NC>  // 64-column slabs of the table row one CTA covers (8: 512 columns, 6: 384, 4: 256)
+__global__ void __launch_bounds__(kGpDwThreads, 1)
+gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const GpDwParams p) {
+  constexpr int kBStage = NC * 4096;
+  constexpr int kPerThread = 2 * NC;  // 16-byte copies per gather thread and stage
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = gp_align1024(smem_dyn);
+  unsigned char* sB = smem;
+  unsigned char* sAm = smem + kGpRing * kBStage;
+  GpDwShared* sh = reinterpret_cast<GpDwShared*>(sAm + kGpRing * kGpDwAStage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * NC * 64;
+  const int tok0 = blockIdx.y * p.tok_per_cta;
+  int tok1 = tok0 + p.tok_per_cta;
+  if (tok1 > p.T) tok1 = p.T;
+  const int nstage = tok1 > tok0 ? (tok1 - tok0 + kGpDwTok - 1) / kGpDwTok : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGpRing; ++s) { mbar_init(&sh->full[s], 1u + 128u); mbar_init(&sh->empty[s], 1u); }
+    mbar_init(&sh->acc_full, 1u);
+    fence_barrier_init();
+    prefetch_tmap(&tmap_dy);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nstage; ++i) {
+        const uint32_t s = (uint32_t)i % kGpRing;
+        mbar_wait_idle(&sh->empty[s], (((uint32_t)i / kGpRing) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&sh->full[s], (uint32_t)kGpDwAStage);
+        const uint32_t dst = smem_u32(sAm + s * kGpDwAStage);
+        tma_load_2d(dst, &tmap_dy, &sh->full[s], 0, tok0 + i * kGpDwTok);
+        tma_load_2d(dst + 4096, &tmap_dy, &sh->full[s], 64, tok0 + i * kGpDwTok);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // M = 128 (output features, MN-major dY), N = NC * 32 per instruction (MN-major table rows), K = 16 tokens
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((NC * 32) >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      for (int i = 0; i < nstage; ++i) {
+        const uint32_t s = (uint32_t)i % kGpRing;
+        mbar_wait(&sh->full[s], ((uint32_t)i / kGpRing) & 1u);
+        tcgen05_fence_after();
+        const uint32_t a_base = smem_u32(sAm + s * kGpDwAStage);
+        const uint32_t b_base = smem_u32(sB + s * kBStage);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint64_t da = umma_desc(a_base + k * 2048, 4096, 1024);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t db = umma_desc(b_base + h * (NC / 2) * 4096 + k * 2048, 4096, 1024);
+            umma_bf16(tmem_base + (uint32_t)(h * NC * 32), da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&sh->empty[s]);
+      }
+      umma_commit(&sh->acc_full);
+    }
+  } else {
+    // ===================== gather: a warp's 32 lanes cover 512 contiguous bytes of one table row =====================
+    const int t = threadIdx.x - 64;
+    constexpr int LAG = kGpRing - 1;
+    constexpr int kChunks = NC * 8;  // 16-byte chunks per row and stage
+    int row_of[kPerThread];
+    uint32_t dst_of[kPerThread];
+    int col_of[kPerThread];
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const int flat = j * 128 + t;
+      const int r = flat / kChunks, ch = flat % kChunks;
+      row_of[j] = r;
+      col_of[j] = n0 + ch * 8;
+      dst_of[j] = (uint32_t)((ch >> 3) * 4096 + r * 128 + (((ch & 7) ^ (r & 7)) << 4));
+    }
+    // node ids: thread t < 32 owns token t of every stage.  Stages [0, kGpDwIdAhead) are loaded here; inside the loop
+    // the ids of stage i + kGpDwIdAhead ride in stage i's cp.async group (no register ever waits on an id load), and
+    // become visible to the other threads through the full -> MMA -> empty barrier chain long before they are read.
+    auto id_src = [&](int stage) { return p.rows + tok0 + stage * kGpDwTok + t; };
+    auto id_ok = [&](int stage) { return tok0 + stage * kGpDwTok + t < tok1; };
+    if (t < kGpDwTok) {
+      for (int st = 0; st < kGpDwIdAhead && st < nstage; ++st) sh->ids[st % kGpDwIdRing][t] = id_ok(st) ? *id_src(st) : -1ll;
+    }
+    named_bar_sync(1, 128);
+    for (int i = 0; i < nstage; ++i) {
+      const uint32_t s = (uint32_t)i % kGpRing;
+      if (i >= LAG) {  // see the forward kernel: arrive first, then wait for the free slot
+        cp_async_wait<LAG - 1>();
+        fence_proxy_async_smem();
+        mbar_arrive(&sh->full[(i - LAG) % kGpRing]);
+      }
+      mbar_wait(&sh->empty[s], (((uint32_t)i / kGpRing) & 1u) ^ 1u);
+      const uint32_t base = smem_u32(sB + s * kBStage);
+      const long long* ids = sh->ids[i % kGpDwIdRing];
+#pragma unroll
+      for (int j = 0; j < kPerThread; ++j) {
+        const long long r = ids[row_of[j]];
+        const bool ok = r >= 0 && r < p.src_rows;
+        const uint16_t* src = ok ? p.table + r * p.ld + col_of[j] : p.table;
+        cp_async_16(base + dst_of[j], src, ok ? 16u : 0u);
+      }
+      if (t < kGpDwTok && i + kGpDwIdAhead < nstage) {
+        long long* dst = &sh->ids[(i + kGpDwIdAhead) % kGpDwIdRing][t];
+        if (id_ok(i + kGpDwIdAhead)) gp_cp_async_8(smem_u32(dst), id_src(i + kGpDwIdAhead));
+        else *dst = -1ll;
+      }
+      cp_async_commit();
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (int i = (nstage > LAG ? nstage - LAG : 0); i < nstage; ++i) mbar_arrive(&sh->full[i % kGpRing]);
+
+    // ---- flush: dW[m][n0 ..] += accumulator row m, 32 columns at a time, the start column rotated per CTA so that
+    //      the CTAs of one column group do not hit the same L2 lines in lock-step
+    if (nstage > 0) {
+      mbar_wait(&sh->acc_full, 0u);
+      tcgen05_fence_after();
+      const int quarter = warp & 3;
+      const int m = quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      float* drow = p.dw + (long long)m * p.ld_dw + n0;
+      constexpr int kGroups = NC * 2;  // 32-column groups
+#pragma unroll 1
+      for (int gq = 0; gq < kGroups; ++gq) {
+        const int c0 = ((gq + (int)blockIdx.y) % kGroups) * 32;
+        uint32_t r[32];
+        tmem_ld_x32(taddr + (uint32_t)c0, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + 4 * j), "f"(__uint_as_float(r[4 * j])),
+                       "f"(__uint_as_float(r[4 * j + 1])), "f"(__uint_as_float(r[4 * j + 2])), "f"(__uint_as_float(r[4 * j + 3]))
+                       : "memory");
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+template <int NC>
+static int launch_dw(const CUtensorMap& tm, const GpDwParams& kp, dim3 grid, cudaStream_t st) {
+  auto kern = gather_proj_dw_kernel<NC>;
+  constexpr int smem = gp_dw_smem<NC>();
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, kGpDwThreads, smem, st>>>(tm, kp);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+static int dw_slabs(long long K) { return K % 512 == 0 ? 8 : (K % 384 == 0 ? 6 : (K % 256 == 0 ? 4 : 0)); }
+
+}  // namespace pmgt
+
+using namespace pmgt;
+
+extern "C" int pmgt_gather_proj_supported(int64_t N, int64_t K) {
+  return N == 128 && K > 0 && K % 128 == 0 && dw_slabs(K) != 0 ? 1 : 0;
+}
+
+static int gp_check(const pmgt_gather_proj_args* a, const char* who) {
+  PMGT_REQUIRE(a, "%s: null args", who);
+  PMGT_REQUIRE(a->T >= 0 && a->T < (1ll << 31) - 4096, "%s: bad token count %lld", who, (long long)a->T);
+  PMGT_REQUIRE(pmgt_gather_proj_supported(128, a->K), "%s: K = %lld is not supported (multiple of 128 and of 256/384/512)", who,
+               (long long)a->K);
+  PMGT_REQUIRE(a->table && a->rows, "%s: null table / rows", who);
+  PMGT_REQUIRE(a->ld % 8 == 0 && ((uintptr_t)a->table & 15) == 0, "%s: table rows must be 16-byte aligned", who);
+  PMGT_REQUIRE(a->table_rows > 0 && a->table_rows < (1ll << 31), "%s: bad table_rows %lld", who, (long long)a->table_rows);
+  return PMGT_OK;
+}
+
+extern "C" int pmgt_gather_proj_fwd(const pmgt_gather_proj_args* a, void* stream) {
+  int rc = gp_check(a, "pmgt_gather_proj_fwd");
+  if (rc) return rc;
+  if (a->T == 0) return PMGT_OK;
+  PMGT_REQUIRE(a->w && a->out, "pmgt_gather_proj_fwd: null w / out");
+  PMGT_REQUIRE(a->ldw % 8 == 0 && ((uintptr_t)a->w & 15) == 0, "pmgt_gather_proj_fwd: w must be 16-byte aligned");
+  PMGT_REQUIRE(a->ldo % 16 == 0 && ((uintptr_t)a->out & 31) == 0, "pmgt_gather_proj_fwd: out rows must be 32-byte aligned");
+  CUtensorMap tw;
+  memset(&tw, 0, sizeof(tw));
+  rc = make_tmap(&tw, a->w, a->K, 128, a->ldw, 64, 128);
+  if (rc) return rc;
+  GpFwdParams kp;
+  kp.T = (int)a->T; kp.K = (int)a->K; kp.num_tiles = (int)((a->T + 127) / 128);
+  kp.table = a->table; kp.ld = a->ld; kp.rows = (const long long*)a->rows; kp.src_rows = a->table_rows;
+  kp.out = a->out; kp.ldo = a->ldo; kp.bias = a->bias;
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured))
+    PMGT_CHECK_CUDA(cudaFuncSetAttribute(gather_proj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGpFwdSmem));
+  const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
+  gather_proj_fwd_kernel<<<grid, kGpFwdThreads, kGpFwdSmem, (cudaStream_t)stream>>>(tw, kp);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+extern "C" int pmgt_gather_proj_dw(const pmgt_gather_proj_args* a, void* stream) {
+  int rc = gp_check(a, "pmgt_gather_proj_dw");
+  if (rc) return rc;
+  if (a->T == 0) return PMGT_OK;
+  PMGT_REQUIRE(a->dy && a->dw, "pmgt_gather_proj_dw: null dy / dw");
+  PMGT_REQUIRE(a->ld_dy % 8 == 0 && ((uintptr_t)a->dy & 15) == 0, "pmgt_gather_proj_dw: dy must be 16-byte aligned");
+  PMGT_REQUIRE(a->ld_dw % 4 == 0 && ((uintptr_t)a->dw & 15) == 0, "pmgt_gather_proj_dw: dw must be 16-byte aligned");
+  CUtensorMap tdy;
+  memset(&tdy, 0, sizeof(tdy));
+  rc = make_tmap(&tdy, a->dy, 128, a->T, a->ld_dy, 64, kGpDwTok);
+  if (rc) return rc;
+  const int nc = dw_slabs(a->K);
+  const int col_groups = (int)(a->K / (nc * 64));
+  int ranges = num_sms() / col_groups;
+  if (ranges < 1) ranges = 1;
+  long long tpc = (a->T + ranges - 1) / ranges;
+  tpc = ((tpc + kGpDwTok - 1) / kGpDwTok) * kGpDwTok;
+  ranges = (int)((a->T + tpc - 1) / tpc);
+  GpDwParams kp;
+  kp.T = (int)a->T; kp.K = (int)a->K; kp.tok_per_cta = (int)tpc;
+  kp.table = a->table; kp.ld = a->ld; kp.rows = (const long long*)a->rows; kp.src_rows = a->table_rows;
+  kp.dw = a->dw; kp.ld_dw = a->ld_dw;
+  dim3 grid((unsigned)col_groups, (unsigned)ranges, 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nc == 8) return launch_dw<8>(tdy, kp, grid, st);
+  if (nc == 6) return launch_dw<6>(tdy, kp, grid, st);
+  return launch_dw<4>(tdy, kp, grid, st);
+}

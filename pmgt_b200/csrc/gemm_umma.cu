@@ -187,6 +187,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        // the stage that has landed is handed to the MMA issuer BEFORE waiting for a free slot (see gather_proj.cu)
+        if (i >= LAG) {
+          cp_async_wait<LAG - 1>();
+          fence_proxy_async_smem();
+          mbar_arrive(&sh->full[(i - LAG) % STAGES]);
+        }
         mbar_wait(&sh->empty[s], ph ^ 1u);
         const int k0 = (kb_begin + i) * BK;
         if (GATHER_A) {
@@ -209,11 +215,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           gather_slab<4>(bs + 8192, t, p.b_src, p.ldb, b_rows_reg, n0 + 64, p.N);
         }
         cp_async_commit();
-        if (i >= LAG) {
-          cp_async_wait<LAG>();
-          fence_proxy_async_smem();
-          mbar_arrive(&sh->full[(i - LAG) % STAGES]);
-        }
       }
       // drain
       cp_async_wait<0>();

@@ -45,6 +45,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // every spin iteration takes an issue slot from the epilogue warps of the same scheduler -- the try_wait carries a
 // suspend-time hint and failed polls back off with nanosleep.
 __device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+#ifdef PMGT_SPIN_WAIT
+  mbar_wait(bar, parity);
+  return;
+#endif
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
   uint32_t spins = 0;

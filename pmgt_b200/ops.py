@@ -132,6 +132,18 @@ def gemm(a, b, out, *, M, N, K, lda, ldb, ldo, a_mn=False, b_mn=False, a_rows=No
     _run(tag, _lib.lib().pmgt_gemm_bf16, (C.byref(g), cur_stream()), 1, nbytes, 2 * M * N * K)
 
 
+# gathered feature projections through the persistent wide-stage kernels (csrc/gather_proj.cu); False: pmgt_gemm_bf16
+GATHER_PROJ = True
+_GP_SUPPORTED = {}
+
+
+def gather_proj_supported(N: int, K: int) -> bool:
+    key = (int(N), int(K))
+    if key not in _GP_SUPPORTED:
+        _GP_SUPPORTED[key] = bool(_lib.lib().pmgt_gather_proj_supported(key[0], key[1]))
+    return _GP_SUPPORTED[key]
+
+
 def linear_fwd(x, w, bias, out, *, rows=None, src_rows=0, gelu_aux=None, tag=None):
     """out[T,N] = x[T,K] @ w[N,K]^T + bias   (x optionally gathered through ``rows``)."""
     N, K = w.shape
@@ -139,6 +151,12 @@ def linear_fwd(x, w, bias, out, *, rows=None, src_rows=0, gelu_aux=None, tag=Non
     epi = EPI_BIAS if bias is not None else 0
     if gelu_aux is not None:
         epi |= EPI_GELU
+    if rows is not None and gelu_aux is None and GATHER_PROJ and gather_proj_supported(N, K) and out.stride(0) % 16 == 0:
+        g = _lib.GatherProjArgs(T, K, ptr(x), x.stride(0), src_rows, ptr(rows), ptr(w), w.stride(0), ptr(bias), ptr(out),
+                                out.stride(0), None, 0, None, 0)
+        _run(tag or "gemm_fwd_gather", _lib.lib().pmgt_gather_proj_fwd, (C.byref(g), cur_stream()), 1,
+             2 * T * K + 2 * N * K + 2 * T * N, 2 * T * N * K)
+        return
     gemm(x, w, out, M=T, N=N, K=K, lda=x.stride(0), ldb=w.stride(0), ldo=out.stride(0), a_rows=rows,
          a_src_rows=src_rows, bias=bias, aux=gelu_aux, ld_aux=(gelu_aux.stride(0) if gelu_aux is not None else 0), epi=epi,
          tag=tag or ("gemm_fwd_gather" if rows is not None else "gemm_fwd"))
@@ -164,6 +182,12 @@ def linear_dw(dy, x, dw_f32, *, rows=None, src_rows=0, x_cols=None, tag=None):
     ``x`` may be a table whose rows are fetched through ``rows`` (T int64 ids)."""
     T, N = dy.shape
     K = x_cols if x_cols is not None else x.shape[1]
+    if rows is not None and GATHER_PROJ and gather_proj_supported(N, K) and dy.stride(1) == 1:
+        g = _lib.GatherProjArgs(T, K, ptr(x), x.stride(0), src_rows, ptr(rows), None, 0, None, None, 0, ptr(dy), dy.stride(0),
+                                ptr(dw_f32), dw_f32.stride(0))
+        _run(tag or "gemm_dw_gather", _lib.lib().pmgt_gather_proj_dw, (C.byref(g), cur_stream()), 1,
+             2 * T * K + 2 * T * N + 4 * N * K, 2 * T * N * K)
+        return
     tiles = ((N + 127) // 128) * ((K + 127) // 128)
     num_kb = (T + 63) // 64
     # two CTAs are resident per SM: the split count keeps tiles * split WITHIN one wave of 2 * SMs CTAs (rounding up put 300

@@ -41,9 +41,9 @@ def test_struct_layouts_match_the_header():
     prog = r'''
 #include <stdio.h>
 #include "pmgt_b200.h"
-int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pmgt_gemm_args), sizeof(pmgt_embed_args), sizeof(pmgt_attn_args),
+int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pmgt_gemm_args), sizeof(pmgt_embed_args), sizeof(pmgt_attn_args),
  sizeof(pmgt_resln_args), sizeof(pmgt_gsr_args), sizeof(pmgt_nfr_args), sizeof(pmgt_block_args), sizeof(pmgt_linear_tile_args),
- sizeof(pmgt_dw_tile_args), sizeof(pmgt_lnbwd_args)); return 0;}
+ sizeof(pmgt_dw_tile_args), sizeof(pmgt_lnbwd_args), sizeof(pmgt_gather_proj_args)); return 0;}
 '''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
@@ -52,7 +52,7 @@ int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pmgt_g
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     got = [ctypes.sizeof(s) for s in (_lib.GemmArgs, _lib.EmbedArgs, _lib.AttnArgs, _lib.ResLnArgs, _lib.GsrArgs, _lib.NfrArgs,
-                                   _lib.BlockArgs, _lib.LinearTileArgs, _lib.DwTileArgs, _lib.LnBwdArgs)]
+                                   _lib.BlockArgs, _lib.LinearTileArgs, _lib.DwTileArgs, _lib.LnBwdArgs, _lib.GatherProjArgs)]
     assert got == sizes, (got, sizes)
 
 

@@ -111,6 +111,38 @@ def test_linear_dw_gathered_rows():
     _close(dw, dy.float().t() @ table[idx].float(), 2e-3)
 
 
+@pytest.mark.parametrize("T,K,nrows", [(40000, 1536, 3000), (20001, 768, 777), (130, 256, 20), (5000, 512, 64), (33, 1536, 9)])
+def test_gather_proj_kernels_match_torch(T, K, nrows):
+    """The persistent gather-fused projection kernels (csrc/gather_proj.cu): forward wraps around the 148 CTAs at
+    T = 40000 (313 tiles), ragged last tiles / stages, ids outside the table read as zero rows; dW over every slab
+    count (K = 512 / 768 / 256 -> 8 / 6 / 4 slabs)."""
+    ops = _ops()
+    assert ops.gather_proj_supported(128, K)
+    g = torch.Generator(device="cuda").manual_seed(T + K)
+    table = torch.randn(nrows, K, device="cuda", generator=g).to(BF16)
+    idx = torch.randint(0, nrows, (T,), device="cuda", dtype=torch.int64, generator=g)
+    idx[::17] = nrows + 5  # out of range: zero row
+    idx[3::29] = -1
+    w = (torch.randn(128, K, device="cuda", generator=g) * 0.05).to(BF16)
+    b = torch.randn(128, device="cuda", generator=g) * 0.1
+    x = table[idx.clamp(0, nrows - 1)].float()
+    x[(idx < 0) | (idx >= nrows)] = 0
+    out = torch.full((T, 128), float("nan"), device="cuda", dtype=BF16)
+    ops.linear_fwd(table, w, b, out, rows=idx, src_rows=nrows)
+    _close(out, x @ w.float().t() + b, 1e-2)
+    dy = (torch.randn(T, 128, device="cuda", generator=g) * 0.1).to(BF16)
+    dw = torch.ones(128, K, device="cuda", dtype=torch.float32)
+    ops.linear_dw(dy, table, dw, rows=idx, src_rows=nrows, x_cols=K)
+    _close(dw, dy.float().t() @ x + 1.0, 3e-3)
+    # the general GEMM path (pmgt_gemm_bf16 with a_rows) agrees
+    ops.GATHER_PROJ = False
+    try:
+        out2 = torch.empty_like(out)
+        ops.linear_fwd(table, w, b, out2, rows=idx, src_rows=nrows)
+    finally:
+        ops.GATHER_PROJ = True
+    assert (out2.float() - out.float()).abs().max() < 2e-2
+
 def test_gemm_rejects_bad_arguments():
     from pmgt_b200 import _lib
     ops = _ops()

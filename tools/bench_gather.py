@@ -11,6 +11,8 @@ ROWS = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_002
 torch.manual_seed(0)
 res = {"T": T, "rows": ROWS}
 ops.set_pdl(False)
+ops.GATHER_PROJ = os.environ.get("GATHER_PROJ", "1") != "0"
+res["gather_proj"] = ops.GATHER_PROJ
 for name, D in (("visual", 1536), ("text", 768)):
     table = torch.randn(ROWS, D, device="cuda", dtype=torch.float32).to(BF16)
     # ids with the duplication of a real step (~68 % unique): a mix of uniform and Zipf-like hot rows

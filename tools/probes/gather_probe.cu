@@ -1,0 +1,75 @@
+// DRAM efficiency of a random row gather by request pattern (rows of ROWB bytes from a table much larger than L2).
+//   mode 0: a warp fetches SEG contiguous bytes of one row per instruction group, all segments of a row back to back
+//   mode 1: GEMM-like: a 128-row tile is walked k-block by k-block (128 B of every row per k-block, barrier between)
+//   mode 2: like 1 with SEGB bytes of every row per step (SEGB = 256 / 512)
+// build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o gather_probe gather_probe.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+
+__global__ void k_rows(const uint4* __restrict__ tab, const int* __restrict__ ids, int T, int row16, unsigned* sink) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  unsigned acc = 0;
+  for (int t = warp; t < T; t += nw) {
+    const uint4* r = tab + (size_t)ids[t] * row16;
+    for (int c = lane; c < row16; c += 32) { uint4 v = __ldg(r + c); acc ^= v.x ^ v.y ^ v.z ^ v.w; }
+  }
+  if (acc == 0x12345u) *sink = acc;
+}
+
+// tile walk: 128 rows per tile, per step every row contributes seg16 16-byte chunks; 128 threads
+template <int SEG16>
+__global__ void k_tile(const uint4* __restrict__ tab, const int* __restrict__ ids, int T, int row16, unsigned* sink) {
+  __shared__ int rid[128];
+  unsigned acc = 0;
+  const int t = threadIdx.x;
+  for (int tile = blockIdx.x; tile * 128 < T; tile += gridDim.x) {
+    __syncthreads();
+    rid[t] = ids[min(tile * 128 + t, T - 1)];
+    __syncthreads();
+    for (int c0 = 0; c0 < row16; c0 += SEG16) {
+      // 128 rows x SEG16 chunks per step: thread -> (row, chunk) with SEG16 consecutive lanes on one row
+      uint4 v[SEG16];
+#pragma unroll
+      for (int i = 0; i < SEG16; ++i) {
+        const int flat = i * 128 + t;
+        const int r = flat / SEG16, c = flat % SEG16;
+        v[i] = __ldg(tab + (size_t)rid[r] * row16 + c0 + c);
+      }
+#pragma unroll
+      for (int i = 0; i < SEG16; ++i) acc ^= v[i].x ^ v[i].y ^ v[i].z ^ v[i].w;
+    }
+  }
+  if (acc == 0x12345u) *sink = acc;
+}
+
+int main(int argc, char** argv) {
+  const int N = 1000002, T = 294912;
+  const int rowb = argc > 1 ? atoi(argv[1]) : 3072;
+  const int row16 = rowb / 16;
+  uint4* tab; int* ids; unsigned* sink;
+  cudaMalloc(&tab, (size_t)N * rowb); cudaMemset(tab, 1, (size_t)N * rowb);
+  cudaMalloc(&ids, T * 4); cudaMalloc(&sink, 4);
+  std::vector<int> h(T); srand(1); for (auto& x : h) x = (int)(((unsigned)rand() * 32768u + (unsigned)rand()) % N);
+  cudaMemcpy(ids, h.data(), T * 4, cudaMemcpyHostToDevice);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  auto run = [&](const char* name, auto fn) {
+    for (int i = 0; i < 2; ++i) fn();
+    cudaEventRecord(e0); for (int i = 0; i < 10; ++i) fn(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 10;
+    printf("%-28s rowb=%d  %8.1f us  %7.1f GB/s  (%s)\n", name, rowb, ms * 1e3, (double)T * rowb / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+  };
+  run("warp per row, 8 CTA x 256/SM", [&] { k_rows<<<148 * 8, 256>>>(tab, ids, T, row16, sink); });
+  run("warp per row, 4 CTA x 256/SM", [&] { k_rows<<<148 * 4, 256>>>(tab, ids, T, row16, sink); });
+  run("tile walk 128B/step 4 CTA/SM", [&] { k_tile<8><<<148 * 4, 128>>>(tab, ids, T, row16, sink); });
+  run("tile walk 128B/step 8 CTA/SM", [&] { k_tile<8><<<148 * 8, 128>>>(tab, ids, T, row16, sink); });
+  run("tile walk 128B/step 16 CTA/SM", [&] { k_tile<8><<<148 * 16, 128>>>(tab, ids, T, row16, sink); });
+  run("tile walk 256B/step 4 CTA/SM", [&] { k_tile<16><<<148 * 4, 128>>>(tab, ids, T, row16, sink); });
+  run("tile walk 256B/step 8 CTA/SM", [&] { k_tile<16><<<148 * 8, 128>>>(tab, ids, T, row16, sink); });
+  run("tile walk 512B/step 2 CTA/SM", [&] { k_tile<32><<<148 * 2, 128>>>(tab, ids, T, row16, sink); });
+  run("tile walk 512B/step 4 CTA/SM", [&] { k_tile<32><<<148 * 4, 128>>>(tab, ids, T, row16, sink); });
+  return 0;
+}
