@@ -306,6 +306,8 @@ int attn_small_fwd(const pmgt_attn_args* a, cudaStream_t st);  // attention_smal
 int attn_small_bwd(const pmgt_attn_args* a, cudaStream_t st);
 int attn_mma_fwd(const pmgt_attn_args* a, cudaStream_t st);    // attention_mma.cu
 int attn_mma_bwd(const pmgt_attn_args* a, cudaStream_t st);
+int attn_reg_fwd(const pmgt_attn_args* a, cudaStream_t st);    // attention_reg.cu (8 < L <= 64, scores in MMA fragments)
+int attn_reg_bwd(const pmgt_attn_args* a, cudaStream_t st);
 int attn_mid_fwd(const pmgt_attn_args* a, cudaStream_t st);    // attention_mid.cu (8 < L <= 64, tensor-core products)
 int attn_mid_bwd(const pmgt_attn_args* a, cudaStream_t st);
 
@@ -322,6 +324,7 @@ int pmgt_attn_core_fwd(const pmgt_attn_args* a, void* stream) {
   {  // register-resident kernel for the short-sequence shapes (default PMGT: L = 6, dh = 128)
     int r = attn_mma_fwd(a, (cudaStream_t)stream);
     if (r == 0) r = attn_small_fwd(a, (cudaStream_t)stream);
+    if (r == 0) r = attn_reg_fwd(a, (cudaStream_t)stream);
     if (r == 0) r = attn_mid_fwd(a, (cudaStream_t)stream);
     if (r < 0) return r;
     if (r > 0) return PMGT_OK;
@@ -346,6 +349,7 @@ int pmgt_attn_core_bwd(const pmgt_attn_args* a, void* stream) {
   PMGT_REQUIRE(a->heads >= 1 && a->H % a->heads == 0, "attention: H must be divisible by heads");
   int rc = attn_mma_bwd(a, (cudaStream_t)stream);
   if (rc == 0) rc = attn_small_bwd(a, (cudaStream_t)stream);
+  if (rc == 0) rc = attn_reg_bwd(a, (cudaStream_t)stream);
   if (rc == 0) rc = attn_mid_bwd(a, (cudaStream_t)stream);
   if (rc < 0) return rc;
   if (rc == 0) {

@@ -203,6 +203,38 @@ def test_attention_core_fwd_bwd(R, L, H, heads, beta):
     _close(dbias, dqkvc.float().sum(0), 1e-3, "d_bias_qkvc")
 
 
+@pytest.mark.parametrize("L,dh", [(33, 64), (20, 32), (64, 128)])
+def test_attention_dropout_mask_agrees_between_fwd_and_bwd_medium_L(L, dh):
+    """Register-resident attention core (attention_reg.cu), train mode: with V = the first L unit vectors the forward
+    output rows ARE the dropped attention matrix A; the backward pass (which regenerates the mask in the transposed
+    orientation) must see the same A: dV_j[c] = A_{i j} for dctx = e_c at row i.  Also the keep rate."""
+    ops = _ops()
+    R, H, heads, p = 6, dh, 1, 0.25
+    T = R * L
+    qkvc = _r(T, 4 * H, s=0.7)
+    v = torch.zeros(R, L, H, device="cuda")
+    v[:, torch.arange(L), torch.arange(L)] = 1.0
+    qkvc[:, 2 * H:3 * H] = v.view(T, H).to(BF16)
+    mask = torch.ones(R, L, device="cuda")
+    ctx = torch.empty(T, H, device="cuda", dtype=BF16)
+    ops.attn_core_fwd(ops.attn_args(R, L, H, heads, 1.0, qkvc, mask, p, 77, 3, ctx=ctx))
+    A = ctx.view(R, L, H)[:, :, :L].float()            # A[r, i, j]
+    zero_rate = float((A == 0).float().mean())
+    assert abs(zero_rate - p) < 0.03, zero_rate
+    ctx0 = torch.empty_like(ctx)
+    ops.attn_core_fwd(ops.attn_args(R, L, H, heads, 1.0, qkvc, mask, 0.0, 77, 3, ctx=ctx0))
+    A0 = ctx0.view(R, L, H)[:, :, :L].float()
+    kept = A != 0
+    assert torch.allclose(A[kept], (A0 / (1 - p))[kept], rtol=3e-2, atol=2e-3)
+    for i_star in (0, L // 2, L - 1):
+        dctx = torch.zeros(R, L, H, device="cuda")
+        dctx[:, i_star, 5] = 1.0
+        dqkvc = torch.empty_like(qkvc)
+        ops.attn_core_bwd(ops.attn_args(R, L, H, heads, 1.0, qkvc, mask, p, 77, 3, dctx=dctx.view(T, H).to(BF16), dqkvc=dqkvc))
+        dV = dqkvc[:, 2 * H:3 * H].float().view(R, L, H)[:, :, 5]     # dV[r, j] = A[r, i*, j]
+        assert torch.allclose(dV, A[:, i_star, :], rtol=2e-2, atol=2e-3), (i_star, float((dV - A[:, i_star, :]).abs().max()))
+
+
 @pytest.mark.parametrize("T,H", [(50, 128), (33, 64), (20, 768), (9, 32)])
 def test_res_ln_fwd_bwd(T, H):
     ops = _ops()
