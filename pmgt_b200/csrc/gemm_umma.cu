@@ -70,6 +70,62 @@ __device__ __forceinline__ void gather_slab(uint32_t slab, int t, const uint16_t
   }
 }
 
+// Epilogue of 32 accumulator columns [n_base, n_base + 32) of output row m (one row per thread)
+__device__ __forceinline__ void epilogue_chunk(const GemmKernelArgs& p, uint32_t epi, int m, int n_base, const uint32_t (&r)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n = n_base + g * 8;
+    if (n >= p.N) break;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
+    if (epi & PMGT_EPI_BIAS) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (epi & PMGT_EPI_GELU) {
+      uint4 pre;
+      pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
+      pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(p.aux + (long long)m * p.ld_aux + n) = pre;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+    }
+    if (epi & PMGT_EPI_GELU_BWD) {
+      const uint4 pre = *reinterpret_cast<const uint4*>(p.aux + (long long)m * p.ld_aux + n);
+      float x[8];
+      unpack_bf16x2(pre.x, x[0], x[1]); unpack_bf16x2(pre.y, x[2], x[3]);
+      unpack_bf16x2(pre.z, x[4], x[5]); unpack_bf16x2(pre.w, x[6], x[7]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(x[j]);
+    }
+    if (epi & PMGT_EPI_ADDEND) {
+      const uint4 ad = *reinterpret_cast<const uint4*>(p.addend + (long long)m * p.ld_addend + n);
+      float x[8];
+      unpack_bf16x2(ad.x, x[0], x[1]); unpack_bf16x2(ad.y, x[2], x[3]);
+      unpack_bf16x2(ad.z, x[4], x[5]); unpack_bf16x2(ad.w, x[6], x[7]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += x[j];
+    }
+    if (epi & PMGT_EPI_ATOMIC) {
+      float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
+    } else if (epi & PMGT_EPI_OUT_F32) {
+      float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (long long)m * p.ldo + n) = o;
+    }
+  }
+}
+
 template <bool A_MN, bool B_MN, bool GATHER_A, bool GATHER_B, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -237,58 +293,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tmem_ld_x32(taddr + (uint32_t)c0, r);
       tmem_wait_ld();
       if (!row_ok) continue;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int n = n0 + c0 + g * 8;
-        if (n >= p.N) break;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
-        if (epi & PMGT_EPI_BIAS) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-        if (epi & PMGT_EPI_GELU) {
-          uint4 pre;
-          pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
-          pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(p.aux + (long long)m * p.ld_aux + n) = pre;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (epi & PMGT_EPI_GELU_BWD) {
-          const uint4 pre = *reinterpret_cast<const uint4*>(p.aux + (long long)m * p.ld_aux + n);
-          float x[8];
-          unpack_bf16x2(pre.x, x[0], x[1]); unpack_bf16x2(pre.y, x[2], x[3]);
-          unpack_bf16x2(pre.z, x[4], x[5]); unpack_bf16x2(pre.w, x[6], x[7]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(x[j]);
-        }
-        if (epi & PMGT_EPI_ADDEND) {
-          const uint4 ad = *reinterpret_cast<const uint4*>(p.addend + (long long)m * p.ld_addend + n);
-          float x[8];
-          unpack_bf16x2(ad.x, x[0], x[1]); unpack_bf16x2(ad.y, x[2], x[3]);
-          unpack_bf16x2(ad.z, x[4], x[5]); unpack_bf16x2(ad.w, x[6], x[7]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += x[j];
-        }
-        if (epi & PMGT_EPI_ATOMIC) {
-          float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
-        } else if (epi & PMGT_EPI_OUT_F32) {
-          float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
-          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        } else {
-          uint4 o;
-          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (long long)m * p.ldo + n) = o;
-        }
-      }
+      epilogue_chunk(p, epi, m, n0 + c0, r);
     }
   }
 
@@ -297,6 +302,144 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// Persistent variant for dense operands (both by TMA) without split-K: one CTA per SM walks the output tiles
+// (n fastest, so that concurrently running CTAs share A rows and W in L2), a 6-stage operand ring, two TMEM
+// accumulators and EIGHT dedicated epilogue warps (two per TMEM lane quarter, 64 columns each), so that the epilogue
+// of tile i runs under the main loop of tile i + 1.  With K = 768 a tile's main loop is ~3000 cycles -- about as long
+// as its prologue + one-row-per-thread epilogue, which the one-tile-per-CTA kernel above can only hide behind the
+// second resident CTA (0.5 PFLOP/s on the H = 768 Linears where the long-K weight-gradient GEMM reaches 1.2).
+// ---------------------------------------------------------------------------
+constexpr int kPersistThreads = 320;  // warp 0: TMA producer | 1: MMA issuer | 2-9: epilogue
+constexpr int kPersistStages = 6;
+
+struct PersistSmem {
+  uint64_t full[kPersistStages];
+  uint64_t empty[kPersistStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmKernelArgs p) {
+  constexpr int STAGES = kPersistStages;
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + STAGES * kOperandStageBytes;
+  PersistSmem* sh = reinterpret_cast<PersistSmem*>(smem + 2 * STAGES * kOperandStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM;
+  const int num_tiles = ntn * ntm;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&sh->full[s], 1u); mbar_init(&sh->empty[s], 1u); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sh->acc_full[s], 1u); mbar_init(&sh->acc_empty[s], 8u); }
+    fence_barrier_init();
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(256u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          mbar_wait(&sh->empty[s], ((it / STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&sh->full[s], 2u * (uint32_t)kOperandStageBytes);
+          const int k0 = kb * BK;
+          const uint32_t da = smem_u32(smem_a + s * kOperandStageBytes), db = smem_u32(smem_b + s * kOperandStageBytes);
+          if (!A_MN) {
+            tma_load_2d(da, &tmap_a, &sh->full[s], k0, m0);
+          } else {
+            tma_load_2d(da, &tmap_a, &sh->full[s], m0, k0);
+            tma_load_2d(da + 8192, &tmap_a, &sh->full[s], m0 + 64, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(db, &tmap_b, &sh->full[s], k0, n0);
+          } else {
+            tma_load_2d(db, &tmap_b, &sh->full[s], n0, k0);
+            tma_load_2d(db + 8192, &tmap_b, &sh->full[s], n0 + 64, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t slot = tl & 1u;
+        mbar_wait(&sh->acc_empty[slot], ((tl >> 1) & 1u) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + slot * 128u;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          mbar_wait(&sh->full[s], (it / STAGES) & 1u);
+          tcgen05_fence_after();
+          const uint32_t a_base = smem_u32(smem_a + s * kOperandStageBytes);
+          const uint32_t b_base = smem_u32(smem_b + s * kOperandStageBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_desc(a_base + k * 2048, 8192, 1024) : umma_desc(a_base + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc(b_base + k * 2048, 8192, 1024) : umma_desc(b_base + k * 32, 16, 1024);
+            umma_bf16(tacc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&sh->empty[s]);
+        }
+        umma_commit(&sh->acc_full[slot]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;        // columns [64 half, 64 half + 64)
+    const uint32_t epi = p.epi;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN;
+      const uint32_t slot = tl & 1u;
+      mbar_wait(&sh->acc_full[slot], (tl >> 1) & 1u);
+      tcgen05_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 128u;
+#pragma unroll 1
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
+        if (n0 + c0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_x32(taddr + (uint32_t)c0, r);
+        tmem_wait_ld();
+        if (row_ok) epilogue_chunk(p, epi, m, n0 + c0, r);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->acc_empty[slot]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
   }
 }
 
@@ -343,6 +486,20 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernel
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, ka);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelArgs& ka, int num_tiles, cudaStream_t st) {
+  auto kern = umma_gemm_persist_kernel<A_MN, B_MN>;
+  const int smem = 2 * kPersistStages * kOperandStageBytes + (int)sizeof(PersistSmem) + 1024;
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) {
+    PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  kern<<<grid, kPersistThreads, smem, st>>>(ta, tb, ka);
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
 }
@@ -407,6 +564,13 @@ extern "C" int pmgt_gemm_bf16(const pmgt_gemm_args* a, void* stream) {
   dim3 grid((unsigned)((a->N + BN - 1) / BN), (unsigned)((a->M + BM - 1) / BM), (unsigned)split);
   PMGT_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "pmgt_gemm_bf16: grid too large (M tiles %u, split %u)", grid.y, grid.z);
   cudaStream_t st = (cudaStream_t)stream;
+  // dense operands, no split-K, more tiles than one wave of the two-CTA-per-SM kernel: the persistent kernel
+  if (!ga && !gb && split == 1 && !(epi & PMGT_EPI_ATOMIC) && (long long)grid.x * grid.y > 2ll * num_sms() && num_kb >= 4) {
+    const int tiles = (int)(grid.x * grid.y);
+    if (!a->a_mn && !a->b_mn) return launch_persist<false, false>(ta, tb, ka, tiles, st);
+    if (!a->a_mn && a->b_mn) return launch_persist<false, true>(ta, tb, ka, tiles, st);
+    if (a->a_mn && a->b_mn) return launch_persist<true, true>(ta, tb, ka, tiles, st);
+  }
   // 3 stages = 96 KiB of operand ring: TWO CTAs fit per SM, so one tile's prologue / epilogue overlaps the other's
   // main loop (with 4 stages a single resident CTA left the SM idle during every tile's head and tail)
   const bool deep = kb_per > 2;

@@ -759,6 +759,8 @@ int embed128_supported(const pmgt_embed_args* a);
 int embed128_fwd(const pmgt_embed_args* a, cudaStream_t st);
 int embed128_bwd(const pmgt_embed_args* a, cudaStream_t st);
 int ln_bwd_stream(const pmgt_lnbwd_args* a, cudaStream_t st);  // ln_bwd_stream.cu
+int res_ln_fwd_wide(const pmgt_resln_args* a, cudaStream_t st);  // res_ln_wide.cu (H a multiple of 256)
+int res_ln_bwd_wide(const pmgt_resln_args* a, cudaStream_t st);
 
 static int persistent_grid(long long work_warps, int warps_per_cta, int ctas_per_sm) {
   long long need = (work_warps + warps_per_cta - 1) / warps_per_cta;
@@ -824,6 +826,10 @@ int pmgt_res_ln_fwd(const pmgt_resln_args* a, void* stream) {
   PMGT_REQUIRE(a && a->o && a->res && a->ln_g && a->ln_b && a->y, "pmgt_res_ln_fwd: null argument");
   PMGT_REQUIRE(a->H % 4 == 0 && a->H >= 4 && a->H <= 1024, "pmgt_res_ln_fwd: H must be a multiple of 4 in [4,1024]");
   if (a->T == 0) return PMGT_OK;
+  {
+    const int r = res_ln_fwd_wide(a, (cudaStream_t)stream);
+    if (r != 0) return r < 0 ? r : PMGT_OK;
+  }
   const int grid = persistent_grid(a->T, kRowThreads / 32, 8);
   PMGT_DISPATCH_G(a->H, (res_ln_fwd_kernel<1><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)),
                   (res_ln_fwd_kernel<6><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(*a)),
@@ -837,6 +843,10 @@ int pmgt_res_ln_bwd(const pmgt_resln_args* a, void* stream) {
   PMGT_REQUIRE(a->H % 4 == 0 && a->H >= 4 && a->H <= 1024, "pmgt_res_ln_bwd: H must be a multiple of 4 in [4,1024]");
   PMGT_REQUIRE(a->dropout_p == 0.f || (a->d_o && a->d_o != a->dz), "pmgt_res_ln_bwd: dropout needs a separate d_o buffer");
   if (a->T == 0) return PMGT_OK;
+  {
+    const int r = res_ln_bwd_wide(a, (cudaStream_t)stream);
+    if (r != 0) return r < 0 ? r : PMGT_OK;
+  }
   const size_t smem = (size_t)(kRowThreads / 32) * 3 * a->H * sizeof(float);
   const int grid = persistent_grid(a->T, kRowThreads / 32, 4);
   if (a->H <= 128) {

@@ -235,7 +235,7 @@ def test_attention_dropout_mask_agrees_between_fwd_and_bwd_medium_L(L, dh):
         assert torch.allclose(dV, A[:, i_star, :], rtol=2e-2, atol=2e-3), (i_star, float((dV - A[:, i_star, :]).abs().max()))
 
 
-@pytest.mark.parametrize("T,H", [(50, 128), (33, 64), (20, 768), (9, 32)])
+@pytest.mark.parametrize("T,H", [(50, 128), (33, 64), (20, 768), (9, 32), (5001, 768), (3000, 256), (1300, 1024), (77, 512)])
 def test_res_ln_fwd_bwd(T, H):
     ops = _ops()
     o, res = _r(T, H), _r(T, H)
@@ -260,6 +260,37 @@ def test_res_ln_fwd_bwd(T, H):
     _close(dg, gg.grad, 5e-3, "d_g")
     _close(db, bb.grad, 5e-3, "d_b")
     _close(dbias, of.grad.sum(0), 1e-2, "d_bias")
+
+
+@pytest.mark.parametrize("H", [768, 256])
+def test_wide_res_ln_dropout_is_consistent_between_fwd_and_bwd(H):
+    """res_ln_wide.cu (H a multiple of 256): keep rate, the backward pass regenerating the forward mask, and the
+    same mask as the generic row-wise kernels would draw (one stream, common.cuh)."""
+    ops = _ops()
+    T, p = 3000, 0.25
+    o = torch.ones(T, H, device="cuda", dtype=BF16)
+    res = torch.zeros(T, H, device="cuda", dtype=BF16)
+    g, b = torch.ones(H, device="cuda"), torch.zeros(H, device="cuda")
+    y = torch.empty(T, H, device="cuda", dtype=BF16)
+    ops.res_ln_fwd(ops.resln_args(T, H, o, res, g, b, 1e-12, p, 1234, 7, y=y))
+    dropped = y.float() < 0
+    rate = float(dropped.float().mean())
+    assert abs(rate - p) < 0.01, rate
+    dy = torch.randn(T, H, device="cuda").to(BF16)
+    dz, d_o = torch.empty_like(y), torch.empty_like(y)
+    dbias = torch.zeros(H, device="cuda")
+    ops.res_ln_bwd(ops.resln_args(T, H, o, res, g, None, 1e-12, p, 1234, 7, dy=dy, dz=dz, d_o=d_o,
+                                  d_g=torch.zeros(H, device="cuda"), d_b=torch.zeros(H, device="cuda"), d_bias=dbias))
+    assert bool((d_o.float()[dropped] == 0).all())
+    kept = ~dropped
+    assert torch.allclose(d_o.float()[kept], (dz.float() / (1 - p))[kept], rtol=2e-2, atol=1e-3)
+    _close(dbias, d_o.float().sum(0), 2e-3, "d_bias = column sums of the stored d_o")
+    # the 4-columns-per-lane kernels (a sliced view breaks the 16-byte alignment the wide kernels ask for) draw the same mask
+    pad = torch.ones(T * H + 4, device="cuda", dtype=BF16)
+    o2 = pad[4:].view(T, H)
+    y2 = torch.empty(T * H + 4, device="cuda", dtype=BF16)[4:].view(T, H)
+    ops.res_ln_fwd(ops.resln_args(T, H, o2, res, g, b, 1e-12, p, 1234, 7, y=y2))
+    assert torch.equal(y2.float() < 0, dropped)
 
 
 def test_dropout_is_consistent_between_fwd_and_bwd():
