@@ -238,6 +238,11 @@ class ClockSampler:
 # kernel families of the encoder layers (SURVEY section 8(d) "K3": tensor-bound by definition, activations ideally on chip)
 K3_FAMILIES = ("lt_qkvc_fwd", "attn_core_fwd", "lt_res_ln_fwd", "lt_gelu_fwd", "ffn_fwd", "ffn_bwd", "ln_bwd", "lt_dxdw_gelu",
                "lt_dxdw", "attn_core_bwd", "lt_dx_qkvc", "dw_tile", "gather_rows", "scatter_rows")
+# widths the token-tile kernels do not cover (--encoder wide): the layers run on pmgt_gemm_bf16 + row-wise LayerNorm
+# (the few non-layer GEMMs of a step -- projected feature tables, NFR heads -- carry their own tags or are < 1 % here)
+K3_FAMILIES_WIDE = ("gemm_fwd", "gemm_dx", "gemm_dw", "res_ln_fwd", "res_ln_bwd", "attn_core_fwd", "attn_core_bwd", "colsum")
+# SURVEY section 8(d) "K2": the multimodal feature path (gather + per-modality projection, then the fusion kernel)
+K2_GATHER_FAMILIES = ("gemm_fwd_gather", "gemm_dw_gather")
 
 
 def k3_flops_per_step(cfg_over, batch, L):
@@ -344,7 +349,7 @@ def measure(a, workload, steps, warmup, profile, rank, local_rank, ws, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = contexts_per_step * steps / (float(t) / 1e3)
     res = {"value": value, "ms_per_step": ms / steps, "e2e_value": e2e_value, "launches": launches, "clocks": clk,
-           "loss_last": loss_host, "roofline": None, "k3": None, "profile": None}
+           "loss_last": loss_host, "roofline": None, "k3": None, "k2": None, "profile": None}
 
     # ---- per-kernel-family profile (CUDA events on the launching stream, inside real steps) -> roofline
     if profile:
@@ -389,7 +394,8 @@ def measure(a, workload, steps, warmup, profile, rank, local_rank, ws, dev):
                     "peak_source": peaks["source"], "share_of_step": d["share"], "launches_per_step": d["calls"] / n_prof,
                     "avg_launch_us": 1e3 * d["ms"] / d["calls"], "tensor_tflops": d["tflops"], "note": note}
             # SURVEY 8(d) classifies the encoder layers (K3) as tensor-bound: FLOP-based fraction of the whole K3 chain
-            k3_ms = sum(v["ms_per_step"] for k, v in prof.items() if k in K3_FAMILIES)
+            fams = K3_FAMILIES_WIDE if a.encoder == "wide" else K3_FAMILIES
+            k3_ms = sum(v["ms_per_step"] for k, v in prof.items() if k in fams)
             L = ENCODERS[a.encoder][0].get("max_ctx_neigh", 5) + 1
             k3_fl = k3_flops_per_step(ENCODERS[a.encoder][0], B, L)
             k3 = {"bound": "tensor", "flops_per_step": k3_fl, "ms_per_step": k3_ms,
@@ -397,6 +403,18 @@ def measure(a, workload, steps, warmup, profile, rank, local_rank, ws, dev):
                   "unit": "TFLOP/s", "frac": (k3_fl / (k3_ms * 1e-3) / 1e12 / peaks["bf16_tflops"]) if k3_ms > 0 else None,
                   "note": "encoder-layer kernels summed (SURVEY 8(d) K3, FLOP model 3 x (8LH^2+6L^2H+2LH^2+4LHI) per sequence "
                           "and layer); the chain is HBM/issue-bound per kernel, see roofline and DESIGN.md section 4"}
+            # K2 on graphs whose tables exceed L2: the gather-fused projection GEMMs, algorithmic bytes (every gathered
+            # row + the operands / outputs once) over the live-timed duration, against the measured copy bandwidth
+            k2 = None
+            if any(k in prof for k in K2_GATHER_FAMILIES):
+                k2 = {"bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s", "kernels": {}}
+                for k in K2_GATHER_FAMILIES:
+                    if k in prof:
+                        v = prof[k]
+                        k2["kernels"][k] = {"achieved": v["gbs"], "frac": v["gbs"] / peaks["hbm_gbs"],
+                                            "avg_launch_us": 1e3 * v["ms"] / v["calls"], "launches_per_step": v["calls"] / n_prof,
+                                            "traffic": load_traffic(workload, B).get(k)}
+            res["k2"] = k2
             res.update(roofline=roof, k3=k3,
                        profile={"per_kernel_family": prof, "steps_profiled": n_prof, "sum_ms_per_step": tot / n_prof,
                                 "ms_per_step_timed": ms / steps})
@@ -468,7 +486,7 @@ def ours(a):
             "e2e": {"value": main_res["e2e_value"], "unit": "contexts/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": 4,
                     "api": "pmgt_b200.trainer.PMGTTrainerModel.train_on_indices(pinned host index batch) + .last_loss() every step"},
             "gpu_launches": main_res["launches"], "clocks": main_res["clocks"], "roofline": main_res["roofline"],
-            "roofline_k3": main_res["k3"], "cpu_baseline": cpu, "gpu_baseline": gpu_eager, "loss_last": main_res["loss_last"],
+            "roofline_k3": main_res["k3"], "roofline_k2": main_res["k2"], "cpu_baseline": cpu, "gpu_baseline": gpu_eager, "loss_last": main_res["loss_last"],
             "config2_TG": second,
         }
         print(json.dumps(line), flush=True)

@@ -46,6 +46,26 @@ __global__ void k_tile(const uint4* __restrict__ tab, const int* __restrict__ id
   if (acc == 0x12345u) *sink = acc;
 }
 
+// random 32-byte sectors out of a table much larger than L2: the ceiling of a dependent-gather kernel such as the
+// neighbour sampler (every access = one sector); ILP independent loads per thread, ids from a cheap hash
+template <int ILP>
+__global__ void k_sector(const uint2* __restrict__ tab, size_t n_sectors, int iters, unsigned* sink) {
+  unsigned x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+  unsigned acc = 0;
+  for (int it = 0; it < iters; ++it) {
+    uint2 v[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+      x = x * 1664525u + 1013904223u;
+      unsigned h = x ^ (x >> 15); h *= 0x2c1b3c6du; h ^= h >> 12;
+      v[i] = __ldg(tab + ((size_t)h % n_sectors) * 4);   // first 8 bytes of sector h
+    }
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc ^= v[i].x ^ v[i].y;
+  }
+  if (acc == 0x12345u) *sink = acc;
+}
+
 int main(int argc, char** argv) {
   const int N = 1000002, T = 294912;
   const int rowb = argc > 1 ? atoi(argv[1]) : 3072;
@@ -71,5 +91,18 @@ int main(int argc, char** argv) {
   run("tile walk 256B/step 8 CTA/SM", [&] { k_tile<16><<<148 * 8, 128>>>(tab, ids, T, row16, sink); });
   run("tile walk 512B/step 2 CTA/SM", [&] { k_tile<32><<<148 * 2, 128>>>(tab, ids, T, row16, sink); });
   run("tile walk 512B/step 4 CTA/SM", [&] { k_tile<32><<<148 * 4, 128>>>(tab, ids, T, row16, sink); });
+  if (argc > 2) {   // sector probe: a 1 GB window of the table
+    const size_t n_sectors = (size_t)1 << 25;
+    for (int cps : {8, 16, 32}) {
+      const int iters = 64, threads = 128, ilp = 8;
+      const double n_acc = (double)148 * cps * threads * iters * ilp;
+      for (int i = 0; i < 2; ++i) k_sector<8><<<148 * cps, threads>>>((const uint2*)tab, n_sectors, iters, sink);
+      cudaEventRecord(e0); for (int i = 0; i < 5; ++i) k_sector<8><<<148 * cps, threads>>>((const uint2*)tab, n_sectors, iters, sink);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+      printf("random 32B sectors, %2d CTA x 128 thr / SM, ILP 8: %6.1f G sectors/s = %7.1f GB/s of 32-byte sectors (%s)\n", cps,
+             n_acc / ms / 1e6, n_acc * 32 / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+    }
+  }
   return 0;
 }
