@@ -16,6 +16,10 @@
 //                              -> dV, dK and the column half of dC, which lands in the same accumulators.
 #include "common.cuh"
 
+#ifndef PMGT_REG_BWD_REGS
+#define PMGT_REG_BWD_REGS 216   // register budget per thread the backward kernel's launch bounds aim at
+#endif
+
 namespace pmgt {
 
 namespace {
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(32 * MT) attn_reg_fwd_kernel(const pmgt_attn_a
 // backward
 // ---------------------------------------------------------------------------------------------------
 template <int DH, int MT>
-__global__ void __launch_bounds__(32 * MT, 65536 / (32 * MT * 216)) attn_reg_bwd_kernel(const pmgt_attn_args a) {
+__global__ void __launch_bounds__(32 * MT, 65536 / (32 * MT * PMGT_REG_BWD_REGS)) attn_reg_bwd_kernel(const pmgt_attn_args a) {
   using Cf = RegCfg<DH, MT>;
   extern __shared__ __align__(16) unsigned char smem[];
   uint16_t* sQ = reinterpret_cast<uint16_t*>(smem);

@@ -110,9 +110,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelArgs& p, uint32_t
       for (int j = 0; j < 8; ++j) v[j] += x[j];
     }
     if (epi & PMGT_EPI_ATOMIC) {
-      float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
+      float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;   // 16-byte aligned: ldo % 4 == 0, n % 8 == 0
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
     } else if (epi & PMGT_EPI_OUT_F32) {
       float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
       *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);

@@ -193,6 +193,9 @@ def linear_dw(dy, x, dw_f32, *, rows=None, src_rows=0, x_cols=None, tag=None):
     # two CTAs are resident per SM: the split count keeps tiles * split WITHIN one wave of 2 * SMs CTAs (rounding up put 300
     # CTAs on 296 slots: a second, nearly empty wave doubled the kernel's duration -- ncu grid 300, round 2)
     split = max(1, min(num_kb, (2 * _num_sms(dy.device)) // tiles))
+    # short reductions (the NFR heads: a few thousand rows): every split flushes a whole fp32 tile through the L2 atomic
+    # units, which then costs more than the products -- keep at least 8 k-blocks (512 rows) per CTA
+    split = max(1, min(split, num_kb // 8))
     gemm(dy, x, dw_f32, M=N, N=K, K=T, lda=dy.stride(0), ldb=x.stride(0), ldo=dw_f32.stride(0), a_mn=True, b_mn=True,
          b_rows=rows, b_src_rows=src_rows, epi=EPI_ATOMIC, split_k=split,
          tag=tag or ("gemm_dw_gather" if rows is not None else "gemm_dw"))

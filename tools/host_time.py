@@ -12,7 +12,9 @@ sys.path.insert(0, os.getcwd())
 from pmgt_b200 import trainer
 
 dev = torch.device("cuda", 0)
-args = trainer.make_args(synthetic="TG", train_batch_size=4096, seed=0)
+WL = sys.argv[1] if len(sys.argv) > 1 else "TG"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+args = trainer.make_args(synthetic=WL, train_batch_size=B, seed=0)
 args.device = dev
 trainer.set_seed(0)
 args.graph, args.feat_init_emb = trainer._load_graph_and_features(args)
@@ -21,7 +23,7 @@ trainer.init_model(args)
 tm = trainer.PMGTTrainerModel(args)
 ds = args.train_dataset
 N = 40
-idx = [torch.from_numpy(np.resize(trainer.epoch_permutation(len(ds), 0, s), 4096).astype(np.int64)).pin_memory() for s in range(N + 1)]
+idx = [torch.from_numpy(np.resize(trainer.epoch_permutation(len(ds), 0, s), B).astype(np.int64)).pin_memory() for s in range(N + 1)]
 
 
 def loop(lo, hi):

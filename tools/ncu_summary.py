@@ -99,7 +99,7 @@ FAMILY = [  # kernel-name pattern -> bench.py profile family (for profiles/ncu_t
     (r"linear_tile_kernel<1, 1, 1, 3", "lt_dx"), (r"linear_tile_kernel<1, 1, 1, 4", "lt_dx_gelu"),
     (r"dw_tile_kernel", "dw_tile"), (r"ln_bwd_stream_kernel<[12]", "ln_bwd"), (r"attn_mma_fwd", "attn_core_fwd"),
     (r"attn_mma_bwd", "attn_core_bwd"), (r"sample_contexts", "sample_contexts"), (r"embed_fwd128", "embed_fuse_fwd"),
-    (r"embed_bwd128", "embed_fuse_bwd"),
+    (r"embed_bwd128", "embed_fuse_bwd"), (r"gather_proj_fwd", "gemm_fwd_gather"), (r"gather_proj_dw", "gemm_dw_gather"),
 ]
 
 
@@ -110,11 +110,16 @@ def rawcsv(src, dst, traffic_json=None, title=""):
     hdr, units, data = rows[0], rows[1], rows[2:]
     H = {h: i for i, h in enumerate(hdr)}
 
+    SCALE = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "Tbyte": 1e6,        # -> MB
+             "ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3, "s": 1e6, "second": 1e6}  # -> us
+
     def g(r, k):
+        """value of metric k; bytes are returned in MB and durations in us whatever unit ncu chose for the column"""
         try:
-            return float(r[H[k]].replace(",", ""))
+            v = float(r[H[k]].replace(",", ""))
         except Exception:
             return float("nan")
+        return v * SCALE.get(units[H[k]], 1.0)
 
     keys = [k for k in KEYS + ["lts__t_sector_hit_rate.pct"] if k in H]
     fam_traffic = {}
