@@ -20,6 +20,8 @@
 //   MN-major operand : 2 slabs of 64 rows (row = K index, 64 M/N elements each).
 //                      UMMA desc: SWIZZLE_128B, LBO = 8192 B (next 64 M/N),
 //                      SBO = 1024 B (next 8 K rows); K advance = +2048 B.
+#include <stdlib.h>
+
 #include "umma.cuh"
 
 namespace pmgt {
@@ -43,6 +45,7 @@ struct GemmKernelArgs {
   float alpha;
   uint32_t epi;
   int kb_per_split;  // k-blocks per blockIdx.z
+  int vec32;         // bf16 out (and GELU aux) rows are 32-byte aligned: 32-byte epilogue stores
 };
 
 struct GemmSmem {
@@ -70,58 +73,90 @@ __device__ __forceinline__ void gather_slab(uint32_t slab, int t, const uint16_t
   }
 }
 
-// Epilogue of 32 accumulator columns [n_base, n_base + 32) of output row m (one row per thread)
+__device__ __forceinline__ void st_global_256(void* ptr, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+               "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+
+// Epilogue of 8 accumulator columns [n, n + 8) of output row m; returns the bf16 result (the caller stores it) unless
+// the output is fp32 / atomic, which is written here
+__device__ __forceinline__ uint4 epilogue_group(const GemmKernelArgs& p, uint32_t epi, int m, int n, const uint32_t* r, uint4& pre_out) {
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+  if (epi & PMGT_EPI_BIAS) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (epi & PMGT_EPI_GELU) {
+    pre_out.x = pack_bf16x2(v[0], v[1]); pre_out.y = pack_bf16x2(v[2], v[3]);
+    pre_out.z = pack_bf16x2(v[4], v[5]); pre_out.w = pack_bf16x2(v[6], v[7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (epi & PMGT_EPI_GELU_BWD) {
+    const uint4 pre = *reinterpret_cast<const uint4*>(p.aux + (long long)m * p.ld_aux + n);
+    float x[8];
+    unpack_bf16x2(pre.x, x[0], x[1]); unpack_bf16x2(pre.y, x[2], x[3]);
+    unpack_bf16x2(pre.z, x[4], x[5]); unpack_bf16x2(pre.w, x[6], x[7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(x[j]);
+  }
+  if (epi & PMGT_EPI_ADDEND) {
+    const uint4 ad = *reinterpret_cast<const uint4*>(p.addend + (long long)m * p.ld_addend + n);
+    float x[8];
+    unpack_bf16x2(ad.x, x[0], x[1]); unpack_bf16x2(ad.y, x[2], x[3]);
+    unpack_bf16x2(ad.z, x[4], x[5]); unpack_bf16x2(ad.w, x[6], x[7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += x[j];
+  }
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (epi & PMGT_EPI_ATOMIC) {
+    float* d = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;   // 16-byte aligned: ldo % 4 == 0, n % 8 == 0
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+  } else if (epi & PMGT_EPI_OUT_F32) {
+    float* d = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
+    *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  }
+  return o;
+}
+
+// Epilogue of 32 accumulator columns [n_base, n_base + 32) of output row m (one row per thread).  bf16 results (and
+// the GELU pre-activations) leave as 32-byte stores -- one full sector per thread and instruction -- when the rows
+// are 32-byte aligned (p.vec32), else as 16-byte stores.
 __device__ __forceinline__ void epilogue_chunk(const GemmKernelArgs& p, uint32_t epi, int m, int n_base, const uint32_t (&r)[32]) {
+  const bool bf16_out = !(epi & (PMGT_EPI_ATOMIC | PMGT_EPI_OUT_F32));
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int n = n_base + g * 8;
+  for (int h = 0; h < 2; ++h) {
+    const int n = n_base + h * 16;
     if (n >= p.N) break;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
-    if (epi & PMGT_EPI_BIAS) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    }
+    const bool two = n + 8 < p.N;
+    uint4 pre0, pre1, o0, o1 = make_uint4(0u, 0u, 0u, 0u);
+    o0 = epilogue_group(p, epi, m, n, r + h * 16, pre0);
+    if (two) o1 = epilogue_group(p, epi, m, n + 8, r + h * 16 + 8, pre1);
     if (epi & PMGT_EPI_GELU) {
-      uint4 pre;
-      pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
-      pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(p.aux + (long long)m * p.ld_aux + n) = pre;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+      uint16_t* a = p.aux + (long long)m * p.ld_aux + n;
+      if (two && p.vec32) st_global_256(a, pre0, pre1);
+      else {
+        *reinterpret_cast<uint4*>(a) = pre0;
+        if (two) *reinterpret_cast<uint4*>(a + 8) = pre1;
+      }
     }
-    if (epi & PMGT_EPI_GELU_BWD) {
-      const uint4 pre = *reinterpret_cast<const uint4*>(p.aux + (long long)m * p.ld_aux + n);
-      float x[8];
-      unpack_bf16x2(pre.x, x[0], x[1]); unpack_bf16x2(pre.y, x[2], x[3]);
-      unpack_bf16x2(pre.z, x[4], x[5]); unpack_bf16x2(pre.w, x[6], x[7]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(x[j]);
-    }
-    if (epi & PMGT_EPI_ADDEND) {
-      const uint4 ad = *reinterpret_cast<const uint4*>(p.addend + (long long)m * p.ld_addend + n);
-      float x[8];
-      unpack_bf16x2(ad.x, x[0], x[1]); unpack_bf16x2(ad.y, x[2], x[3]);
-      unpack_bf16x2(ad.z, x[4], x[5]); unpack_bf16x2(ad.w, x[6], x[7]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += x[j];
-    }
-    if (epi & PMGT_EPI_ATOMIC) {
-      float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;   // 16-byte aligned: ldo % 4 == 0, n % 8 == 0
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
-    } else if (epi & PMGT_EPI_OUT_F32) {
-      float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + n;
-      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } else {
-      uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (long long)m * p.ldo + n) = o;
+    if (bf16_out) {
+      uint16_t* d = reinterpret_cast<uint16_t*>(p.out) + (long long)m * p.ldo + n;
+      if (two && p.vec32) st_global_256(d, o0, o1);
+      else {
+        *reinterpret_cast<uint4*>(d) = o0;
+        if (two) *reinterpret_cast<uint4*>(d + 8) = o1;
+      }
     }
   }
 }
@@ -324,18 +359,20 @@ struct PersistSmem {
   uint32_t tmem_base;
 };
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN_>  // BN_ = 128 or 256 output columns per tile
 __global__ void __launch_bounds__(kPersistThreads, 1)
 umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmKernelArgs p) {
-  constexpr int STAGES = kPersistStages;
+  constexpr int STAGES = BN_ == 128 ? kPersistStages : 4;
+  constexpr int kAStage = kOperandStageBytes;         // 128 rows x 64 k
+  constexpr int kBStage = BN_ * BK * 2;               // BN_ rows x 64 k (K-major) or BN_ / 64 slabs of 64 k x 64 n
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_a = smem;
-  unsigned char* smem_b = smem + STAGES * kOperandStageBytes;
-  PersistSmem* sh = reinterpret_cast<PersistSmem*>(smem + 2 * STAGES * kOperandStageBytes);
+  unsigned char* smem_b = smem + STAGES * kAStage;
+  PersistSmem* sh = reinterpret_cast<PersistSmem*>(smem + STAGES * (kAStage + kBStage));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntn = (p.N + BN - 1) / BN, ntm = (p.M + BM - 1) / BM;
+  const int ntn = (p.N + BN_ - 1) / BN_, ntm = (p.M + BM - 1) / BM;
   const int num_tiles = ntn * ntm;
   const int num_kb = (p.K + BK - 1) / BK;
 
@@ -347,7 +384,7 @@ umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     prefetch_tmap(&tmap_b);
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(256u));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"((uint32_t)(2 * BN_)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tcgen05_fence_before();
@@ -359,13 +396,13 @@ umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN;
+        const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN_;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES;
           mbar_wait(&sh->empty[s], ((it / STAGES) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&sh->full[s], 2u * (uint32_t)kOperandStageBytes);
+          mbar_arrive_expect_tx(&sh->full[s], (uint32_t)(kAStage + kBStage));
           const int k0 = kb * BK;
-          const uint32_t da = smem_u32(smem_a + s * kOperandStageBytes), db = smem_u32(smem_b + s * kOperandStageBytes);
+          const uint32_t da = smem_u32(smem_a + s * kAStage), db = smem_u32(smem_b + s * kBStage);
           if (!A_MN) {
             tma_load_2d(da, &tmap_a, &sh->full[s], k0, m0);
           } else {
@@ -373,10 +410,11 @@ umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             tma_load_2d(da + 8192, &tmap_a, &sh->full[s], m0 + 64, k0);
           }
           if (!B_MN) {
-            tma_load_2d(db, &tmap_b, &sh->full[s], k0, n0);
+#pragma unroll
+            for (int j = 0; j < BN_ / 128; ++j) tma_load_2d(db + j * 16384, &tmap_b, &sh->full[s], k0, n0 + 128 * j);
           } else {
-            tma_load_2d(db, &tmap_b, &sh->full[s], n0, k0);
-            tma_load_2d(db + 8192, &tmap_b, &sh->full[s], n0 + 64, k0);
+#pragma unroll
+            for (int j = 0; j < BN_ / 64; ++j) tma_load_2d(db + j * 8192, &tmap_b, &sh->full[s], n0 + 64 * j, k0);
           }
         }
       }
@@ -384,19 +422,19 @@ umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t it = 0, tl = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
         const uint32_t slot = tl & 1u;
         mbar_wait(&sh->acc_empty[slot], ((tl >> 1) & 1u) ^ 1u);
         tcgen05_fence_after();
-        const uint32_t tacc = tmem_base + slot * 128u;
+        const uint32_t tacc = tmem_base + slot * (uint32_t)BN_;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES;
           mbar_wait(&sh->full[s], (it / STAGES) & 1u);
           tcgen05_fence_after();
-          const uint32_t a_base = smem_u32(smem_a + s * kOperandStageBytes);
-          const uint32_t b_base = smem_u32(smem_b + s * kOperandStageBytes);
+          const uint32_t a_base = smem_u32(smem_a + s * kAStage);
+          const uint32_t b_base = smem_u32(smem_b + s * kBStage);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = A_MN ? umma_desc(a_base + k * 2048, 8192, 1024) : umma_desc(a_base + k * 32, 16, 1024);
@@ -410,19 +448,21 @@ umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else {
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;        // columns [64 half, 64 half + 64)
+    const int half = (warp - 2) >> 2;        // columns [BN_/2 half, BN_/2 half + BN_/2)
     const uint32_t epi = p.epi;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-      const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN;
+      const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN_;
       const uint32_t slot = tl & 1u;
       mbar_wait(&sh->acc_full[slot], (tl >> 1) & 1u);
       tcgen05_fence_after();
       const int m = m0 + quarter * 32 + lane;
       const bool row_ok = m < p.M;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 128u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * (uint32_t)BN_;
+      // (loading the next 32 columns from tensor memory while the current ones are converted was measured slower:
+      // 644 vs 568 us on the [101376, 768] x [768, 3072] forward -- the epilogue is bound by its row-wise stores)
 #pragma unroll 1
-      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
+      for (int c0 = half * (BN_ / 2); c0 < (half + 1) * (BN_ / 2); c0 += 32) {
         if (n0 + c0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_x32(taddr + (uint32_t)c0, r);
@@ -439,7 +479,7 @@ umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN_)));
   }
 }
 
@@ -490,15 +530,27 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernel
   return PMGT_OK;
 }
 
-template <bool A_MN, bool B_MN>
-static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelArgs& ka, int num_tiles, cudaStream_t st) {
-  auto kern = umma_gemm_persist_kernel<A_MN, B_MN>;
-  const int smem = 2 * kPersistStages * kOperandStageBytes + (int)sizeof(PersistSmem) + 1024;
+// PMGT_GEMM_NARROW=1 keeps the persistent kernel on 128-column tiles (measurement switch)
+static bool persist_narrow() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PMGT_GEMM_NARROW");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
+template <bool A_MN, bool B_MN, int BN_>
+static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelArgs& ka, cudaStream_t st) {
+  auto kern = umma_gemm_persist_kernel<A_MN, B_MN, BN_>;
+  constexpr int stages = BN_ == 128 ? kPersistStages : 4;
+  const int smem = stages * (kOperandStageBytes + BN_ * BK * 2) + (int)sizeof(PersistSmem) + 1024;
   static unsigned long long configured = 0;
   if (first_use_on_device(configured)) {
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  const long long tiles = (long long)((ka.N + BN_ - 1) / BN_) * ((ka.M + BM - 1) / BM);
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   kern<<<grid, kPersistThreads, smem, st>>>(ta, tb, ka);
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
@@ -561,15 +613,19 @@ extern "C" int pmgt_gemm_bf16(const pmgt_gemm_args* a, void* stream) {
   ka.out = a->out; ka.ldo = a->ldo; ka.bias = a->bias;
   ka.addend = a->addend; ka.ld_addend = a->ld_addend; ka.aux = a->aux; ka.ld_aux = a->ld_aux;
   ka.alpha = a->alpha; ka.epi = epi; ka.kb_per_split = kb_per;
+  ka.vec32 = (((uintptr_t)a->out & 31) == 0 && a->ldo % 16 == 0 &&
+              (!(epi & PMGT_EPI_GELU) || (((uintptr_t)a->aux & 31) == 0 && a->ld_aux % 16 == 0))) ? 1 : 0;
   dim3 grid((unsigned)((a->N + BN - 1) / BN), (unsigned)((a->M + BM - 1) / BM), (unsigned)split);
   PMGT_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "pmgt_gemm_bf16: grid too large (M tiles %u, split %u)", grid.y, grid.z);
   cudaStream_t st = (cudaStream_t)stream;
-  // dense operands, no split-K, more tiles than one wave of the two-CTA-per-SM kernel: the persistent kernel
+  // dense operands, no split-K, more tiles than one wave of the two-CTA-per-SM kernel: the persistent kernel; with 256
+  // output columns per tile when N allows (85 instead of 64 FLOP per operand byte through L2 -> SM)
   if (!ga && !gb && split == 1 && !(epi & PMGT_EPI_ATOMIC) && (long long)grid.x * grid.y > 2ll * num_sms() && num_kb >= 4) {
-    const int tiles = (int)(grid.x * grid.y);
-    if (!a->a_mn && !a->b_mn) return launch_persist<false, false>(ta, tb, ka, tiles, st);
-    if (!a->a_mn && a->b_mn) return launch_persist<false, true>(ta, tb, ka, tiles, st);
-    if (a->a_mn && a->b_mn) return launch_persist<true, true>(ta, tb, ka, tiles, st);
+    // (the GELU epilogues are bound by their own instruction issue, and measured slower on the wide tiles: 1353 vs 919 us)
+    const bool wide_n = a->N >= 512 && (!(epi & (PMGT_EPI_GELU | PMGT_EPI_GELU_BWD)) || getenv("PMGT_GEMM_WIDE_GELU")) && !persist_narrow();
+    if (!a->a_mn && !a->b_mn) return wide_n ? launch_persist<false, false, 256>(ta, tb, ka, st) : launch_persist<false, false, 128>(ta, tb, ka, st);
+    if (!a->a_mn && a->b_mn) return wide_n ? launch_persist<false, true, 256>(ta, tb, ka, st) : launch_persist<false, true, 128>(ta, tb, ka, st);
+    if (a->a_mn && a->b_mn) return wide_n ? launch_persist<true, true, 256>(ta, tb, ka, st) : launch_persist<true, true, 128>(ta, tb, ka, st);
   }
   // 3 stages = 96 KiB of operand ring: TWO CTAs fit per SM, so one tile's prologue / epilogue overlaps the other's
   // main loop (with 4 stages a single resident CTA left the SM idle during every tile's head and tail)

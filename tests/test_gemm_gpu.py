@@ -143,6 +143,37 @@ def test_gather_proj_kernels_match_torch(T, K, nrows):
         ops.GATHER_PROJ = True
     assert (out2.float() - out.float()).abs().max() < 2e-2
 
+@pytest.mark.parametrize("M,N,K", [(40037, 768, 256), (40000, 384, 320), (38000, 640, 256), (20001, 3072, 192)])
+def test_persistent_gemm_kernels_match_torch(M, N, K):
+    """Large dense GEMMs take the persistent kernel (umma_gemm_persist_kernel: more tiles than one wave): 128-column
+    tiles for N < 512, 256-column tiles otherwise, ragged last row tile, a last column tile that is half out of range
+    (N = 640), every epilogue of the Linear forward / dX paths."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = torch.randn(M, K, device="cuda", generator=g).to(BF16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(BF16)
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=BF16)
+    ops.linear_fwd(x, w, b, out)
+    sl = torch.cat([torch.arange(0, 300, device="cuda"), torch.arange(M - 300, M, device="cuda"),
+                    torch.randint(0, M, (400,), device="cuda", generator=g)])
+    ref = x[sl].float() @ w.float().t() + b
+    _close(out[sl], ref, 1e-2)
+    assert torch.isfinite(out.float()).all()
+    aux = torch.empty(M, N, device="cuda", dtype=BF16)
+    ops.linear_fwd(x, w, b, out, gelu_aux=aux)
+    _close(aux[sl], ref, 1e-2)
+    _close(out[sl], torch.nn.functional.gelu(ref), 1e-2)
+    # dX = dY W (+ addend) (* gelu'(aux)): B operand MN-major
+    dy = torch.randn(M, N, device="cuda", generator=g).to(BF16)
+    add = torch.randn(M, K, device="cuda", generator=g).to(BF16)
+    dx = torch.full((M, K), float("nan"), device="cuda", dtype=BF16)
+    if K >= 512 or M * ((K + 127) // 128) // 128 > 2 * 148:
+        ops.linear_dx(dy, w, dx, addend=add)
+        _close(dx[sl], dy[sl].float() @ w.float() + add[sl].float(), 1e-2)
+        assert torch.isfinite(dx.float()).all()
+
+
 def test_gemm_rejects_bad_arguments():
     from pmgt_b200 import _lib
     ops = _ops()
