@@ -233,7 +233,7 @@ class PMGTTrainerModel:
         """
         dev = self.args.device
         if self._side is None:
-            self._side = torch.cuda.Stream(device=dev, priority=-1)
+            self._side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("PMGT_SIDE_PRIORITY", "-1")))
         # No wait on the main stream (that would serialise us behind the very step we want to overlap): host indices
         # are copied on the side stream; device-resident indices must already be complete.
         with torch.cuda.stream(self._side):
