@@ -66,6 +66,43 @@ __global__ void k_sector(const uint2* __restrict__ tab, size_t n_sectors, int it
   if (acc == 0x12345u) *sink = acc;
 }
 
+// row-visit probe for the sampler's data layout: every "visit" reads three 32-byte sectors that depend on each other
+// (row pointer -> guide entry -> (cdf, id) pair).  SPLIT: the three sectors lie in three different 256 MB arrays (the
+// CSR layout: indptr | guide | ec).  RECORD: all three lie inside one 512-byte record of a single array.
+template <bool RECORD>
+__global__ void k_visit(const uint2* __restrict__ tab, int iters, unsigned* sink) {
+  const size_t region = (size_t)1 << 23;   // sectors per 256 MB region
+  unsigned x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 777u;
+  unsigned acc = 0;
+  for (int it = 0; it < iters; ++it) {
+    uint2 v[4];
+    size_t s0[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // four independent visits in flight per thread
+      x = x * 1664525u + 1013904223u;
+      unsigned h = x ^ (x >> 15); h *= 0x2c1b3c6du; h ^= h >> 12;
+      s0[i] = RECORD ? ((size_t)h % (region * 3 / 16)) * 16 : (size_t)h % region;   // record = 16 sectors
+      v[i] = __ldg(tab + s0[i] * 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // dependent second access
+      const unsigned d = (v[i].x ^ s0[i]) & 7u;
+      const size_t s1 = RECORD ? s0[i] + 1 + d : region + (s0[i] * 2654435761ull + d) % region;
+      v[i] = __ldg(tab + s1 * 4);
+      s0[i] = s1;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // dependent third access
+      const unsigned d = (v[i].y ^ s0[i]) & 3u;
+      const size_t s2 = RECORD ? (s0[i] & ~(size_t)15) + 9 + d : 2 * region + (s0[i] * 40503ull + d) % region;
+      v[i] = __ldg(tab + s2 * 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc ^= v[i].x ^ v[i].y;
+  }
+  if (acc == 0x12345u) *sink = acc;
+}
+
 int main(int argc, char** argv) {
   const int N = 1000002, T = 294912;
   const int rowb = argc > 1 ? atoi(argv[1]) : 3072;
@@ -91,6 +128,19 @@ int main(int argc, char** argv) {
   run("tile walk 256B/step 8 CTA/SM", [&] { k_tile<16><<<148 * 8, 128>>>(tab, ids, T, row16, sink); });
   run("tile walk 512B/step 2 CTA/SM", [&] { k_tile<32><<<148 * 2, 128>>>(tab, ids, T, row16, sink); });
   run("tile walk 512B/step 4 CTA/SM", [&] { k_tile<32><<<148 * 4, 128>>>(tab, ids, T, row16, sink); });
+  if (argc > 2) {   // row-visit probe (768 MB window)
+    for (int rec = 0; rec < 2; ++rec) for (int cps : {8, 16}) {
+      const int iters = 64, threads = 128;
+      const double visits = (double)148 * cps * threads * iters * 4;
+      auto go = [&] { if (rec) k_visit<true><<<148 * cps, threads>>>((const uint2*)tab, iters, sink); else k_visit<false><<<148 * cps, threads>>>((const uint2*)tab, iters, sink); };
+      go(); go();
+      cudaEventRecord(e0); for (int i = 0; i < 5; ++i) go();
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+      printf("row visits of 3 dependent sectors, %s layout, %2d CTA x 128 thr / SM: %6.1f G visits/s (%s)\n", rec ? "RECORD" : "SPLIT ", cps,
+             visits / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+    }
+  }
   if (argc > 2) {   // sector probe: a 1 GB window of the table
     const size_t n_sectors = (size_t)1 << 25;
     for (int cps : {8, 16, 32}) {
