@@ -39,7 +39,7 @@ typedef enum pmgt_status {
 } pmgt_status;
 
 /* ABI version of this header; bumped on any signature change. */
-#define PMGT_B200_ABI_VERSION 10
+#define PMGT_B200_ABI_VERSION 11
 int pmgt_abi_version(void);
 const char* pmgt_last_error(void);
 
@@ -507,6 +507,9 @@ int pmgt_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t*
 int pmgt_cast_f32_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);
 /* sum of squares of a flat fp32 buffer accumulated into out[0] (clip_grad_norm_) */
 int pmgt_sumsq_f32(const float* x, int64_t n, float* out, void* stream);
+/* torch.nn.utils.clip_grad_norm_ (pmgt/base_trainer.py:314 gradient_clip_val) folded with the gradient scale:
+ * out[0] = scale * min(1, max_norm / (sqrt(sumsq[0]) * scale + 1e-6)); sumsq[0] is reset to 0 for the next step */
+int pmgt_clip_coef(float* sumsq, float scale, float max_norm, float* out, void* stream);
 /* out[r][:] = src[idx[r]][:]   (bf16 rows, D elements, D % 8 == 0) */
 int pmgt_gather_rows_bf16(const uint16_t* src, int64_t ld_src, const int64_t* idx, int64_t n_rows,
                           int64_t D, uint16_t* out, int64_t ld_out, void* stream);

@@ -700,6 +700,14 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
   }
 }
 
+// clip_grad_norm_ coefficient folded with the gradient scale: out = scale * min(1, max_norm / (sqrt(sumsq) * scale + 1e-6));
+// sumsq is reset for the next step (one launch instead of seven tiny eager kernels between backward and AdamW)
+__global__ void clip_coef_kernel(float* __restrict__ sumsq, float scale, float max_norm, float* __restrict__ out) {
+  const float norm = sqrtf(sumsq[0]) * scale;
+  out[0] = scale * fminf(1.f, max_norm / (norm + 1e-6f));
+  sumsq[0] = 0.f;
+}
+
 __global__ void __launch_bounds__(256) gather_rows_kernel(const uint16_t* __restrict__ src, long long ld_src,
                                                           const long long* __restrict__ idx, long long n_rows, int D,
                                                           uint16_t* __restrict__ out, long long ld_out) {
@@ -915,6 +923,13 @@ int pmgt_cast_f32_bf16(const float* src, uint16_t* dst, int64_t n, void* stream)
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+int pmgt_clip_coef(float* sumsq, float scale, float max_norm, float* out, void* stream) {
+  PMGT_REQUIRE(sumsq && out, "pmgt_clip_coef: null argument");
+  clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, scale, max_norm, out);
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
 }

@@ -232,6 +232,29 @@ class PMGT(PMGTPretrainedModel):
             return masked_input_ids, mask, target_idx, mask.nonzero(as_tuple=False)
         return masked_input_ids, mask, target_idx
 
+    def prepare_inputs(self, target_node_inputs, pair_node_inputs, num_pairs, masked_inputs) -> Dict[str, torch.Tensor]:
+        """Everything ``forward`` derives from the batch alone (training with pairs): the concatenated
+        [targets | pairs | masked targets] ids / masks, the pair offsets and the compact row numbers of the masked
+        positions.  ``forward`` computes it itself when not handed in; the trainer's prefetch builds it on the side
+        stream as the fifth element of ``masked_inputs``."""
+        t_ids, t_mask = target_node_inputs["node_ids"], target_node_inputs["attention_mask"]
+        p_ids, p_mask = pair_node_inputs["node_ids"], pair_node_inputs["attention_mask"]
+        B, L = t_ids.shape
+        SP = p_ids.shape[0]
+        dev = t_ids.device
+        m_ids, m_mask = masked_inputs[0], masked_inputs[1]
+        m_pos = masked_inputs[3] if len(masked_inputs) > 3 else m_mask.nonzero(as_tuple=False)  # (Mm, 2): row, position-1
+        pair_off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(num_pairs.to(dev), 0, out=pair_off[1:])
+        return {
+            "ids_all": torch.cat([t_ids, p_ids, m_ids], dim=0).reshape(-1),
+            "mask_all": torch.cat([t_mask, p_mask, t_mask], dim=0),
+            "pair_off": pair_off,
+            # compact row numbers of the masked positions (inside the masked-target block of the encoder's output)
+            "nfr_rows": B * L + SP + m_pos[:, 0] * L + m_pos[:, 1] + 1,
+            "target_ids": masked_inputs[2].contiguous(),
+        }
+
     # ------------------------------------------------------------------
     def forward(
         self,
@@ -267,30 +290,29 @@ class PMGT(PMGTPretrainedModel):
         else:
             arena = GradArena(fp)
 
-        ids = [t_ids]
-        masks = [t_mask]
         SP = 0
         nfr_on = False
+        prep = None
         if pair_node_inputs is not None:
-            p_ids = pair_node_inputs["node_ids"]
-            SP = p_ids.shape[0]
-            ids.append(p_ids)
-            masks.append(pair_node_inputs["attention_mask"])
+            SP = pair_node_inputs["node_ids"].shape[0]
             if self.training:
                 nfr_on = True
                 if masked_inputs is None:
                     masked_inputs = self.mask_nodes(t_ids)
-                m_ids, m_mask, target_idx = masked_inputs[:3]
-                ids.append(m_ids)
-                masks.append(t_mask)
-                # data-dependent shapes are resolved HERE, before the encoder is enqueued: nonzero() synchronises
-                # the stream, and a sync after the encoder launch would drain the whole launch pipeline
-                m_pos = masked_inputs[3] if len(masked_inputs) > 3 else m_mask.nonzero(as_tuple=False)  # (Mm, 2): row, position-1
-        ids_all = ids[0] if len(ids) == 1 else torch.cat(ids, dim=0)
-        mask_all = masks[0] if len(masks) == 1 else torch.cat(masks, dim=0)
-        R = ids_all.shape[0]
+                # data-dependent shapes (nonzero() of the mask) are resolved HERE, before the encoder is enqueued: a sync
+                # after the encoder launch would drain the whole launch pipeline
+                prep = masked_inputs[4] if len(masked_inputs) > 4 else \
+                    self.prepare_inputs(target_node_inputs, pair_node_inputs, num_pairs, masked_inputs)
+                ids_flat, mask_all = prep["ids_all"], prep["mask_all"]
+            else:
+                ids_flat = torch.cat([t_ids, pair_node_inputs["node_ids"]], dim=0).reshape(-1)
+                mask_all = torch.cat([t_mask, pair_node_inputs["attention_mask"]], dim=0)
+        else:
+            ids_flat, mask_all = t_ids.reshape(-1), t_mask
+        ids_flat = ids_flat.contiguous()
+        R = mask_all.shape[0]
         if pair_node_inputs is None:
-            hidden = self.bert.encode(tables[0], tables[1], ids_all.reshape(-1).contiguous(), mask_all, R, L,
+            hidden = self.bert.encode(tables[0], tables[1], ids_flat, mask_all, R, L,
                                       arena=arena, refresh=False)  # (R, L, H) fp32
             H = hidden.shape[-1]
             last_hidden_state = hidden[:B]
@@ -300,7 +322,7 @@ class PMGT(PMGTPretrainedModel):
             # masked ones).  The encoder prunes its last layer to them and returns the compact [Tc, H] matrix.
             dev = t_ids.device
             sel = self._last_rows(B, SP, L, nfr_on, dev)
-            hidden = self.bert.encode(tables[0], tables[1], ids_all.reshape(-1).contiguous(), mask_all, R, L,
+            hidden = self.bert.encode(tables[0], tables[1], ids_flat, mask_all, R, L,
                                       arena=arena, refresh=False, last_rows=sel)  # (Tc, H) fp32
             H = hidden.shape[-1]
             last_hidden_state = hidden[:B * L].view(B, L, H)
@@ -309,13 +331,13 @@ class PMGT(PMGTPretrainedModel):
         prediction_logits = None
         if pair_node_inputs is not None:
             plan = self.bert._active_plan
-            pair_off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
-            torch.cumsum(num_pairs.to(dev), 0, out=pair_off[1:])
             nfr_rows = None
             target_ids = None
-            if nfr_on:  # compact row numbers of the masked positions (inside the masked-target block)
-                nfr_rows = B * L + SP + m_pos[:, 0] * L + m_pos[:, 1] + 1
-                target_ids = target_idx.contiguous()
+            if nfr_on:
+                pair_off, nfr_rows, target_ids = prep["pair_off"], prep["nfr_rows"], prep["target_ids"]
+            else:
+                pair_off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+                torch.cumsum(num_pairs.to(dev), 0, out=pair_off[1:])
             nfr_params = [p for _, p in self.nfr_loss.param_order()] if nfr_on else []
             loss, prediction_logits = _PretrainLossFn.apply(
                 self, hidden, B, SP, L, pair_off, labels.to(torch.float32).contiguous(), nfr_rows, target_ids, tables, arena,

@@ -451,6 +451,11 @@ def sumsq(x, out):
     _run("sumsq", _lib.lib().pmgt_sumsq_f32, (ptr(x), x.numel(), ptr(out), cur_stream()), 1, 4 * x.numel())
 
 
+def clip_coef(sumsq_buf, scale: float, max_norm: float, out):
+    """out[0] = scale * min(1, max_norm / (sqrt(sumsq) * scale + 1e-6)); resets ``sumsq_buf`` (clip_grad_norm_)."""
+    _run("clip_coef", _lib.lib().pmgt_clip_coef, (ptr(sumsq_buf), float(scale), float(max_norm), ptr(out), cur_stream()), 1, 8)
+
+
 def gather_rows(src, idx, out):
     _run("gather_rows", _lib.lib().pmgt_gather_rows_bf16, (ptr(src), src.stride(0), ptr(idx), idx.numel(), src.shape[1],
                                                            ptr(out), out.stride(0), cur_stream()), 1,

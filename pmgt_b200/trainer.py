@@ -243,6 +243,9 @@ class PMGTTrainerModel:
             masked = None
             if dataset.is_training:
                 masked = self.net.mask_nodes(batch[0]["node_ids"], with_positions=True)
+                # the concatenated [targets | pairs | masked targets] inputs and the loss indices depend on the batch
+                # only: built here, they cost the main stream nothing
+                masked = masked + (self.net.prepare_inputs(batch[0], batch[1], batch[2], masked),)
             ready = torch.cuda.Event()
             ready.record(self._side)
         self._prefetched = (dataset, indices, epoch, batch, masked, ready)
@@ -254,9 +257,13 @@ class PMGTTrainerModel:
         _, _, _, batch, masked, ready = pf
         main = torch.cuda.current_stream(self.args.device)
         main.wait_event(ready)
-        for t in (batch[0]["node_ids"], batch[0]["attention_mask"], batch[1]["node_ids"], batch[1]["attention_mask"],
-                  batch[2], batch[3], *(masked or ())):
-            t.record_stream(main)  # allocated on the side stream, consumed on the main one
+        tensors = [batch[0]["node_ids"], batch[0]["attention_mask"], batch[1]["node_ids"], batch[1]["attention_mask"],
+                   batch[2], batch[3]]
+        for m in (masked or ()):
+            tensors.extend(m.values() if isinstance(m, dict) else [m])
+        for t in tensors:
+            if isinstance(t, torch.Tensor):
+                t.record_stream(main)  # allocated on the side stream, consumed on the main one
         return batch, masked
 
     # -- one optimisation step on a sampled batch (sample -> fwd -> bwd -> allreduce -> AdamW)
@@ -318,18 +325,19 @@ class PMGTTrainerModel:
             scale = scale / ws
         scale_dev = None
         if args.gradient_max_norm:
-            # torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)), on the averaged gradient
+            # torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)), on the averaged gradient; one small
+            # kernel folds it with the gradient scale and resets the accumulator for the next step
             if self._sumsq is None:
                 self._sumsq = torch.zeros(1, dtype=torch.float32, device=loss.device)
-            self._sumsq.zero_()
+                self._coef = torch.empty(1, dtype=torch.float32, device=loss.device)
             if fv is not None and fv[1] is not None:
                 ops.sumsq(fv[1], self._sumsq)
             else:
                 for p in self.net.parameters():
                     if p.grad is not None:
                         ops.sumsq(p.grad.contiguous().view(-1), self._sumsq)
-            norm = self._sumsq.sqrt() * scale
-            scale_dev = (scale * torch.clamp(args.gradient_max_norm / (norm + 1e-6), max=1.0)).to(torch.float32)
+            ops.clip_coef(self._sumsq, scale, float(args.gradient_max_norm), self._coef)
+            scale_dev = self._coef
         # step with exactly the buffer that was reduced / measured above (it is a temporary when the gradients are not
         # zero-copy views of the arena: a second flat_views() call would rebuild it from the un-reduced p.grad)
         self.optimizer.step(grad_scale=scale, grad_scale_dev=scale_dev,

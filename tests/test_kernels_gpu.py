@@ -320,6 +320,19 @@ def test_dropout_is_consistent_between_fwd_and_bwd():
     assert not torch.equal(y, y2)  # another seed, another mask
 
 
+def test_clip_coef_matches_clip_grad_norm():
+    """pmgt_clip_coef: scale * min(1, max_norm / (sqrt(sumsq) * scale + 1e-6)) and the accumulator reset."""
+    ops = _ops()
+    for ss, scale, mx in ((4.0, 1.0, 1.0), (0.25, 0.5, 1.0), (9.0e4, 0.125, 2.0), (0.0, 1.0, 1.0)):
+        acc = torch.tensor([ss], device="cuda")
+        out = torch.empty(1, device="cuda")
+        ops.clip_coef(acc, scale, mx, out)
+        norm = ss ** 0.5 * scale
+        want = scale * min(1.0, mx / (norm + 1e-6))
+        assert abs(float(out) - want) <= 1e-6 * max(1.0, abs(want)), (float(out), want)
+        assert float(acc) == 0.0
+
+
 def test_colsum_cast_gather_sumsq():
     ops = _ops()
     x = _r(1234, 512)
