@@ -232,6 +232,27 @@ class PMGT(PMGTPretrainedModel):
             return masked_input_ids, mask, target_idx, mask.nonzero(as_tuple=False)
         return masked_input_ids, mask, target_idx
 
+    @torch.no_grad()
+    def item_embeddings(self, target_node_inputs: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """``self(inputs)[0][:, 0]`` -- the item embedding the downstream recommenders load (trainer.py:153-154,
+        base_trainer.py:400-407) -- as a ``[B, H]`` fp32 matrix, with the last encoder layer's post-attention half run
+        on position 0 only (rows are independent after the attention core; results are identical row for row)."""
+        ids, mask = target_node_inputs["node_ids"], target_node_inputs["attention_mask"]
+        if not ids.is_cuda:
+            raise PMGTError("PMGT.item_embeddings needs CUDA tensors: pmgt_b200 has no CPU fallback")
+        B, L = ids.shape
+        fp = self._flat()
+        fp.refresh_bf16()
+        tables = self.feature_tables_bf16()
+        key = ("emb", B, L, str(ids.device))
+        cache = self.__dict__.setdefault("_last_rows_cache", {})
+        sel = cache.get(key)
+        if sel is None:
+            if len(cache) > 8:
+                cache.clear()
+            sel = cache[key] = (torch.arange(B, device=ids.device) * L).contiguous()
+        return self.bert.encode(tables[0], tables[1], ids.reshape(-1).contiguous(), mask, B, L, refresh=False, last_rows=sel)
+
     def prepare_inputs(self, target_node_inputs, pair_node_inputs, num_pairs, masked_inputs) -> Dict[str, torch.Tensor]:
         """Everything ``forward`` derives from the batch alone (training with pairs): the concatenated
         [targets | pairs | masked targets] ids / masks, the pair offsets and the compact row numbers of the masked

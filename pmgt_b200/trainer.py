@@ -525,12 +525,20 @@ def inference(args: AttrDict) -> np.ndarray:
     rank, ws = world()
     n = len(ds)
     lo, hi = n * rank // ws, n * (rank + 1) // ws
-    out = torch.empty((hi - lo, args.hidden_size), dtype=torch.float32, device=args.device)
+    # position-0 states only (the last layer is pruned to them), written batch by batch into PINNED host memory with
+    # asynchronous copies that overlap the next batch's sampling and encoding; one synchronisation at the end
+    out = torch.empty((hi - lo, args.hidden_size), dtype=torch.float32).pin_memory()
     bs = args.test_batch_size
+    order = torch.arange(lo, hi, device=args.device)
+    tm.net.bert.use_launch_plans = True   # fixed-shape forward passes: record the launch list once, replay it
     for s in range(lo, hi, bs):
         e = min(s + bs, hi)
-        out[s - lo: e - lo] = tm.net(ds.sample_batch(np.arange(s, e)))[0][:, 0]
-    res = out.cpu().numpy()
+        emb = tm.net.item_embeddings(ds.sample_batch(order[s - lo: e - lo]))
+        # (a planned pass's output aliases a plan-owned buffer that the next pass overwrites: the copy is enqueued on
+        # the same stream before that pass, so it reads the right data)
+        out[s - lo: e - lo].copy_(emb, non_blocking=True)
+    torch.cuda.synchronize(args.device)
+    res = out.numpy()
     if ws > 1:
         parts = [None] * ws
         dist.all_gather_object(parts, res)
