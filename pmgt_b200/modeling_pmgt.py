@@ -282,10 +282,15 @@ class GradArena:
         shape = fp.shapes[name]
         if span is not None:
             shape = (shape[0] * span,) + shape[1:]
-        n = 1
-        for s in shape:
-            n *= s
-        return self.get()[off: off + n].view(shape)
+        # one as_strided instead of slice + view: this runs ~100 times per backward pass (host-bound small batches)
+        strides = fp.__dict__.setdefault("_strides", {}).get(shape)
+        if strides is None:
+            st, acc = [], 1
+            for d in reversed(shape):
+                st.append(acc)
+                acc *= d
+            strides = fp._strides[shape] = tuple(reversed(st))
+        return torch.as_strided(self.get(), shape, strides, off)
 
 
 def encoder_param_order(bert: "PMGTModel", prefix: str = "") -> List[Tuple[str, nn.Parameter]]:
