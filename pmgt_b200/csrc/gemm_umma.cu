@@ -622,7 +622,7 @@ extern "C" int pmgt_gemm_bf16(const pmgt_gemm_args* a, void* stream) {
   // output columns per tile when N allows (85 instead of 64 FLOP per operand byte through L2 -> SM)
   if (!ga && !gb && split == 1 && !(epi & PMGT_EPI_ATOMIC) && (long long)grid.x * grid.y > 2ll * num_sms() && num_kb >= 4) {
     // (the GELU epilogues are bound by their own instruction issue, and measured slower on the wide tiles: 1353 vs 919 us)
-    const bool wide_n = a->N >= 512 && (!(epi & (PMGT_EPI_GELU | PMGT_EPI_GELU_BWD)) || getenv("PMGT_GEMM_WIDE_GELU")) && !persist_narrow();
+    const bool wide_n = a->N >= 512 && !(epi & (PMGT_EPI_GELU | PMGT_EPI_GELU_BWD)) && !persist_narrow();
     if (!a->a_mn && !a->b_mn) return wide_n ? launch_persist<false, false, 256>(ta, tb, ka, st) : launch_persist<false, false, 128>(ta, tb, ka, st);
     if (!a->a_mn && a->b_mn) return wide_n ? launch_persist<false, true, 256>(ta, tb, ka, st) : launch_persist<false, true, 128>(ta, tb, ka, st);
     if (a->a_mn && a->b_mn) return wide_n ? launch_persist<true, true, 256>(ta, tb, ka, st) : launch_persist<true, true, 128>(ta, tb, ka, st);

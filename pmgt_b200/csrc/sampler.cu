@@ -625,10 +625,8 @@ int pmgt_sample_contexts(const pmgt_graph* gh, const int64_t* roots, const int64
   // the 1M graph, 0.50 -> 0.44 ms on TG, and the short-lived CTAs of the side-stream launch interleave better with the
   // main stream's persistent kernels (1M step 6.16 -> 6.01 ms).  PMGT_SAMPLER_CTAS_PER_SM=n restores a persistent grid.
   int64_t grid = n_ctx;
-  if (const char* e = getenv("PMGT_SAMPLER_CTAS_PER_SM")) {
-    const int v = atoi(e);
-    if (v > 0) grid = (int64_t)num_sms() * (v < occ ? v : occ);
-  }
+  static const int persistent_ctas = [] { const char* e = getenv("PMGT_SAMPLER_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+  if (persistent_ctas > 0) grid = (int64_t)num_sms() * (persistent_ctas < occ ? persistent_ctas : occ);
   if (grid > n_ctx) grid = n_ctx;
   kern<<<(unsigned)grid, kSamplerThreads, smem, (cudaStream_t)stream>>>(p);
   PMGT_LAUNCH_CHECK();
