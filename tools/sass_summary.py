@@ -35,7 +35,7 @@ for k, ls in lines.items():
 print(f"| **total** | {sum(len(v) for v in lines.values())} | " + " | ".join(str(tot[m]) for m in MN) + " |")
 print("\n## Excerpts (first tensor-core / TMA instructions of the hot kernels)\n")
 for pat in ("linear_tile_kernel<1, 1, false, 2", "ffn_fwd_kernel", "ffn_bwd_kernel", "dw_tile_kernel<4", "umma_gemm_kernel<false, false, true",
-            "attn_mma_bwd_kernel<6, 128>", "sample_contexts_kernel<8, true>", "ln_bwd_stream_kernel<2, false>"):
+            "attn_mma_bwd_kernel<6, 128>", "sample_contexts_kernel<8, true>", "ln_bwd_stream_kernel<2, false>", "gather_proj_fwd_kernel", "gather_proj_dw_kernel<8>", "umma_gemm_persist_kernel<false, false, 256>", "attn_reg_bwd_kernel<64, 3>"):
     for k, ls in lines.items():
         if pat in k:
             idx = next((i for i, ln in enumerate(ls) if re.search(r"UTCHMMA|HMMA|UTMALDG|UBLKCP|LDG", ln)), 0)
