@@ -16,6 +16,7 @@ for ln in out.splitlines():
     m = re.search(r"Function : (\S+)", ln)
     if m:
         kern = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        kern = kern.replace("(anonymous namespace)::", "")
         kern = re.sub(r"\(.*", "", kern)
         lines[kern] = []
     elif kern and "/*" in ln and ";" in ln:
