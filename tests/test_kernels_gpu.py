@@ -169,7 +169,10 @@ def test_embed_fuse_dropout_mask_agrees_between_fwd_and_bwd():
                                               # medium-L tensor-core kernel (attention_mid.cu): config-5 heads, L = 64,
                                               # one / three k-tiles, head sizes 32 / 48 / 128, more items than warps
                                               (4, 33, 768, 12, 0.5), (3, 64, 128, 4, 0.7), (40, 17, 256, 2, 0.2),
-                                              (5, 12, 96, 2, 0.0), (2, 48, 64, 1, 0.5)])
+                                              (5, 12, 96, 2, 0.0), (2, 48, 64, 1, 0.5),
+                                              # register-resident kernel (attention_reg.cu): one row block (L = 12 / 16), L an exact
+                                              # multiple of 16, head sizes 32 / 64 / 128
+                                              (6, 12, 128, 2, 0.5), (3, 16, 64, 2, 0.4), (4, 32, 256, 2, 0.6), (7, 10, 128, 1, 0.5)])
 def test_attention_core_fwd_bwd(R, L, H, heads, beta):
     ops = _ops()
     T = R * L
