@@ -39,7 +39,7 @@ typedef enum pmgt_status {
 } pmgt_status;
 
 /* ABI version of this header; bumped on any signature change. */
-#define PMGT_B200_ABI_VERSION 11
+#define PMGT_B200_ABI_VERSION 12
 int pmgt_abi_version(void);
 const char* pmgt_last_error(void);
 
@@ -510,6 +510,12 @@ int pmgt_sumsq_f32(const float* x, int64_t n, float* out, void* stream);
 /* torch.nn.utils.clip_grad_norm_ (pmgt/base_trainer.py:314 gradient_clip_val) folded with the gradient scale:
  * out[0] = scale * min(1, max_norm / (sqrt(sumsq[0]) * scale + 1e-6)); sumsq[0] is reset to 0 for the next step */
 int pmgt_clip_coef(float* sumsq, float scale, float max_norm, float* out, void* stream);
+/* In-place sum of a flat fp32 vector over the ranks of one NVSwitch domain (replaces the gradient all-reduce of the
+ * reference's implicit DDP, pmgt/base_trainer.py:309-322).  peer_ptrs[r] = device address of rank r's copy as mapped into
+ * THIS process (symmetric memory / CUDA IPC; 16-byte aligned; peer_ptrs[rank] is the local copy).  Rank `rank` reduces
+ * slice `rank` of the vector and stores the sum into every copy.  The caller brackets the call with barriers over all
+ * ranks: every copy complete before it, every slice written after it.  world_size <= 8. */
+int pmgt_peer_reduce_f32(const uint64_t* peer_ptrs, int world_size, int rank, int64_t n, void* stream);
 /* out[r][:] = src[idx[r]][:]   (bf16 rows, D elements, D % 8 == 0) */
 int pmgt_gather_rows_bf16(const uint16_t* src, int64_t ld_src, const int64_t* idx, int64_t n_rows,
                           int64_t D, uint16_t* out, int64_t ld_out, void* stream);

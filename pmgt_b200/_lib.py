@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmgt_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _lib = None
 
@@ -224,6 +224,7 @@ SIGNATURES = {
     "pmgt_adamw_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_int64, C.c_float, c_vp, c_vp]),
     "pmgt_cast_f32_bf16": (C.c_int, [c_vp, c_vp, C.c_int64, c_vp]),
+    "pmgt_peer_reduce_f32": (C.c_int, [C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int64, c_vp]),
     "pmgt_clip_coef": (C.c_int, [c_vp, C.c_float, C.c_float, c_vp, c_vp]),
     "pmgt_sumsq_f32": (C.c_int, [c_vp, C.c_int64, c_vp, c_vp]),
     "pmgt_gather_rows_bf16": (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int64, C.c_int64, c_vp, C.c_int64, c_vp]),

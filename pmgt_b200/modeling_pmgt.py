@@ -247,7 +247,7 @@ class FlatParams:
         """The persistent gradient arena of this parameter set (one per flat buffer), zeroed for a new step."""
         a = getattr(self, "_step_arena", None)
         if a is None or a.buf is None or a.buf.device != self.flat.device or a.buf.numel() != self.total:
-            a = GradArena(self, persistent=True)
+            a = GradArena(self, persistent=True, symm_group=getattr(self, "symm_group", None))
             a.get()
             self._step_arena = a
             return a
@@ -261,10 +261,14 @@ class GradArena:
     """One fp32 buffer per backward pass holding every parameter gradient in
     FlatParams order; autograd receives views of it."""
 
-    def __init__(self, fp: FlatParams, persistent: bool = False):
+    def __init__(self, fp: FlatParams, persistent: bool = False, symm_group=None):
         self.fp = fp
         self.buf = None
         self.persistent = persistent  # the same buffer every step (zeroed by `reset`): what a launch plan needs
+        # data parallel: allocate the buffer in symmetric memory of this process group, so that the ranks can sum their
+        # gradients through peer pointers (trainer.train_on_indices, csrc/peer_reduce.cu); `symm` = the handle
+        self.symm_group = symm_group
+        self.symm = None
 
     def reset(self):
         if self.buf is not None:
@@ -273,7 +277,14 @@ class GradArena:
 
     def get(self):
         if self.buf is None:
-            self.buf = torch.zeros(self.fp.total, dtype=torch.float32, device=self.fp.flat.device)
+            dev = self.fp.flat.device
+            if self.symm_group is not None:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.buf = symm_mem.empty(self.fp.total, dtype=torch.float32, device=dev)
+                self.buf.zero_()
+                self.symm = symm_mem.rendezvous(self.buf, self.symm_group)   # collective: every rank allocates here
+            else:
+                self.buf = torch.zeros(self.fp.total, dtype=torch.float32, device=dev)
         return self.buf
 
     def view(self, name, span=None):

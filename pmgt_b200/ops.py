@@ -451,6 +451,14 @@ def sumsq(x, out):
     _run("sumsq", _lib.lib().pmgt_sumsq_f32, (ptr(x), x.numel(), ptr(out), cur_stream()), 1, 4 * x.numel())
 
 
+def peer_reduce(peer_ptrs, rank: int, n: int):
+    """In-place sum of the flat fp32 vector whose per-rank copies are at ``peer_ptrs`` (symmetric memory); the caller
+    brackets it with barriers over the ranks."""
+    ws = len(peer_ptrs)
+    arr = (C.c_uint64 * ws)(*[int(p) for p in peer_ptrs])
+    _run("peer_reduce", _lib.lib().pmgt_peer_reduce_f32, (arr, ws, int(rank), int(n), cur_stream()), 1, 8 * n * (ws - 1) // ws)
+
+
 def clip_coef(sumsq_buf, scale: float, max_norm: float, out):
     """out[0] = scale * min(1, max_norm / (sqrt(sumsq) * scale + 1e-6)); resets ``sumsq_buf`` (clip_grad_norm_)."""
     _run("clip_coef", _lib.lib().pmgt_clip_coef, (ptr(sumsq_buf), float(scale), float(max_norm), ptr(out), cur_stream()), 1, 8)

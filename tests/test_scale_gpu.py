@@ -150,9 +150,10 @@ def _make_trainer(dev, B):
     return trainer, args, trainer.PMGTTrainerModel(args)
 
 
-def _dp_worker(rank, ws, port, q):
+def _dp_worker(rank, ws, port, q, symm_reduce):
     import torch.distributed as dist
     try:
+        os.environ["PMGT_SYMM_REDUCE"] = "1" if symm_reduce else "0"
         torch.cuda.set_device(rank)
         dev = torch.device("cuda", rank)
         B = 96
@@ -179,6 +180,9 @@ def _dp_worker(rank, ws, port, q):
         loss = tm2.train_on_indices(args2.train_dataset, shards[rank], 0)
         torch.cuda.synchronize()
         assert torch.isfinite(loss)
+        # which exchange ran: the in-place peer reduction over symmetric memory, or NCCL
+        arena = tm2.net._flat()._step_arena
+        assert (arena.symm is not None) == bool(symm_reduce), (arena.symm, symm_reduce)
         fv = tm2.optimizer.flat_views()
         dp_grad = fv[1].clone() / ws          # allreduced (sum) flat gradient
         p1 = torch.cat([p.detach().reshape(-1) for p in tm2.net.parameters() if p.requires_grad])
@@ -220,13 +224,16 @@ def _dp_worker(rank, ws, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
-def test_two_nccl_ranks_end_the_step_with_identical_parameters():
+@pytest.mark.parametrize("symm_reduce", [True, False])
+def test_two_nccl_ranks_end_the_step_with_identical_parameters(symm_reduce):
+    """Two ranks of the product end a step with bit-identical parameters equal to one GPU on the concatenated batch --
+    through the symmetric-memory peer reduction (csrc/peer_reduce.cu) and through the NCCL all-reduce."""
     import torch.multiprocessing as mp
     ws = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_dp_worker, args=(r, ws, port, q)) for r in range(ws)]
+    procs = [ctx.Process(target=_dp_worker, args=(r, ws, port, q, symm_reduce)) for r in range(ws)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in range(ws)]
