@@ -336,6 +336,23 @@ def test_clip_coef_matches_clip_grad_norm():
         assert float(acc) == 0.0
 
 
+@pytest.mark.parametrize("ws,n", [(2, 1000), (4, 1_187_003), (8, 4099), (3, 5)])
+def test_peer_reduce_sums_every_copy_in_place(ws, n):
+    """pmgt_peer_reduce_f32 with the ranks' copies emulated by `ws` buffers on one device: after every rank has reduced
+    its slice, every copy holds the sum (including the elements beyond the last whole float4)."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    bufs = [torch.randn(n, device="cuda", generator=g) for _ in range(ws)]
+    want = torch.stack(bufs).double().sum(0)
+    ptrs = [b.data_ptr() for b in bufs]
+    for r in range(ws):
+        ops.peer_reduce(ptrs, r, n)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.allclose(b.double(), want, rtol=1e-5, atol=1e-5)
+    assert all(torch.equal(bufs[0], b) for b in bufs)
+
+
 def test_colsum_cast_gather_sumsq():
     ops = _ops()
     x = _r(1234, 512)
