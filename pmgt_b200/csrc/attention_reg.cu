@@ -108,7 +108,7 @@ __device__ __forceinline__ void stage_tile_async(uint16_t* tile, const uint16_t*
 
 // D[nt][*] += A_rows(16 x DH, tile rows a_row0..) . B(all LP rows)^T : the "row block x all rows" L x L product
 template <int DH, int MT>
-__device__ __forceinline__ void block_nt(float (&d)[2 * MT][4], const uint16_t* A, int a_row0, const uint16_t* B, int lane) {
+__device__ __forceinline__ void block_nt(float (&d)[2 * MT][4], const uint16_t* A, int a_row0, const uint16_t* B, int lane, int L) {
   using Cf = RegCfg<DH, MT>;
 #pragma unroll
   for (int ks = 0; ks < Cf::KS; ++ks) {
@@ -119,7 +119,7 @@ __device__ __forceinline__ void block_nt(float (&d)[2 * MT][4], const uint16_t* 
       uint32_t bf[4];
       rldsm4(rsaddr(B + (np * 16 + (lane & 7) + ((lane >> 4) << 3)) * Cf::RS + ks * 16 + ((lane >> 3) & 1) * 8), bf);
       rmma(d[2 * np], af, bf[0], bf[1]);
-      rmma(d[2 * np + 1], af, bf[2], bf[3]);
+      if ((2 * np + 1) * 8 < L) rmma(d[2 * np + 1], af, bf[2], bf[3]);   // a column tile beyond L stays zero
     }
   }
 }
@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(32 * MT) attn_reg_fwd_kernel(const pmgt_attn_a
   float* madd = nrm + Cf::LP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int L = a.L, H = a.H, heads = a.heads;
+  const int nt_live = (L + 7) >> 3;   // 8-wide column tiles that hold at least one real position (L = 33: 5 of 6)
   const long long item = blockIdx.x;
   const long long row = item / heads;
   const int head = (int)(item - row * heads);
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(32 * MT) attn_reg_fwd_kernel(const pmgt_attn_a
   float s1[Cf::NT][4], s2[Cf::NT][4];
   zero_acc<Cf::NT>(s1);
   zero_acc<Cf::NT>(s2);
-  block_nt<DH, MT>(s1, sC, warp * 16, sC, lane);
+  block_nt<DH, MT>(s1, sC, warp * 16, sC, lane, L);
 #pragma unroll
   for (int ks = 0; ks < Cf::KS; ++ks) {
 #pragma unroll
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(32 * MT) attn_reg_fwd_kernel(const pmgt_attn_a
       uint32_t bf[4];
       rldsm4(rsaddr(sK + (np * 16 + (lane & 7) + ((lane >> 4) << 3)) * Cf::RS + ks * 16 + ((lane >> 3) & 1) * 8), bf);
       rmma(s2[2 * np], qf[ks], bf[0], bf[1]);
-      rmma(s2[2 * np + 1], qf[ks], bf[2], bf[3]);
+      if ((2 * np + 1) * 8 < L) rmma(s2[2 * np + 1], qf[ks], bf[2], bf[3]);
     }
   }
   // scores -> probabilities, in place
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(32 * MT) attn_reg_fwd_kernel(const pmgt_attn_a
   const float rn0 = nrm[i0], rn1 = nrm[i1];
   float m1a = -INFINITY, m1b = -INFINITY, m2a = -INFINITY, m2b = -INFINITY;
 #pragma unroll
-  for (int nt = 0; nt < Cf::NT; ++nt) {
+  for (int nt = 0; nt < Cf::NT; ++nt) if (nt < nt_live) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int j = nt * 8 + 2 * t + (e & 1);
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(32 * MT) attn_reg_fwd_kernel(const pmgt_attn_a
   m1a = quad_max(m1a); m1b = quad_max(m1b); m2a = quad_max(m2a); m2b = quad_max(m2b);
   float z1a = 0.f, z1b = 0.f, z2a = 0.f, z2b = 0.f;
 #pragma unroll
-  for (int nt = 0; nt < Cf::NT; ++nt) {
+  for (int nt = 0; nt < Cf::NT; ++nt) if (nt < nt_live) {
     s1[nt][0] = __expf(s1[nt][0] - m1a); s1[nt][1] = __expf(s1[nt][1] - m1a);
     s1[nt][2] = __expf(s1[nt][2] - m1b); s1[nt][3] = __expf(s1[nt][3] - m1b);
     s2[nt][0] = __expf(s2[nt][0] - m2a); s2[nt][1] = __expf(s2[nt][1] - m2a);
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(32 * MT) attn_reg_fwd_kernel(const pmgt_attn_a
   const float beta = a.beta;
   const uint32_t dbase0 = (uint32_t)(i0 * L), dbase1 = (uint32_t)(i1 * L);
 #pragma unroll
-  for (int nt = 0; nt < Cf::NT; ++nt) {
+  for (int nt = 0; nt < Cf::NT; ++nt) if (nt < nt_live) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int j = nt * 8 + 2 * t + (e & 1);
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(32 * MT, 65536 / (32 * MT * PMGT_REG_BWD_REGS)
   float* st_r2 = st_r1 + Cf::LP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int L = a.L, H = a.H, heads = a.heads;
+  const int nt_live = (L + 7) >> 3;   // 8-wide column tiles that hold at least one real position (L = 33: 5 of 6)
   const long long item = blockIdx.x;
   const long long row = item / heads;
   const int head = (int)(item - row * heads);
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(32 * MT, 65536 / (32 * MT * PMGT_REG_BWD_REGS)
 
   float gram[Cf::NT][4];  // raw C C^T block of these rows: symmetric, so it serves both orientations
   zero_acc<Cf::NT>(gram);
-  block_nt<DH, MT>(gram, sC, warp * 16, sC, lane);
+  block_nt<DH, MT>(gram, sC, warp * 16, sC, lane, L);
   float accC[Cf::ON][4];  // sum_j [dS1_ij + dS1_ji] / (n_i n_j) C_j for rows r0 / r1
   zero_acc<Cf::ON>(accC);
   float rc0 = 0.f, rc1 = 0.f;  // sum_j (dS1_ij + dS1_ji) cos_ij
@@ -350,13 +352,14 @@ __global__ void __launch_bounds__(32 * MT, 65536 / (32 * MT * PMGT_REG_BWD_REGS)
   // ===================== phase A: rows = queries =====================
   {
     float p1[Cf::NT][4], p2[Cf::NT][4], dA[Cf::NT][4];
+    zero_acc<Cf::NT>(p1);
     zero_acc<Cf::NT>(p2);
     zero_acc<Cf::NT>(dA);
-    block_nt<DH, MT>(p2, sQ, warp * 16, sK, lane);
-    block_nt<DH, MT>(dA, sO, warp * 16, sV, lane);
+    block_nt<DH, MT>(p2, sQ, warp * 16, sK, lane, L);
+    block_nt<DH, MT>(dA, sO, warp * 16, sV, lane, L);
     float m1a = -INFINITY, m1b = -INFINITY, m2a = -INFINITY, m2b = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < Cf::NT; ++nt) {
+    for (int nt = 0; nt < Cf::NT; ++nt) if (nt < nt_live) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = nt * 8 + 2 * t + (e & 1);
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(32 * MT, 65536 / (32 * MT * PMGT_REG_BWD_REGS)
     m1a = quad_max(m1a); m1b = quad_max(m1b); m2a = quad_max(m2a); m2b = quad_max(m2b);
     float z1a = 0.f, z1b = 0.f, z2a = 0.f, z2b = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < Cf::NT; ++nt) {
+    for (int nt = 0; nt < Cf::NT; ++nt) if (nt < nt_live) {
       p1[nt][0] = __expf(p1[nt][0] - m1a); p1[nt][1] = __expf(p1[nt][1] - m1a);
       p1[nt][2] = __expf(p1[nt][2] - m1b); p1[nt][3] = __expf(p1[nt][3] - m1b);
       p2[nt][0] = __expf(p2[nt][0] - m2a); p2[nt][1] = __expf(p2[nt][1] - m2a);
@@ -385,8 +388,9 @@ __global__ void __launch_bounds__(32 * MT, 65536 / (32 * MT * PMGT_REG_BWD_REGS)
     // g1 = beta dA drop1, g2 = (1 - beta) dA drop2 (into dA / p-independent temporaries), row dots r = sum_j g P
     float r1a = 0.f, r1b = 0.f, r2a = 0.f, r2b = 0.f;
     float g2[Cf::NT][4];
+    zero_acc<Cf::NT>(g2);
 #pragma unroll
-    for (int nt = 0; nt < Cf::NT; ++nt) {
+    for (int nt = 0; nt < Cf::NT; ++nt) if (nt < nt_live) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = nt * 8 + 2 * t + (e & 1);
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(32 * MT, 65536 / (32 * MT * PMGT_REG_BWD_REGS)
     }
     // dS2 -> g2 (in place), dS1 / (n_i n_j) -> dA (in place); cosine row dot
 #pragma unroll
-    for (int nt = 0; nt < Cf::NT; ++nt) {
+    for (int nt = 0; nt < Cf::NT; ++nt) if (nt < nt_live) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = nt * 8 + 2 * t + (e & 1);
@@ -435,12 +439,13 @@ __global__ void __launch_bounds__(32 * MT, 65536 / (32 * MT * PMGT_REG_BWD_REGS)
     float p2[Cf::NT][4], dA[Cf::NT][4];
     zero_acc<Cf::NT>(p2);
     zero_acc<Cf::NT>(dA);
-    block_nt<DH, MT>(p2, sK, warp * 16, sQ, lane);   // K_j . Q_i
-    block_nt<DH, MT>(dA, sV, warp * 16, sO, lane);   // V_j . dO_i
+    block_nt<DH, MT>(p2, sK, warp * 16, sQ, lane, L);   // K_j . Q_i
+    block_nt<DH, MT>(dA, sV, warp * 16, sO, lane, L);   // V_j . dO_i
     const float ma0 = madd[r0], ma1 = madd[r1];
-    float am[Cf::NT][4];  // A_ij (with dropout) for dV, then dS1 / (n n) for dC
+    float am[Cf::NT][4];  // A_ij (with dropout) for dV
+    zero_acc<Cf::NT>(am);
 #pragma unroll
-    for (int nt = 0; nt < Cf::NT; ++nt) {
+    for (int nt = 0; nt < Cf::NT; ++nt) if (nt < nt_live) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int i = nt * 8 + 2 * t + (e & 1);   // query (column)
