@@ -247,4 +247,44 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + pdf_x;
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): the epilogues are bound by instruction issue, and one packed
+// instruction does the work of two
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f32x2 pk2u(uint32_t a, uint32_t b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ f32x2 pk1(float a) { return pk2(a, a); }
+__device__ __forceinline__ void up2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ void up2u(f32x2 v, uint32_t& a, uint32_t& b) { asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint32_t pack2_bf16(f32x2 v) { float a, b; up2(v, a, b); return pack_bf16x2(a, b); }
+__device__ __forceinline__ f32x2 unpack2_bf16(uint32_t v) { return pk2u(v << 16, v & 0xffff0000u); }
+
+// erf-GELU of two elements at once (gelu_parts with packed arithmetic; the 1/2 of Phi folded into the coefficients):
+// h = x Phi(x) and, if asked, gelu'(x) = Phi(x) + x phi(x).  ~11 instructions per element instead of ~17: the GELU
+// epilogues are bound by instruction issue.
+__device__ __forceinline__ void gelu_pair(f32x2 x, f32x2& h, f32x2* grad) {
+  float x0, x1;
+  up2(x, x0, x1);
+  const float t0 = __fdividef(1.0f, fmaf(0.2316418882f, fabsf(x0), 1.0f));   // 0.3275911 / sqrt 2
+  const float t1 = __fdividef(1.0f, fmaf(0.2316418882f, fabsf(x1), 1.0f));
+  float a0, a1;
+  up2(mul2(mul2(x, x), pk1(-0.72134752044448170368f)), a0, a1);
+  const f32x2 e = pk2(exp2f(a0), exp2f(a1));                                  // e^{-x^2/2}
+  const f32x2 t = pk2(t0, t1);
+  f32x2 poly = fma2(pk1(0.5f * 1.061405429f), t, pk1(0.5f * -1.453152027f));
+  poly = fma2(poly, t, pk1(0.5f * 1.421413741f));
+  poly = fma2(poly, t, pk1(0.5f * -0.284496736f));
+  poly = fma2(poly, t, pk1(0.5f * 0.254829592f));
+  const f32x2 half = mul2(mul2(poly, t), e);            // (1 - erf(|x| / sqrt 2)) / 2 = Phi(-|x|)
+  uint32_t q0, q1;
+  up2u(fma2(half, pk1(-1.f), pk1(0.5f)), q0, q1);       // 1/2 - Phi(-|x|) >= 0
+  q0 |= __float_as_uint(x0) & 0x80000000u;              // ... with the sign of x
+  q1 |= __float_as_uint(x1) & 0x80000000u;
+  const f32x2 cdf = add2(pk2u(q0, q1), pk1(0.5f));      // Phi(x)
+  h = mul2(x, cdf);
+  if (grad) *grad = add2(cdf, mul2(mul2(x, e), pk1(0.39894228040143267794f)));   // + x phi(x)
+}
+
 }  // namespace pmgt

@@ -111,20 +111,6 @@ __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
                : "memory");
 }
 
-// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): the epilogues are bound by instruction issue, and one packed
-// instruction does the work of two
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ f32x2 pk2u(uint32_t a, uint32_t b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
-__device__ __forceinline__ f32x2 pk1(float a) { return pk2(a, a); }
-__device__ __forceinline__ void up2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ void up2u(f32x2 v, uint32_t& a, uint32_t& b) { asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ uint32_t pack2_bf16(f32x2 v) { float a, b; up2(v, a, b); return pack_bf16x2(a, b); }
-__device__ __forceinline__ f32x2 unpack2_bf16(uint32_t v) { return pk2u(v << 16, v & 0xffff0000u); }
-
 // dropout multipliers (1 / (1 - p) or 0) of the 8 elements idx8 .. idx8 + 7 as four packed pairs; thr16 =
 // dropout_threshold(p) << 16.  Same stream as dropout_keep8 (common.cuh).
 __device__ __forceinline__ void dropout_factors8(uint64_t seed, uint32_t site, uint64_t idx8, uint32_t thr16, float ks, f32x2 (&f)[4]) {

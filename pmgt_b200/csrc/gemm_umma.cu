@@ -91,19 +91,25 @@ __device__ __forceinline__ uint4 epilogue_group(const GemmKernelArgs& p, uint32_
     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
     v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
   }
-  if (epi & PMGT_EPI_GELU) {
+  if (epi & PMGT_EPI_GELU) {   // two elements per instruction (gelu_pair): this epilogue is bound by instruction issue
     pre_out.x = pack_bf16x2(v[0], v[1]); pre_out.y = pack_bf16x2(v[2], v[3]);
     pre_out.z = pack_bf16x2(v[4], v[5]); pre_out.w = pack_bf16x2(v[6], v[7]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 8; j += 2) {
+      f32x2 h;
+      gelu_pair(pk2(v[j], v[j + 1]), h, nullptr);
+      up2(h, v[j], v[j + 1]);
+    }
   }
   if (epi & PMGT_EPI_GELU_BWD) {
     const uint4 pre = *reinterpret_cast<const uint4*>(p.aux + (long long)m * p.ld_aux + n);
-    float x[8];
-    unpack_bf16x2(pre.x, x[0], x[1]); unpack_bf16x2(pre.y, x[2], x[3]);
-    unpack_bf16x2(pre.z, x[4], x[5]); unpack_bf16x2(pre.w, x[6], x[7]);
+    const uint32_t pw[4] = {pre.x, pre.y, pre.z, pre.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(x[j]);
+    for (int j = 0; j < 4; ++j) {
+      f32x2 h, gr;
+      gelu_pair(unpack2_bf16(pw[j]), h, &gr);
+      up2(mul2(pk2(v[2 * j], v[2 * j + 1]), gr), v[2 * j], v[2 * j + 1]);
+    }
   }
   if (epi & PMGT_EPI_ADDEND) {
     const uint4 ad = *reinterpret_cast<const uint4*>(p.addend + (long long)m * p.ld_addend + n);
