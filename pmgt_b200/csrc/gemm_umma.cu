@@ -167,6 +167,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelArgs& p, uint32_t
   }
 }
 
+// Staged variant of epilogue_chunk for the persistent kernel: the 32 columns are written as bf16 into a 128-byte-swizzled
+// shared-memory image of the output tile (and of the GELU pre-activation tile), which one thread then hands to TMA as
+// [128 rows x 64 columns] boxes -- whole 128-byte lines per row instead of one 32-byte piece per thread and
+// instruction (the row-per-thread stores bound the epilogue: 505 vs ~420 us for the [101376, 768] x [768, 3072] Linear).
+__device__ __forceinline__ void epilogue_chunk_staged(const GemmKernelArgs& p, uint32_t epi, int m, bool row_ok, int r, int n_base,
+                                                      int c_tile, const uint32_t (&acc)[32], unsigned char* stg_out,
+                                                      unsigned char* stg_aux) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n = n_base + g * 8;
+    uint4 pre = make_uint4(0u, 0u, 0u, 0u), o = pre;
+    if (row_ok && n < p.N) o = epilogue_group(p, epi, m, n, acc + g * 8, pre);
+    const int c = c_tile + g * 8;   // column inside the tile
+    const uint32_t off = (uint32_t)((c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4));
+    *reinterpret_cast<uint4*>(stg_out + off) = o;
+    if (epi & PMGT_EPI_GELU) *reinterpret_cast<uint4*>(stg_aux + off) = pre;
+  }
+}
+
 template <bool A_MN, bool B_MN, bool GATHER_A, bool GATHER_B, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -362,21 +381,35 @@ struct PersistSmem {
   uint64_t full[kPersistStages];
   uint64_t empty[kPersistStages];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t stg_empty;   // staged epilogue: the TMA store of the previous tile has finished reading the staging images
   uint32_t tmem_base;
 };
 
-template <bool A_MN, bool B_MN, int BN_>  // BN_ = 128 or 256 output columns per tile
+// operand ring depth and staging bytes of a persistent-kernel configuration
+template <int BN_, bool STG>
+struct PersistCfg {
+  static constexpr int kStages = !STG ? (BN_ == 128 ? kPersistStages : 4) : (BN_ == 128 ? 4 : 3);
+  static constexpr int kStgOut = STG ? 128 * BN_ * 2 : 0;              // bf16 image of the output tile
+  static constexpr int kStgAux = (STG && BN_ == 128) ? 128 * BN_ * 2 : 0;   // GELU pre-activation image (narrow tiles only)
+  static constexpr int kSmem = kStages * (kOperandStageBytes + BN_ * BK * 2) + kStgOut + kStgAux + (int)sizeof(PersistSmem) + 1024;
+};
+
+template <bool A_MN, bool B_MN, int BN_, bool STG>  // BN_ = 128 or 256 output columns per tile; STG: TMA-store epilogue
 __global__ void __launch_bounds__(kPersistThreads, 1)
 umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                          const GemmKernelArgs p) {
-  constexpr int STAGES = BN_ == 128 ? kPersistStages : 4;
+  using Cfg = PersistCfg<BN_, STG>;
+  constexpr int STAGES = Cfg::kStages;
   constexpr int kAStage = kOperandStageBytes;         // 128 rows x 64 k
   constexpr int kBStage = BN_ * BK * 2;               // BN_ rows x 64 k (K-major) or BN_ / 64 slabs of 64 k x 64 n
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem + STAGES * kAStage;
-  PersistSmem* sh = reinterpret_cast<PersistSmem*>(smem + STAGES * (kAStage + kBStage));
+  unsigned char* stg_out = smem + STAGES * (kAStage + kBStage);
+  unsigned char* stg_aux = stg_out + Cfg::kStgOut;
+  PersistSmem* sh = reinterpret_cast<PersistSmem*>(stg_aux + Cfg::kStgAux);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntn = (p.N + BN_ - 1) / BN_, ntm = (p.M + BM - 1) / BM;
   const int num_tiles = ntn * ntm;
@@ -385,9 +418,11 @@ umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&sh->full[s], 1u); mbar_init(&sh->empty[s], 1u); }
     for (int s = 0; s < 2; ++s) { mbar_init(&sh->acc_full[s], 1u); mbar_init(&sh->acc_empty[s], 8u); }
+    mbar_init(&sh->stg_empty, 1u);
     fence_barrier_init();
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (STG) prefetch_tmap(&tmap_out);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"((uint32_t)(2 * BN_)));
@@ -466,19 +501,38 @@ umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const bool row_ok = m < p.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * (uint32_t)BN_;
       // (loading the next 32 columns from tensor memory while the current ones are converted was measured slower:
-      // 644 vs 568 us on the [101376, 768] x [768, 3072] forward -- the epilogue is bound by its row-wise stores)
+      // 644 vs 568 us on the [101376, 768] x [768, 3072] forward -- the epilogue is bound by its stores)
+      if (STG) mbar_wait(&sh->stg_empty, (tl & 1u) ^ 1u);   // the previous tile's TMA store has read the staging images
 #pragma unroll 1
       for (int c0 = half * (BN_ / 2); c0 < (half + 1) * (BN_ / 2); c0 += 32) {
-        if (n0 + c0 >= p.N) break;  // warp-uniform
+        if (!STG && n0 + c0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_x32(taddr + (uint32_t)c0, r);
         tmem_wait_ld();
-        if (row_ok) epilogue_chunk(p, epi, m, n0 + c0, r);
+        if (STG) epilogue_chunk_staged(p, epi, m, row_ok, quarter * 32 + lane, n0 + c0, c0, r, stg_out, stg_aux);
+        else if (row_ok) epilogue_chunk(p, epi, m, n0 + c0, r);
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->acc_empty[slot]);
+      if (STG) {
+        fence_proxy_async_smem();          // the generic-proxy writes of the staging images, before the TMA reads them
+        named_bar_sync(2, 256);            // all eight epilogue warps
+        if (threadIdx.x == 64) {           // first epilogue thread: one box per 64-column slab (TMA clips at M and N)
+#pragma unroll
+          for (int sl = 0; sl < BN_ / 64; ++sl) {
+            if (n0 + sl * 64 < p.N) {
+              tma_store_2d(&tmap_out, smem_u32(stg_out + sl * 16384), n0 + sl * 64, m0);
+              if (Cfg::kStgAux > 0 && (epi & PMGT_EPI_GELU)) tma_store_2d(&tmap_aux, smem_u32(stg_aux + sl * 16384), n0 + sl * 64, m0);
+            }
+          }
+          tma_store_commit();
+          tma_store_wait_read0();
+          mbar_arrive(&sh->stg_empty);
+        }
+      }
     }
+    if (STG && threadIdx.x == 64) tma_store_wait_all0();   // the last tile's stores have reached global memory
   }
 
   tcgen05_fence_before();
@@ -546,20 +600,42 @@ static bool persist_narrow() {
   return v != 0;
 }
 
-template <bool A_MN, bool B_MN, int BN_>
-static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelArgs& ka, cudaStream_t st) {
-  auto kern = umma_gemm_persist_kernel<A_MN, B_MN, BN_>;
-  constexpr int stages = BN_ == 128 ? kPersistStages : 4;
-  const int smem = stages * (kOperandStageBytes + BN_ * BK * 2) + (int)sizeof(PersistSmem) + 1024;
+template <bool A_MN, bool B_MN, int BN_, bool STG>
+static int launch_persist_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
+                              const GemmKernelArgs& ka, cudaStream_t st) {
+  auto kern = umma_gemm_persist_kernel<A_MN, B_MN, BN_, STG>;
+  constexpr int smem = PersistCfg<BN_, STG>::kSmem;
   static unsigned long long configured = 0;
   if (first_use_on_device(configured)) {
     PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   const long long tiles = (long long)((ka.N + BN_ - 1) / BN_) * ((ka.M + BM - 1) / BM);
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  kern<<<grid, kPersistThreads, smem, st>>>(ta, tb, ka);
+  kern<<<grid, kPersistThreads, smem, st>>>(ta, tb, to, tx, ka);
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
+}
+
+// bf16 outputs leave through the staged TMA-store epilogue (PMGT_GEMM_DIRECT_STORE=1: row-per-thread stores)
+template <bool A_MN, bool B_MN, int BN_>
+static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelArgs& ka, cudaStream_t st) {
+  static const bool direct = [] { const char* e = getenv("PMGT_GEMM_DIRECT_STORE"); return e && e[0] == '1'; }();
+  // staged stores pay when the epilogue is long next to the main loop (K <= 1024: 428 vs 499 us on the qkvc Linear); with
+  // a long K loop the shallower operand ring they leave costs more than the stores save (K = 3072: 383 vs 354 us)
+  const bool bf16_out = !(ka.epi & (PMGT_EPI_OUT_F32 | PMGT_EPI_ATOMIC)) && ka.K <= 1024;
+  CUtensorMap to, tx;
+  memset(&to, 0, sizeof(to));
+  memset(&tx, 0, sizeof(tx));
+  if (bf16_out && !direct) {
+    int rc = make_tmap(&to, ka.out, ka.N, ka.M, ka.ldo, 64, 128);
+    if (rc) return rc;
+    if (ka.epi & PMGT_EPI_GELU) {
+      rc = make_tmap(&tx, ka.aux, ka.N, ka.M, ka.ld_aux, 64, 128);
+      if (rc) return rc;
+    }
+    return launch_persist_cfg<A_MN, B_MN, BN_, true>(ta, tb, to, tx, ka, st);
+  }
+  return launch_persist_cfg<A_MN, B_MN, BN_, false>(ta, tb, to, tx, ka, st);
 }
 
 }  // namespace pmgt
