@@ -241,8 +241,13 @@ class PMGTTrainerModel:
         dev = self.args.device
         if self._side is None:
             self._side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("PMGT_SIDE_PRIORITY", "-1")))
-        # No wait on the main stream (that would serialise us behind the very step we want to overlap): host indices
-        # are copied on the side stream; device-resident indices must already be complete.
+        # No wait on the main stream's tail (that would serialise us behind the very step we want to overlap): host indices
+        # are copied on the side stream; device-resident indices must already be complete.  The side stream does wait for
+        # the END OF THE RUNNING STEP'S FORWARD PASS (its loss event): the encoder's persistent kernels leave a sampler CTA
+        # no room, so sampling beside them only displaces them, while the loss kernels and the head of the backward pass
+        # that follow (~0.35 ms of small grids) leave most SMs free (PMGT_PREFETCH_AFTER_FWD=0: start immediately).
+        if self._loss_event is not None and os.environ.get("PMGT_PREFETCH_AFTER_FWD", "1") != "0":
+            self._side.wait_event(self._loss_event)
         with torch.cuda.stream(self._side):
             idx = indices if isinstance(indices, torch.Tensor) else torch.as_tensor(np.asarray(indices))
             idx = idx.to(dev, non_blocking=True)
