@@ -79,6 +79,37 @@ def test_forward_asserts_like_the_reference():
         net(x, x, labels=torch.zeros(1))
 
 
+def test_prepare_inputs_layout_matches_the_reference_order():
+    """PMGT.prepare_inputs (what the trainer's prefetch builds on the side stream): the batched encoder input is
+    [targets | pairs | masked targets] (models.py:104-162 encodes them in that order), the pair offsets are the running
+    sum of num_pairs, and the NFR rows point at the masked positions inside the masked-target block of the compact
+    hidden matrix [all target positions | position 0 of every pair | all masked-target positions]."""
+    torch.manual_seed(3)
+    B, L, P = 4, 6, 3
+    net = PMGT(50, config=PMGTConfig(num_hidden_layers=1))
+    t = {"node_ids": torch.randint(2, 52, (B, L)), "attention_mask": torch.ones(B, L)}
+    num_pairs = torch.tensor([3, 1, 2, 3])
+    SP = int(num_pairs.sum())
+    p = {"node_ids": torch.randint(2, 52, (SP, L)), "attention_mask": torch.ones(SP, L)}
+    masked = net.mask_nodes(t["node_ids"], with_positions=True)
+    m_ids, m_mask, target_idx, m_pos = masked
+    prep = net.prepare_inputs(t, p, num_pairs, masked)
+    assert torch.equal(prep["ids_all"].view(-1, L), torch.cat([t["node_ids"], p["node_ids"], m_ids]))
+    assert torch.equal(prep["mask_all"], torch.cat([t["attention_mask"], p["attention_mask"], t["attention_mask"]]))
+    assert prep["pair_off"].tolist() == [0, 3, 4, 6, 9]
+    assert torch.equal(prep["target_ids"], target_idx)
+    # masked positions: row b, position 1 + j of the masked-target block that starts after B * L + SP compact rows
+    rows = prep["nfr_rows"]
+    assert rows.numel() == int(m_mask.sum()) == m_pos.shape[0]
+    for k in range(rows.numel()):
+        b, j = int(m_pos[k, 0]), int(m_pos[k, 1])
+        assert int(rows[k]) == B * L + SP + b * L + 1 + j
+        assert int(m_ids[b, 1 + j]) == 1                        # the <mask> index sits exactly there
+    # without the precomputed positions (the 3-tuple the reference-style mask_nodes returns) the result is the same
+    prep2 = net.prepare_inputs(t, p, num_pairs, masked[:3])
+    assert all(torch.equal(prep[k], prep2[k]) for k in prep)
+
+
 def test_collate_layout():
     L = 6
     item = lambda p: ((torch.arange(L), torch.ones(L)), (torch.zeros(p, L, dtype=torch.long), torch.ones(p, L)), torch.ones(p))
