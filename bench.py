@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--encoder", default="default", choices=["default", "wide"],
                     help="wide = BASELINE config 5: H=768, 12 layers, 12 heads, I=3072, 32 neighbours (L=33)")
     ap.add_argument("--batch", type=int, default=4096, help="targets per GPU per step")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling (SURVEY 8(d) config 3: global B = 8192): targets per step over ALL ranks; each "
+                         "rank takes global_batch / N of them and the line says \"scaling\": \"strong\"")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the config-2 (TG) block of the N = 1 line")
@@ -390,7 +393,9 @@ def measure(a, workload, steps, warmup, profile, rank, local_rank, ws, dev):
                 note = f"byte model invalid for this kernel (would give {frac:.2f}); not quoted"
                 frac, achieved = None, None
             roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": frac, "traffic": traffic, "algorithmic_bytes_per_launch": d["bytes"] / d["calls"],
+                    "frac": frac, "traffic": traffic,
+                    # no algorithmic byte model for the sampler (see note): null, not 0
+                    "algorithmic_bytes_per_launch": (d["bytes"] / d["calls"]) if d["bytes"] else None,
                     "peak_source": peaks["source"], "share_of_step": d["share"], "launches_per_step": d["calls"] / n_prof,
                     "avg_launch_us": 1e3 * d["ms"] / d["calls"], "tensor_tflops": d["tflops"], "note": note}
             # SURVEY 8(d) classifies the encoder layers (K3) as tensor-bound: FLOP-based fraction of the whole K3 chain
@@ -436,6 +441,11 @@ def ours(a):
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: pmgt_b200 has no CPU fallback (use --impl reference for the CPU port)")
+    scaling = "weak"
+    if a.global_batch:
+        if a.global_batch % ws:
+            raise SystemExit(f"--global-batch {a.global_batch} is not a multiple of the {ws} ranks")
+        a.batch, scaling = a.global_batch // ws, "strong"
 
     # baselines first (rank 0, N = 1 only), each in its own subprocess, so they never overlap the GPU timing
     cpu, gpu_eager = None, None
@@ -481,7 +491,7 @@ def ours(a):
         line = {
             "metric": "pmgt_pretrain_node_contexts_per_s", "value": main_res["value"], "unit": "contexts/s", "n_gpus": ws,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(a.workload, B, "gpu", a.encoder),
             "e2e": {"value": main_res["e2e_value"], "unit": "contexts/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": 4,
                     "api": "pmgt_b200.trainer.PMGTTrainerModel.train_on_indices(pinned host index batch) + .last_loss() every step"},
