@@ -12,27 +12,48 @@
 // two CTAs per SM, 96 KB ring shared by both operands):
 //   * one persistent CTA per SM whose shared memory is almost entirely the ring of the GATHERED operand
 //     (forward 5 x 32 KB: 128 rows x 256 B per stage; backward 5 x 32 KB: 32 rows x 1024 B per stage);
-//   * a warp's 16-byte cp.async copies cover 512 contiguous bytes of ONE row (two rows x 256 B in the forward kernel);
+//   * the rows are fetched by TMA (cp.async.bulk.tensor.2d tile::gather4, box {64 columns, 1 row}, 128-byte swizzle):
+//     one instruction lands 4 arbitrary table rows x 128 B as 4 consecutive rows of a UMMA slab and reports its bytes
+//     to the stage's mbarrier, so NO thread hands a stage over -- the MMA issuer wakes when the last byte lands.  An
+//     instruction occupies its issuing thread for ~120 clocks and a warp serialises its lanes, so 8 warps issue with one
+//     lane each (tools/probes/gather4_ring.cu: one warp 2.1 TB/s, 8 warps 5.8, 16 warps 6.4);
+//   * the fallback / comparison path (PMGT_GATHER_TMA=0, bit 0 forward, bit 1 backward): 128 threads x 16-byte cp.async
+//     with hand-written swizzle, a warp covering 512 contiguous bytes of ONE row, and a gather thread handing over the
+//     stage that has landed BEFORE it waits for the next free slot (the other order chains consume -> issue -> arrive
+//     into one serial loop of ~1 us per stage: 4.4 instead of 5.4 TB/s);
 //   * the dense operand (W from L2, dY) streams through a small TMA ring of its own;
-//   * a gather thread hands over the stage that has landed BEFORE it waits for the next free slot (the other order
-//     chains consume -> issue -> arrive into one serial loop of ~1 us per stage: 4.4 instead of 5.4 TB/s);
 //   * forward: two TMEM accumulators, the epilogue of tile n runs under the gather of tile n + 1;
-//     backward: every CTA owns a [128 x 512] (or 384) slice of dW in TMEM for its whole token range and flushes it once.
-// Measured on B200 (tools/bench_gather.py, 294,912 tokens, 1M-row tables, 75 % unique rows): forward 183 us visual /
-// 105 us text (5.4 / 5.1 TB/s of gathered + written bytes), dW 230 / 124 us (4.3 TB/s); pmgt_gemm_bf16 with a_rows /
-// b_rows: 237 / 160 and 245 / 144 us.  Tried and dropped: cp.async.bulk.prefetch.L2 of the rows of later stages
-// (forward 270 us, dW 378 us: the prefetches compete with the demand fetches instead of running ahead of them).
+//     backward: every CTA owns a [128 x 512] (or 384) slice of dW in TMEM for its token range and flushes it once.
+// Measured on B200 (tools/bench_gather.py, 294,912 tokens, 1M-row tables, 75 % unique rows; gathered + written bytes):
+//              TMA gather4                        cp.async
+//   forward    187 us visual / 96 us text         185 / 105 us   (5.3 / 5.5 TB/s  vs  5.3 / 5.1)
+//   dW         164 us visual / 90 us text         224 / 120 us   (6.0 / 5.9 TB/s  vs  4.4 / 4.4)
+// (pmgt_gemm_bf16 with a_rows / b_rows: 237 / 160 and 245 / 144 us.)  Tried and dropped: cp.async.bulk.prefetch.L2 of the
+// rows of later stages (forward 270 us, dW 378 us: the prefetches compete with the demand fetches).
 #include "umma.cuh"
 
 namespace pmgt {
 
 constexpr int kGpRing = 5;  // stages of the gathered operand in flight
+constexpr int kGpTmaDefault = 3;  // PMGT_GATHER_TMA when the variable is not set: TMA row gather in both kernels
 
 __device__ __forceinline__ unsigned char* gp_align1024(unsigned char* p) {
   return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
 }
 __device__ __forceinline__ void gp_cp_async_8(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+// TMA row gather: 4 arbitrary rows x one 64-column (128-byte) box of a row-major bf16 matrix land as 4 consecutive
+// 128-byte rows of a 128B-swizzled slab (dst = slab + 512 * row group; tools/probes/gather4_probe.cu).  Row indices
+// outside the tensor map read as zeros.  The instruction occupies its issuing thread for ~120 clocks and a warp
+// serialises its lanes, so the issuing lanes are spread over 8 warps (tools/probes/gather4_ring.cu).
+__device__ __forceinline__ void gp_tma_gather4(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int col, int r0, int r1,
+                                               int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(col),
+      "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
 }
 __device__ __forceinline__ void gp_stg256(void* p, const uint32_t* r) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
@@ -44,6 +65,8 @@ __device__ __forceinline__ void gp_stg256(void* p, const uint32_t* r) {
 // forward
 // ---------------------------------------------------------------------------------------------------
 constexpr int kGpFwdThreads = 320;  // warp 0: W TMA producer | 1: MMA issuer | 2-5: gather | 6-9: epilogue
+constexpr int kGpFwdTmaThreads = 448;  // TMA gather: warps 2-5 epilogue | 6-13: one issuing lane each
+constexpr int kGpTmaWarps = 8;
 constexpr int kGpFwdAStage = 32768; // 128 rows x 128 columns: two 64-column slabs
 constexpr int kGpFwdWRing = 3;
 constexpr int kGpFwdWStage = 16384; // W[128][64 columns]
@@ -75,8 +98,10 @@ __device__ __forceinline__ int gp_row_id(const long long* rows, long long src_ro
   return (r < 0 || r >= src_rows) ? -1 : (int)r;
 }
 
-__global__ void __launch_bounds__(kGpFwdThreads, 1)
-gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const GpFwdParams p) {
+template <bool TMAG>  // gathered operand by TMA tile::gather4 (true) or by 16-byte cp.async (false)
+__global__ void __launch_bounds__(TMAG ? kGpFwdTmaThreads : kGpFwdThreads, 1)
+gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_tab,
+                       const GpFwdParams p) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = gp_align1024(smem_dyn);
   unsigned char* sA = smem;
@@ -86,11 +111,12 @@ gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const GpFwdPa
   const int nstage = p.K >> 7;  // 128-column stages per tile
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGpRing; ++s) { mbar_init(&sh->a_full[s], 128u); mbar_init(&sh->a_empty[s], 1u); }
+    for (int s = 0; s < kGpRing; ++s) { mbar_init(&sh->a_full[s], TMAG ? (uint32_t)kGpTmaWarps : 128u); mbar_init(&sh->a_empty[s], 1u); }
     for (int s = 0; s < kGpFwdWRing; ++s) { mbar_init(&sh->w_full[s], 1u); mbar_init(&sh->w_empty[s], 1u); }
     for (int s = 0; s < 2; ++s) { mbar_init(&sh->acc_full[s], 1u); mbar_init(&sh->acc_empty[s], 4u); }
     fence_barrier_init();
     prefetch_tmap(&tmap_w);
+    if (TMAG) prefetch_tmap(&tmap_tab);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(256u));
@@ -147,7 +173,42 @@ gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const GpFwdPa
         umma_commit(&sh->acc_full[slot]);
       }
     }
-  } else if (warp < 6) {
+  } else if (TMAG ? (warp >= 6) : (warp < 6)) {
+   if constexpr (TMAG) {
+    // ===================== gather by TMA: warp gw owns rows 16 gw .. 16 gw + 15 of every tile; per stage its lane 0
+    // issues 4 row groups x 2 slabs (8 x 512 B) against the stage's barrier, which needs no thread to hand it over
+    const int gw = warp - 6;
+    auto load_id = [&](int tile) -> int {
+      if (lane >= 16 || tile >= p.num_tiles) return (int)p.src_rows;
+      const int r = gp_row_id(p.rows, p.src_rows, tile * 128 + gw * 16 + lane, p.T);
+      return r < 0 ? (int)p.src_rows : r;  // beyond the tensor map: zero row
+    };
+    int myid = load_id(blockIdx.x);
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nid = load_id(tile + gridDim.x);
+      int rid[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) rid[i] = __shfl_sync(0xffffffffu, myid, i);
+      if (lane == 0) {
+        for (int st = 0; st < nstage; ++st, ++g) {
+          const uint32_t s = g % kGpRing;
+          mbar_wait(&sh->a_empty[s], ((g / kGpRing) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(kGpFwdAStage / kGpTmaWarps));
+          const uint32_t base = smem_u32(sA + s * kGpFwdAStage) + (uint32_t)gw * 2048u;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              gp_tma_gather4(base + h * 16384 + q * 512, &tmap_tab, &sh->a_full[s], st * 128 + h * 64, rid[4 * q],
+                             rid[4 * q + 1], rid[4 * q + 2], rid[4 * q + 3]);
+          }
+        }
+      }
+      __syncwarp();
+      myid = nid;
+    }
+   } else {
     // ===================== gather: 16 lanes x 16 B = 256 contiguous bytes of one table row =====================
     const int t = threadIdx.x - 64;
     const int c16 = t & 15, rb = t >> 4;
@@ -194,6 +255,7 @@ gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const GpFwdPa
     cp_async_wait<0>();
     fence_proxy_async_smem();
     for (uint32_t i = (g > (uint32_t)LAG ? g - LAG : 0u); i < g; ++i) mbar_arrive(&sh->a_full[i % kGpRing]);  // the last LAG stages
+   }
   } else {
     // ===================== epilogue: + bias, bf16, one output row per thread =====================
     const int quarter = warp & 3;
@@ -242,6 +304,7 @@ gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const GpFwdPa
 // backward (weight gradient)
 // ---------------------------------------------------------------------------------------------------
 constexpr int kGpDwThreads = 192;  // warp 0: dY TMA producer | 1: MMA issuer | 2-5: gather, then the flush
+constexpr int kGpDwTmaThreads = 320;  // TMA gather: warps 2-9 one issuing lane each, warps 2-5 flush
 constexpr int kGpDwTok = 32;       // tokens per stage
 constexpr int kGpDwAStage = 8192;  // dY[32 tokens][128]: two slabs of 32 rows x 128 B
 
@@ -268,9 +331,10 @@ struct GpDwShared {
 template <int NC>
 constexpr int gp_dw_smem() { return kGpRing * (kGpDwAStage + NC * 4096) + (int)sizeof(GpDwShared) + 1024; }
 
-template <int NC>  // 64-column slabs of the table row one CTA covers (8: 512 columns, 6: 384, 4: 256)
-__global__ void __launch_bounds__(kGpDwThreads, 1)
-gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const GpDwParams p) {
+template <int NC, bool TMAG>  // NC: 64-column slabs of the table row one CTA covers (8: 512 columns, 6: 384, 4: 256)
+__global__ void __launch_bounds__(TMAG ? kGpDwTmaThreads : kGpDwThreads, 1)
+gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_tab,
+                      const GpDwParams p) {
   constexpr int kBStage = NC * 4096;
   constexpr int kPerThread = 2 * NC;  // 16-byte copies per gather thread and stage
   extern __shared__ unsigned char smem_dyn[];
@@ -286,10 +350,11 @@ gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const GpDwPar
   const int nstage = tok1 > tok0 ? (tok1 - tok0 + kGpDwTok - 1) / kGpDwTok : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGpRing; ++s) { mbar_init(&sh->full[s], 1u + 128u); mbar_init(&sh->empty[s], 1u); }
+    for (int s = 0; s < kGpRing; ++s) { mbar_init(&sh->full[s], 1u + (TMAG ? (uint32_t)kGpTmaWarps : 128u)); mbar_init(&sh->empty[s], 1u); }
     mbar_init(&sh->acc_full, 1u);
     fence_barrier_init();
     prefetch_tmap(&tmap_dy);
+    if (TMAG) prefetch_tmap(&tmap_tab);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512u));
@@ -336,6 +401,39 @@ gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const GpDwPar
       umma_commit(&sh->acc_full);
     }
   } else {
+   if constexpr (TMAG) {
+    // ===================== gather by TMA: warp gw owns tokens 4 gw .. 4 gw + 3 of every 32-token stage; its lane 0 issues
+    // one gather4 per 64-column slab.  Node ids: one load per 8 stages (lane -> stage lane / 4, token lane % 4), the
+    // next block requested before the current one is issued.
+    const int gw = warp - 2;
+    auto load_ids = [&](int blk) -> int {
+      const int st = blk * 8 + (lane >> 2);
+      const long long tok = (long long)tok0 + (long long)st * kGpDwTok + gw * 4 + (lane & 3);
+      if (st >= nstage || tok >= tok1) return (int)p.src_rows;
+      const long long r = p.rows[tok];
+      return (r < 0 || r >= p.src_rows) ? (int)p.src_rows : (int)r;  // beyond the tensor map: zero row
+    };
+    int cur = load_ids(0);
+    for (int blk = 0; blk * 8 < nstage; ++blk) {
+      const int nxt = load_ids(blk + 1);
+      const int jn = nstage - blk * 8 < 8 ? nstage - blk * 8 : 8;
+      for (int j = 0; j < jn; ++j) {
+        const int i = blk * 8 + j;
+        const int r0 = __shfl_sync(0xffffffffu, cur, 4 * j), r1 = __shfl_sync(0xffffffffu, cur, 4 * j + 1);
+        const int r2 = __shfl_sync(0xffffffffu, cur, 4 * j + 2), r3 = __shfl_sync(0xffffffffu, cur, 4 * j + 3);
+        if (lane == 0) {
+          const uint32_t s = (uint32_t)i % kGpRing;
+          mbar_wait(&sh->empty[s], (((uint32_t)i / kGpRing) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&sh->full[s], (uint32_t)(NC * 512));
+          const uint32_t base = smem_u32(sB + s * kBStage) + (uint32_t)gw * 512u;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) gp_tma_gather4(base + c * 4096, &tmap_tab, &sh->full[s], n0 + c * 64, r0, r1, r2, r3);
+        }
+        __syncwarp();
+      }
+      cur = nxt;
+    }
+   } else {
     // ===================== gather: a warp's 32 lanes cover 512 contiguous bytes of one table row =====================
     const int t = threadIdx.x - 64;
     constexpr int LAG = kGpRing - 1;
@@ -387,10 +485,11 @@ gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const GpDwPar
     cp_async_wait<0>();
     fence_proxy_async_smem();
     for (int i = (nstage > LAG ? nstage - LAG : 0); i < nstage; ++i) mbar_arrive(&sh->full[i % kGpRing]);
+   }
 
     // ---- flush: dW[m][n0 ..] += accumulator row m, 32 columns at a time, the start column rotated per CTA so that
     //      the CTAs of one column group do not hit the same L2 lines in lock-step
-    if (nstage > 0) {
+    if (nstage > 0 && warp < 6) {
       mbar_wait(&sh->acc_full, 0u);
       tcgen05_fence_after();
       const int quarter = warp & 3;
@@ -422,15 +521,22 @@ gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const GpDwPar
   }
 }
 
-template <int NC>
-static int launch_dw(const CUtensorMap& tm, const GpDwParams& kp, dim3 grid, cudaStream_t st) {
-  auto kern = gather_proj_dw_kernel<NC>;
+template <int NC, bool TMAG>
+static int launch_dw(const CUtensorMap& tm, const CUtensorMap& ttab, const GpDwParams& kp, dim3 grid, cudaStream_t st) {
+  auto kern = gather_proj_dw_kernel<NC, TMAG>;
   constexpr int smem = gp_dw_smem<NC>();
   static unsigned long long configured = 0;
   if (first_use_on_device(configured)) PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, kGpDwThreads, smem, st>>>(tm, kp);
+  kern<<<grid, TMAG ? kGpDwTmaThreads : kGpDwThreads, smem, st>>>(tm, ttab, kp);
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
+}
+
+// PMGT_GATHER_TMA (read at every call, so a test can compare both paths in one process): bit 0 = forward, bit 1 = weight
+// gradient fetch the table rows by TMA tile::gather4 instead of 16-byte cp.async
+static int gather_tma_mode() {
+  const char* e = getenv("PMGT_GATHER_TMA");
+  return e && *e ? (atoi(e) & 3) : kGpTmaDefault;
 }
 
 static int dw_slabs(long long K) { return K % 512 == 0 ? 8 : (K % 384 == 0 ? 6 : (K % 256 == 0 ? 4 : 0)); }
@@ -469,11 +575,22 @@ extern "C" int pmgt_gather_proj_fwd(const pmgt_gather_proj_args* a, void* stream
   kp.T = (int)a->T; kp.K = (int)a->K; kp.num_tiles = (int)((a->T + 127) / 128);
   kp.table = a->table; kp.ld = a->ld; kp.rows = (const long long*)a->rows; kp.src_rows = a->table_rows;
   kp.out = a->out; kp.ldo = a->ldo; kp.bias = a->bias;
-  static unsigned long long configured = 0;
-  if (first_use_on_device(configured))
-    PMGT_CHECK_CUDA(cudaFuncSetAttribute(gather_proj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGpFwdSmem));
   const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
-  gather_proj_fwd_kernel<<<grid, kGpFwdThreads, kGpFwdSmem, (cudaStream_t)stream>>>(tw, kp);
+  CUtensorMap ttab;
+  memset(&ttab, 0, sizeof(ttab));
+  if (gather_tma_mode() & 1) {
+    rc = make_tmap(&ttab, a->table, a->K, a->table_rows, a->ld, 64, 1);
+    if (rc) return rc;
+    static unsigned long long configured = 0;
+    if (first_use_on_device(configured))
+      PMGT_CHECK_CUDA(cudaFuncSetAttribute(gather_proj_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGpFwdSmem));
+    gather_proj_fwd_kernel<true><<<grid, kGpFwdTmaThreads, kGpFwdSmem, (cudaStream_t)stream>>>(tw, ttab, kp);
+  } else {
+    static unsigned long long configured = 0;
+    if (first_use_on_device(configured))
+      PMGT_CHECK_CUDA(cudaFuncSetAttribute(gather_proj_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGpFwdSmem));
+    gather_proj_fwd_kernel<false><<<grid, kGpFwdThreads, kGpFwdSmem, (cudaStream_t)stream>>>(tw, ttab, kp);
+  }
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
 }
@@ -502,7 +619,16 @@ extern "C" int pmgt_gather_proj_dw(const pmgt_gather_proj_args* a, void* stream)
   kp.dw = a->dw; kp.ld_dw = a->ld_dw;
   dim3 grid((unsigned)col_groups, (unsigned)ranges, 1);
   cudaStream_t st = (cudaStream_t)stream;
-  if (nc == 8) return launch_dw<8>(tdy, kp, grid, st);
-  if (nc == 6) return launch_dw<6>(tdy, kp, grid, st);
-  return launch_dw<4>(tdy, kp, grid, st);
+  CUtensorMap ttab;
+  memset(&ttab, 0, sizeof(ttab));
+  if (gather_tma_mode() & 2) {
+    rc = make_tmap(&ttab, a->table, a->K, a->table_rows, a->ld, 64, 1);
+    if (rc) return rc;
+    if (nc == 8) return launch_dw<8, true>(tdy, ttab, kp, grid, st);
+    if (nc == 6) return launch_dw<6, true>(tdy, ttab, kp, grid, st);
+    return launch_dw<4, true>(tdy, ttab, kp, grid, st);
+  }
+  if (nc == 8) return launch_dw<8, false>(tdy, ttab, kp, grid, st);
+  if (nc == 6) return launch_dw<6, false>(tdy, ttab, kp, grid, st);
+  return launch_dw<4, false>(tdy, ttab, kp, grid, st);
 }

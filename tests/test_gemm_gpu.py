@@ -143,6 +143,38 @@ def test_gather_proj_kernels_match_torch(T, K, nrows):
         ops.GATHER_PROJ = True
     assert (out2.float() - out.float()).abs().max() < 2e-2
 
+@pytest.mark.parametrize("T,K,nrows", [(40000, 1536, 3000), (20001, 768, 777), (4100, 256, 50)])
+def test_gather_proj_tma_and_cp_async_paths_agree(T, K, nrows, monkeypatch):
+    """csrc/gather_proj.cu fetches the table rows either with TMA tile::gather4 (one issuing lane in each of 8 warps,
+    stages completed by the copies' own byte counts) or with per-thread 16-byte cp.async (PMGT_GATHER_TMA bit 0 forward,
+    bit 1 weight gradient).  Same stage order and operands: the forward results are bit-identical, the weight gradients
+    differ by the order of the fp32 reductions only.  Ids outside the table are zero rows on both paths."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(T * 3 + K)
+    table = torch.randn(nrows, K, device="cuda", generator=g).to(BF16)
+    idx = torch.randint(0, nrows, (T,), device="cuda", dtype=torch.int64, generator=g)
+    idx[5::13] = nrows
+    idx[2::31] = -7
+    w = (torch.randn(128, K, device="cuda", generator=g) * 0.05).to(BF16)
+    b = torch.randn(128, device="cuda", generator=g) * 0.1
+    dy = (torch.randn(T, 128, device="cuda", generator=g) * 0.1).to(BF16)
+    res = {}
+    for mode in ("0", "3"):
+        monkeypatch.setenv("PMGT_GATHER_TMA", mode)
+        out = torch.full((T, 128), float("nan"), device="cuda", dtype=BF16)
+        ops.linear_fwd(table, w, b, out, rows=idx, src_rows=nrows)
+        dw = torch.zeros(128, K, device="cuda", dtype=torch.float32)
+        ops.linear_dw(dy, table, dw, rows=idx, src_rows=nrows, x_cols=K)
+        torch.cuda.synchronize()
+        res[mode] = (out, dw)
+    assert torch.equal(res["0"][0], res["3"][0])
+    _close(res["3"][1], res["0"][1], 1e-4)
+    x = table[idx.clamp(0, nrows - 1)].float()
+    x[(idx < 0) | (idx >= nrows)] = 0
+    _close(res["3"][0], x @ w.float().t() + b, 1e-2)
+    _close(res["3"][1], dy.float().t() @ x, 3e-3)
+
+
 @pytest.mark.parametrize("M,N,K", [(40037, 768, 256), (40000, 384, 320), (38000, 640, 256), (20001, 3072, 192)])
 def test_persistent_gemm_kernels_match_torch(M, N, K):
     """Large dense GEMMs take the persistent kernel (umma_gemm_persist_kernel: more tiles than one wave): 128-column
