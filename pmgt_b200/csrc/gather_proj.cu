@@ -29,12 +29,16 @@
 //   forward    187 us visual / 96 us text         185 / 105 us   (5.3 / 5.5 TB/s  vs  5.3 / 5.1)
 //   dW         164 us visual / 90 us text         224 / 120 us   (6.0 / 5.9 TB/s  vs  4.4 / 4.4)
 // (pmgt_gemm_bf16 with a_rows / b_rows: 237 / 160 and 245 / 144 us.)  Tried and dropped: cp.async.bulk.prefetch.L2 of the
-// rows of later stages (forward 270 us, dW 378 us: the prefetches compete with the demand fetches).
+// rows of later stages (forward 270 us, dW 378 us: the prefetches compete with the demand fetches).  The forward
+// kernel does not depend on its ring depths (gathered operand / W stages 5 + 3, 5 + 4, 4 + 6, 4 + 5: 184-186 us visual,
+// 94.6-95.0 us text), so neither the W stream from L2 nor the bytes in flight bound it.
 #include "umma.cuh"
 
 namespace pmgt {
 
 constexpr int kGpRing = 5;  // stages of the gathered operand in flight
+constexpr int kGpFwdWarpsDefault = 8;   // 8 warps: 184 / 95 us, 16 warps: 199 / 98 us
+constexpr int kGpDwWarpsDefault = 16;  // 8 warps: 161 / 89 us, 16 warps: 148 / 85 us (visual / text)
 constexpr int kGpTmaDefault = 3;  // PMGT_GATHER_TMA when the variable is not set: TMA row gather in both kernels
 
 __device__ __forceinline__ unsigned char* gp_align1024(unsigned char* p) {
@@ -65,10 +69,8 @@ __device__ __forceinline__ void gp_stg256(void* p, const uint32_t* r) {
 // forward
 // ---------------------------------------------------------------------------------------------------
 constexpr int kGpFwdThreads = 320;  // warp 0: W TMA producer | 1: MMA issuer | 2-5: gather | 6-9: epilogue
-constexpr int kGpFwdTmaThreads = 448;  // TMA gather: warps 2-5 epilogue | 6-13: one issuing lane each
-constexpr int kGpTmaWarps = 8;
+constexpr int gp_fwd_threads(bool tmag, int gw) { return tmag ? 64 + 128 + gw * 32 : kGpFwdThreads; }  // TMA gather: warps 2-5 epilogue | 6..: one issuing lane each
 constexpr int kGpFwdAStage = 32768; // 128 rows x 128 columns: two 64-column slabs
-constexpr int kGpFwdWRing = 3;
 constexpr int kGpFwdWStage = 16384; // W[128][64 columns]
 
 struct GpFwdParams {
@@ -82,15 +84,19 @@ struct GpFwdParams {
   const float* bias;
 };
 
+template <bool TMAG, int ARING, int WRING>
 struct GpFwdShared {
-  uint64_t a_full[kGpRing], a_empty[kGpRing];
-  uint64_t w_full[kGpFwdWRing], w_empty[kGpFwdWRing];
+  uint64_t a_full[ARING], a_empty[ARING];
+  uint64_t w_full[WRING], w_empty[WRING];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
-  int ids[4][128];
+  int ids[TMAG ? 1 : 4][TMAG ? 1 : 128];  // node ids of the tiles in flight (the TMA path keeps them in registers)
 };
 
-constexpr int kGpFwdSmem = kGpRing * kGpFwdAStage + kGpFwdWRing * kGpFwdWStage + (int)sizeof(GpFwdShared) + 1024;
+template <bool TMAG, int ARING, int WRING>
+constexpr int gp_fwd_smem() {
+  return ARING * kGpFwdAStage + WRING * kGpFwdWStage + (int)sizeof(GpFwdShared<TMAG, ARING, WRING>) + 1024;
+}
 
 __device__ __forceinline__ int gp_row_id(const long long* rows, long long src_rows, int m, int T) {
   if (m >= T) return -1;
@@ -98,21 +104,24 @@ __device__ __forceinline__ int gp_row_id(const long long* rows, long long src_ro
   return (r < 0 || r >= src_rows) ? -1 : (int)r;
 }
 
-template <bool TMAG>  // gathered operand by TMA tile::gather4 (true) or by 16-byte cp.async (false)
-__global__ void __launch_bounds__(TMAG ? kGpFwdTmaThreads : kGpFwdThreads, 1)
+// TMAG: gathered operand by TMA tile::gather4 (true) or by 16-byte cp.async (false); ARING / WRING: stages of the gathered
+// operand (32 KB each) and of W (16 KB each) in flight
+template <bool TMAG, int ARING, int WRING, int GW>
+__global__ void __launch_bounds__(gp_fwd_threads(TMAG, GW), 1)
 gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_tab,
                        const GpFwdParams p) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = gp_align1024(smem_dyn);
   unsigned char* sA = smem;
-  unsigned char* sW = smem + kGpRing * kGpFwdAStage;
-  GpFwdShared* sh = reinterpret_cast<GpFwdShared*>(sW + kGpFwdWRing * kGpFwdWStage);
+  unsigned char* sW = smem + ARING * kGpFwdAStage;
+  using Shared = GpFwdShared<TMAG, ARING, WRING>;
+  Shared* sh = reinterpret_cast<Shared*>(sW + WRING * kGpFwdWStage);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nstage = p.K >> 7;  // 128-column stages per tile
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGpRing; ++s) { mbar_init(&sh->a_full[s], TMAG ? (uint32_t)kGpTmaWarps : 128u); mbar_init(&sh->a_empty[s], 1u); }
-    for (int s = 0; s < kGpFwdWRing; ++s) { mbar_init(&sh->w_full[s], 1u); mbar_init(&sh->w_empty[s], 1u); }
+    for (int s = 0; s < ARING; ++s) { mbar_init(&sh->a_full[s], TMAG ? (uint32_t)GW : 128u); mbar_init(&sh->a_empty[s], 1u); }
+    for (int s = 0; s < WRING; ++s) { mbar_init(&sh->w_full[s], 1u); mbar_init(&sh->w_empty[s], 1u); }
     for (int s = 0; s < 2; ++s) { mbar_init(&sh->acc_full[s], 1u); mbar_init(&sh->acc_empty[s], 4u); }
     fence_barrier_init();
     prefetch_tmap(&tmap_w);
@@ -134,8 +143,8 @@ gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       const int nkb = p.K >> 6;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < nkb; ++kb, ++wi) {
-          const uint32_t s = wi % kGpFwdWRing;
-          mbar_wait_idle(&sh->w_empty[s], ((wi / kGpFwdWRing) & 1u) ^ 1u);
+          const uint32_t s = wi % WRING;
+          mbar_wait_idle(&sh->w_empty[s], ((wi / WRING) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&sh->w_full[s], (uint32_t)kGpFwdWStage);
           tma_load_2d(smem_u32(sW + s * kGpFwdWStage), &tmap_w, &sh->w_full[s], kb * 64, 0);
         }
@@ -152,13 +161,13 @@ gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + slot * 128u;
         for (int st = 0; st < nstage; ++st, ++ai) {
-          const uint32_t sa = ai % kGpRing;
-          mbar_wait(&sh->a_full[sa], (ai / kGpRing) & 1u);
+          const uint32_t sa = ai % ARING;
+          mbar_wait(&sh->a_full[sa], (ai / ARING) & 1u);
           const uint32_t a_base = smem_u32(sA + sa * kGpFwdAStage);
 #pragma unroll
           for (int h = 0; h < 2; ++h, ++wi) {
-            const uint32_t sw = wi % kGpFwdWRing;
-            mbar_wait(&sh->w_full[sw], (wi / kGpFwdWRing) & 1u);
+            const uint32_t sw = wi % WRING;
+            mbar_wait(&sh->w_full[sw], (wi / WRING) & 1u);
             tcgen05_fence_after();
             const uint32_t w_base = smem_u32(sW + sw * kGpFwdWStage);
 #pragma unroll
@@ -175,29 +184,30 @@ gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     }
   } else if (TMAG ? (warp >= 6) : (warp < 6)) {
    if constexpr (TMAG) {
-    // ===================== gather by TMA: warp gw owns rows 16 gw .. 16 gw + 15 of every tile; per stage its lane 0
-    // issues 4 row groups x 2 slabs (8 x 512 B) against the stage's barrier, which needs no thread to hand it over
+    // ===================== gather by TMA: warp gw of GW owns RPW = 128 / GW rows of every tile; per stage its lane 0
+    // issues RPW / 4 row groups x 2 slabs (512 B each) against the stage's barrier, which needs no thread to hand it over
+    constexpr int RPW = 128 / GW;
     const int gw = warp - 6;
     auto load_id = [&](int tile) -> int {
-      if (lane >= 16 || tile >= p.num_tiles) return (int)p.src_rows;
-      const int r = gp_row_id(p.rows, p.src_rows, tile * 128 + gw * 16 + lane, p.T);
+      if (lane >= RPW || tile >= p.num_tiles) return (int)p.src_rows;
+      const int r = gp_row_id(p.rows, p.src_rows, tile * 128 + gw * RPW + lane, p.T);
       return r < 0 ? (int)p.src_rows : r;  // beyond the tensor map: zero row
     };
     int myid = load_id(blockIdx.x);
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nid = load_id(tile + gridDim.x);
-      int rid[16];
+      int rid[RPW];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) rid[i] = __shfl_sync(0xffffffffu, myid, i);
+      for (int i = 0; i < RPW; ++i) rid[i] = __shfl_sync(0xffffffffu, myid, i);
       if (lane == 0) {
         for (int st = 0; st < nstage; ++st, ++g) {
-          const uint32_t s = g % kGpRing;
-          mbar_wait(&sh->a_empty[s], ((g / kGpRing) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(kGpFwdAStage / kGpTmaWarps));
-          const uint32_t base = smem_u32(sA + s * kGpFwdAStage) + (uint32_t)gw * 2048u;
+          const uint32_t s = g % ARING;
+          mbar_wait(&sh->a_empty[s], ((g / ARING) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(kGpFwdAStage / GW));
+          const uint32_t base = smem_u32(sA + s * kGpFwdAStage) + (uint32_t)(gw * RPW * 128);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < RPW / 4; ++q) {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
               gp_tma_gather4(base + h * 16384 + q * 512, &tmap_tab, &sh->a_full[s], st * 128 + h * 64, rid[4 * q],
@@ -213,7 +223,7 @@ gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     const int t = threadIdx.x - 64;
     const int c16 = t & 15, rb = t >> 4;
     const uint32_t dst_off = (uint32_t)((c16 >> 3) * 16384 + rb * 128 + (((c16 & 7) ^ rb) << 4));
-    constexpr int LAG = kGpRing - 1;
+    constexpr int LAG = ARING - 1;
     uint32_t g = 0;
     sh->ids[0][t] = gp_row_id(p.rows, p.src_rows, blockIdx.x * 128 + t, p.T);
     named_bar_sync(1, 128);
@@ -227,16 +237,16 @@ gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
 #pragma unroll
       for (int i = 0; i < 16; ++i) rid[i] = sh->ids[buf][rb + 8 * i];
       for (int st = 0; st < nstage; ++st, ++g) {
-        const uint32_t s = g % kGpRing;
+        const uint32_t s = g % ARING;
         // hand over the stage issued LAG iterations ago BEFORE waiting for a free slot: the MMA on it then overlaps the
         // address arithmetic and issue of this stage (arriving after the issue chained consume -> issue -> arrive ->
         // consume into one serial loop of ~1 us per stage, whatever the memory latency)
         if (g >= (uint32_t)LAG) {
           cp_async_wait<LAG - 1>();
           fence_proxy_async_smem();
-          mbar_arrive(&sh->a_full[(g - LAG) % kGpRing]);
+          mbar_arrive(&sh->a_full[(g - LAG) % ARING]);
         }
-        mbar_wait(&sh->a_empty[s], ((g / kGpRing) & 1u) ^ 1u);
+        mbar_wait(&sh->a_empty[s], ((g / ARING) & 1u) ^ 1u);
         const uint32_t base = smem_u32(sA + s * kGpFwdAStage) + dst_off;
         const int col = st * 128 + c16 * 8;
 #pragma unroll
@@ -254,7 +264,7 @@ gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
     }
     cp_async_wait<0>();
     fence_proxy_async_smem();
-    for (uint32_t i = (g > (uint32_t)LAG ? g - LAG : 0u); i < g; ++i) mbar_arrive(&sh->a_full[i % kGpRing]);  // the last LAG stages
+    for (uint32_t i = (g > (uint32_t)LAG ? g - LAG : 0u); i < g; ++i) mbar_arrive(&sh->a_full[i % ARING]);  // the last LAG stages
    }
   } else {
     // ===================== epilogue: + bias, bf16, one output row per thread =====================
@@ -304,7 +314,7 @@ gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
 // backward (weight gradient)
 // ---------------------------------------------------------------------------------------------------
 constexpr int kGpDwThreads = 192;  // warp 0: dY TMA producer | 1: MMA issuer | 2-5: gather, then the flush
-constexpr int kGpDwTmaThreads = 320;  // TMA gather: warps 2-9 one issuing lane each, warps 2-5 flush
+constexpr int gp_dw_threads(bool tmag, int gw) { return tmag ? 64 + gw * 32 : kGpDwThreads; }  // TMA gather: warps 2.. one issuing lane each, warps 2-5 flush
 constexpr int kGpDwTok = 32;       // tokens per stage
 constexpr int kGpDwAStage = 8192;  // dY[32 tokens][128]: two slabs of 32 rows x 128 B
 
@@ -331,8 +341,8 @@ struct GpDwShared {
 template <int NC>
 constexpr int gp_dw_smem() { return kGpRing * (kGpDwAStage + NC * 4096) + (int)sizeof(GpDwShared) + 1024; }
 
-template <int NC, bool TMAG>  // NC: 64-column slabs of the table row one CTA covers (8: 512 columns, 6: 384, 4: 256)
-__global__ void __launch_bounds__(TMAG ? kGpDwTmaThreads : kGpDwThreads, 1)
+template <int NC, bool TMAG, int GW>  // NC: 64-column slabs of the table row one CTA covers (8: 512 columns, 6: 384, 4: 256)
+__global__ void __launch_bounds__(gp_dw_threads(TMAG, GW), 1)
 gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_tab,
                       const GpDwParams p) {
   constexpr int kBStage = NC * 4096;
@@ -350,7 +360,7 @@ gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
   const int nstage = tok1 > tok0 ? (tok1 - tok0 + kGpDwTok - 1) / kGpDwTok : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGpRing; ++s) { mbar_init(&sh->full[s], 1u + (TMAG ? (uint32_t)kGpTmaWarps : 128u)); mbar_init(&sh->empty[s], 1u); }
+    for (int s = 0; s < kGpRing; ++s) { mbar_init(&sh->full[s], 1u + (TMAG ? (uint32_t)GW : 128u)); mbar_init(&sh->empty[s], 1u); }
     mbar_init(&sh->acc_full, 1u);
     fence_barrier_init();
     prefetch_tmap(&tmap_dy);
@@ -402,10 +412,11 @@ gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
     }
   } else {
    if constexpr (TMAG) {
-    // ===================== gather by TMA: warp gw owns tokens 4 gw .. 4 gw + 3 of every 32-token stage; its lane 0 issues
-    // one gather4 per 64-column slab.  Node ids: one load per 8 stages (lane -> stage lane / 4, token lane % 4), the
-    // next block requested before the current one is issued.
-    const int gw = warp - 2;
+    // ===================== gather by TMA: warp gw owns tokens 4 gw .. 4 gw + 3 of every 32-token stage (GW = 16: and one
+    // half of the slabs); its lane 0 issues one gather4 per 64-column slab.  Node ids: one load per 8 stages (lane ->
+    // stage lane / 4, token lane % 4), the next block requested before the current one is issued.
+    constexpr int kSlabs = NC / (GW / 8);  // slabs per issuing warp
+    const int gw = (warp - 2) & 7, c_first = ((warp - 2) >> 3) * kSlabs;
     auto load_ids = [&](int blk) -> int {
       const int st = blk * 8 + (lane >> 2);
       const long long tok = (long long)tok0 + (long long)st * kGpDwTok + gw * 4 + (lane & 3);
@@ -424,10 +435,11 @@ gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
         if (lane == 0) {
           const uint32_t s = (uint32_t)i % kGpRing;
           mbar_wait(&sh->empty[s], (((uint32_t)i / kGpRing) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&sh->full[s], (uint32_t)(NC * 512));
+          mbar_arrive_expect_tx(&sh->full[s], (uint32_t)(kSlabs * 512));
           const uint32_t base = smem_u32(sB + s * kBStage) + (uint32_t)gw * 512u;
 #pragma unroll
-          for (int c = 0; c < NC; ++c) gp_tma_gather4(base + c * 4096, &tmap_tab, &sh->full[s], n0 + c * 64, r0, r1, r2, r3);
+          for (int c = c_first; c < c_first + kSlabs; ++c)
+            gp_tma_gather4(base + c * 4096, &tmap_tab, &sh->full[s], n0 + c * 64, r0, r1, r2, r3);
         }
         __syncwarp();
       }
@@ -521,13 +533,25 @@ gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
   }
 }
 
-template <int NC, bool TMAG>
+template <int NC, bool TMAG, int GW>
 static int launch_dw(const CUtensorMap& tm, const CUtensorMap& ttab, const GpDwParams& kp, dim3 grid, cudaStream_t st) {
-  auto kern = gather_proj_dw_kernel<NC, TMAG>;
+  auto kern = gather_proj_dw_kernel<NC, TMAG, GW>;
   constexpr int smem = gp_dw_smem<NC>();
   static unsigned long long configured = 0;
   if (first_use_on_device(configured)) PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, TMAG ? kGpDwTmaThreads : kGpDwThreads, smem, st>>>(tm, ttab, kp);
+  kern<<<grid, gp_dw_threads(TMAG, GW), smem, st>>>(tm, ttab, kp);
+  PMGT_LAUNCH_CHECK();
+  return PMGT_OK;
+}
+
+template <bool TMAG, int ARING, int WRING, int GW>
+static int launch_fwd(const CUtensorMap& tw, const CUtensorMap& ttab, const GpFwdParams& kp, int grid, cudaStream_t st) {
+  auto kern = gather_proj_fwd_kernel<TMAG, ARING, WRING, GW>;
+  constexpr int smem = gp_fwd_smem<TMAG, ARING, WRING>();
+  static_assert(smem <= 232448, "shared memory of the forward gather kernel");
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) PMGT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, gp_fwd_threads(TMAG, GW), smem, st>>>(tw, ttab, kp);
   PMGT_LAUNCH_CHECK();
   return PMGT_OK;
 }
@@ -578,21 +602,15 @@ extern "C" int pmgt_gather_proj_fwd(const pmgt_gather_proj_args* a, void* stream
   const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
   CUtensorMap ttab;
   memset(&ttab, 0, sizeof(ttab));
+  cudaStream_t st = (cudaStream_t)stream;
   if (gather_tma_mode() & 1) {
     rc = make_tmap(&ttab, a->table, a->K, a->table_rows, a->ld, 64, 1);
     if (rc) return rc;
-    static unsigned long long configured = 0;
-    if (first_use_on_device(configured))
-      PMGT_CHECK_CUDA(cudaFuncSetAttribute(gather_proj_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGpFwdSmem));
-    gather_proj_fwd_kernel<true><<<grid, kGpFwdTmaThreads, kGpFwdSmem, (cudaStream_t)stream>>>(tw, ttab, kp);
-  } else {
-    static unsigned long long configured = 0;
-    if (first_use_on_device(configured))
-      PMGT_CHECK_CUDA(cudaFuncSetAttribute(gather_proj_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGpFwdSmem));
-    gather_proj_fwd_kernel<false><<<grid, kGpFwdThreads, kGpFwdSmem, (cudaStream_t)stream>>>(tw, ttab, kp);
+    const char* e = getenv("PMGT_GATHER_FWD_WARPS");  // measurement switch: issuing warps of the forward kernel
+    if ((e && *e ? atoi(e) : kGpFwdWarpsDefault) == 16) return launch_fwd<true, 5, 3, 16>(tw, ttab, kp, grid, st);
+    return launch_fwd<true, 5, 3, 8>(tw, ttab, kp, grid, st);
   }
-  PMGT_LAUNCH_CHECK();
-  return PMGT_OK;
+  return launch_fwd<false, 5, 3, 4>(tw, ttab, kp, grid, st);
 }
 
 extern "C" int pmgt_gather_proj_dw(const pmgt_gather_proj_args* a, void* stream) {
@@ -624,11 +642,17 @@ extern "C" int pmgt_gather_proj_dw(const pmgt_gather_proj_args* a, void* stream)
   if (gather_tma_mode() & 2) {
     rc = make_tmap(&ttab, a->table, a->K, a->table_rows, a->ld, 64, 1);
     if (rc) return rc;
-    if (nc == 8) return launch_dw<8, true>(tdy, ttab, kp, grid, st);
-    if (nc == 6) return launch_dw<6, true>(tdy, ttab, kp, grid, st);
-    return launch_dw<4, true>(tdy, ttab, kp, grid, st);
+    const char* e = getenv("PMGT_GATHER_DW_WARPS");  // measurement switch: issuing warps of the weight-gradient kernel
+    if ((e && *e ? atoi(e) : kGpDwWarpsDefault) == 16) {
+      if (nc == 8) return launch_dw<8, true, 16>(tdy, ttab, kp, grid, st);
+      if (nc == 6) return launch_dw<6, true, 16>(tdy, ttab, kp, grid, st);
+      return launch_dw<4, true, 16>(tdy, ttab, kp, grid, st);
+    }
+    if (nc == 8) return launch_dw<8, true, 8>(tdy, ttab, kp, grid, st);
+    if (nc == 6) return launch_dw<6, true, 8>(tdy, ttab, kp, grid, st);
+    return launch_dw<4, true, 8>(tdy, ttab, kp, grid, st);
   }
-  if (nc == 8) return launch_dw<8, false>(tdy, ttab, kp, grid, st);
-  if (nc == 6) return launch_dw<6, false>(tdy, ttab, kp, grid, st);
-  return launch_dw<4, false>(tdy, ttab, kp, grid, st);
+  if (nc == 8) return launch_dw<8, false, 4>(tdy, ttab, kp, grid, st);
+  if (nc == 6) return launch_dw<6, false, 4>(tdy, ttab, kp, grid, st);
+  return launch_dw<4, false, 4>(tdy, ttab, kp, grid, st);
 }
