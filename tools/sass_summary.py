@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "pmgt_b200", "libpmgt_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-MN = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "HMMA", "LDGSTS", "SYNCS", "REDG", "ATOMS", "SHFL", "MUFU"]
+MN = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "GATHER4", "UTMASTG", "UBLKCP", "HMMA", "LDGSTS", "SYNCS", "REDG", "ATOMS", "SHFL", "MUFU"]
 kern, lines = None, collections.OrderedDict()
 for ln in out.splitlines():
     m = re.search(r"Function : (\S+)", ln)
@@ -36,10 +36,11 @@ for k, ls in lines.items():
 print(f"| **total** | {sum(len(v) for v in lines.values())} | " + " | ".join(str(tot[m]) for m in MN) + " |")
 print("\n## Excerpts (first tensor-core / TMA instructions of the hot kernels)\n")
 for pat in ("linear_tile_kernel<1, 1, false, 2", "ffn_fwd_kernel", "ffn_bwd_kernel", "dw_tile_kernel<4", "umma_gemm_kernel<false, false, true",
-            "attn_mma_bwd_kernel<6, 128>", "sample_contexts_kernel<8, true>", "ln_bwd_stream_kernel<2, false>", "gather_proj_fwd_kernel", "gather_proj_dw_kernel<8>", "umma_gemm_persist_kernel<false, false, 256>", "attn_reg_bwd_kernel<64, 3>"):
+            "attn_mma_bwd_kernel<6, 128>", "sample_contexts_kernel<8, true>", "ln_bwd_stream_kernel<2, false>", "gather_proj_fwd_kernel<true", "gather_proj_dw_kernel<8, true, 16>", "umma_gemm_persist_kernel<false, false, 256>", "attn_reg_bwd_kernel<64, 3>"):
     for k, ls in lines.items():
         if pat in k:
-            idx = next((i for i, ln in enumerate(ls) if re.search(r"UTCHMMA|HMMA|UTMALDG|UBLKCP|LDG", ln)), 0)
+            first = r"GATHER4" if "gather_proj" in pat else r"UTCHMMA|HMMA|UTMALDG|UBLKCP|LDG"
+            idx = next((i for i, ln in enumerate(ls) if re.search(first, ln)), 0)
             print(f"### `{k[:100]}`\n```")
             for ln in ls[max(0, idx - 3): idx + 9]:
                 print(re.sub(r"\s+/\* 0x[0-9a-f]+ \*/\s*$", "", ln.rstrip()))
