@@ -234,8 +234,9 @@ int pmgt_embed_fuse_bwd(const pmgt_embed_args* a, void* stream);
 
 /*
  * Gather-fused feature projection for large graphs, H = 128 (csrc/gather_proj.cu): persistent tcgen05 kernels whose
- * shared-memory ring belongs to the gathered operand (>= 256 contiguous bytes of a table row per request, ~160 KB in
- * flight per SM).  Same contract as pmgt_gemm_bf16 with a_rows / b_rows (get_input_feat_embeds, pmgt/pmgt/utils.py:43-50,
+ * shared-memory ring belongs to the gathered operand (~160 KB in flight per SM); table rows are fetched by TMA
+ * tile::gather4 (environment PMGT_GATHER_TMA: bit 0 forward, bit 1 weight gradient; 0 selects the 16-byte cp.async
+ * gather kept for comparison; default 3).  Same contract as pmgt_gemm_bf16 with a_rows / b_rows (get_input_feat_embeds, pmgt/pmgt/utils.py:43-50,
  * + feat_linear, pmgt/pmgt/modeling_pmgt.py:195-198):
  *   pmgt_gather_proj_fwd  out[T][128] (bf16) = table[rows[t]][0:K] . w[128][K]^T + bias
  *   pmgt_gather_proj_dw   dw[128][K] (fp32) += dy[T][128]^T . table[rows[t]][0:K]
