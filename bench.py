@@ -429,6 +429,16 @@ def measure(a, workload, steps, warmup, profile, rank, local_rank, ws, dev):
     return res
 
 
+def resolve_batch(batch, global_batch, ws):
+    """(targets per GPU per step, "weak" | "strong"): --batch fixes the per-GPU work (weak scaling); --global-batch fixes the
+    total (one strong-scaling run at global B = 8192) and every rank takes its equal share."""
+    if not global_batch:
+        return batch, "weak"
+    if global_batch < ws or global_batch % ws:
+        raise SystemExit(f"--global-batch {global_batch} is not a positive multiple of the {ws} ranks")
+    return global_batch // ws, "strong"
+
+
 def ours(a):
     import torch
     import torch.distributed as dist
@@ -441,11 +451,7 @@ def ours(a):
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: pmgt_b200 has no CPU fallback (use --impl reference for the CPU port)")
-    scaling = "weak"
-    if a.global_batch:
-        if a.global_batch % ws:
-            raise SystemExit(f"--global-batch {a.global_batch} is not a multiple of the {ws} ranks")
-        a.batch, scaling = a.global_batch // ws, "strong"
+    a.batch, scaling = resolve_batch(a.batch, a.global_batch, ws)
 
     # baselines first (rank 0, N = 1 only), each in its own subprocess, so they never overlap the GPU timing
     cpu, gpu_eager = None, None

@@ -167,3 +167,20 @@ def test_edge_list_duplicates_follow_networkx_semantics():
                                  np.array([e[2] for e in edges]))
     assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
     assert np.allclose(a.weights, b.weights) and np.array_equal(a.cdf, b.cdf)
+
+
+def test_bench_batch_resolution_weak_and_strong():
+    """bench.py: --batch is per GPU (weak scaling); --global-batch is the total of a step, split evenly (strong scaling,
+    SURVEY 8(d) config 3)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.resolve_batch(4096, 0, 8) == (4096, "weak")
+    assert bench.resolve_batch(4096, 8192, 1) == (8192, "strong")
+    assert bench.resolve_batch(4096, 8192, 8) == (1024, "strong")
+    with pytest.raises(SystemExit):
+        bench.resolve_batch(4096, 8190, 4)
+    with pytest.raises(SystemExit):
+        bench.resolve_batch(4096, 4, 8)
