@@ -104,6 +104,94 @@ __device__ __forceinline__ int gp_row_id(const long long* rows, long long src_ro
   return (r < 0 || r >= src_rows) ? -1 : (int)r;
 }
 
+// Gathered operand of the forward kernel by TMA: gather warp gw of GW owns RPW = 128 / GW rows of every tile; per stage
+// its lane 0 issues RPW / 4 row groups x 2 slabs (512 B each) against the stage's barrier, which needs no thread to hand it over.
+template <int ARING, int GW, class Shared>
+__device__ __forceinline__ void gp_fwd_gather_tma(const CUtensorMap& tmap_tab, const GpFwdParams& p, Shared* sh, unsigned char* sA,
+                                                  int gw, int lane, int nstage) {
+  constexpr int RPW = 128 / GW;
+  auto load_id = [&](int tile) -> int {
+    if (lane >= RPW || tile >= p.num_tiles) return (int)p.src_rows;
+    const int r = gp_row_id(p.rows, p.src_rows, tile * 128 + gw * RPW + lane, p.T);
+    return r < 0 ? (int)p.src_rows : r;  // beyond the tensor map: zero row
+  };
+  int myid = load_id(blockIdx.x);
+  uint32_t g = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int nid = load_id(tile + gridDim.x);
+    int rid[RPW];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) rid[i] = __shfl_sync(0xffffffffu, myid, i);
+    if (lane == 0) {
+      for (int st = 0; st < nstage; ++st, ++g) {
+        const uint32_t s = g % ARING;
+        mbar_wait(&sh->a_empty[s], ((g / ARING) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(kGpFwdAStage / GW));
+        const uint32_t base = smem_u32(sA + s * kGpFwdAStage) + (uint32_t)(gw * RPW * 128);
+#pragma unroll
+        for (int q = 0; q < RPW / 4; ++q) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            gp_tma_gather4(base + h * 16384 + q * 512, &tmap_tab, &sh->a_full[s], st * 128 + h * 64, rid[4 * q],
+                           rid[4 * q + 1], rid[4 * q + 2], rid[4 * q + 3]);
+        }
+      }
+    }
+    __syncwarp();
+    myid = nid;
+  }
+}
+
+// Gathered operand of the forward kernel by cp.async (PMGT_GATHER_TMA bit 0 clear): 128 threads, 16 lanes x 16 B = 256
+// contiguous bytes of one table row.
+template <int ARING, class Shared>
+__device__ __forceinline__ void gp_fwd_gather_cp_async(const GpFwdParams& p, Shared* sh, unsigned char* sA, int t, int nstage) {
+  const int c16 = t & 15, rb = t >> 4;
+  const uint32_t dst_off = (uint32_t)((c16 >> 3) * 16384 + rb * 128 + (((c16 & 7) ^ rb) << 4));
+  constexpr int LAG = ARING - 1;
+  uint32_t g = 0;
+  sh->ids[0][t] = gp_row_id(p.rows, p.src_rows, blockIdx.x * 128 + t, p.T);
+  named_bar_sync(1, 128);
+  uint32_t tl = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+    const int buf = tl & 3, nbuf = (tl + 1) & 3;
+    const int next = tile + gridDim.x;
+    // the next tile's node ids are requested now and parked in the next buffer after the first stage is on its way
+    const int nid = next < p.num_tiles ? gp_row_id(p.rows, p.src_rows, next * 128 + t, p.T) : -1;
+    int rid[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) rid[i] = sh->ids[buf][rb + 8 * i];
+    for (int st = 0; st < nstage; ++st, ++g) {
+      const uint32_t s = g % ARING;
+      // hand over the stage issued LAG iterations ago BEFORE waiting for a free slot: the MMA on it then overlaps the
+      // address arithmetic and issue of this stage (arriving after the issue chained consume -> issue -> arrive ->
+      // consume into one serial loop of ~1 us per stage, whatever the memory latency)
+      if (g >= (uint32_t)LAG) {
+        cp_async_wait<LAG - 1>();
+        fence_proxy_async_smem();
+        mbar_arrive(&sh->a_full[(g - LAG) % ARING]);
+      }
+      mbar_wait(&sh->a_empty[s], ((g / ARING) & 1u) ^ 1u);
+      const uint32_t base = smem_u32(sA + s * kGpFwdAStage) + dst_off;
+      const int col = st * 128 + c16 * 8;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const bool ok = rid[i] >= 0;
+        const uint16_t* src = ok ? p.table + (long long)rid[i] * p.ld + col : p.table;
+        cp_async_16(base + i * 1024, src, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (st == 0) {
+        sh->ids[nbuf][t] = nid;
+        named_bar_sync(1, 128);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  fence_proxy_async_smem();
+  for (uint32_t i = (g > (uint32_t)LAG ? g - LAG : 0u); i < g; ++i) mbar_arrive(&sh->a_full[i % ARING]);  // the last LAG stages
+}
+
 // TMAG: gathered operand by TMA tile::gather4 (true) or by 16-byte cp.async (false); ARING / WRING: stages of the gathered
 // operand (32 KB each) and of W (16 KB each) in flight
 template <bool TMAG, int ARING, int WRING, int GW>
@@ -183,89 +271,9 @@ gather_proj_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       }
     }
   } else if (TMAG ? (warp >= 6) : (warp < 6)) {
-   if constexpr (TMAG) {
-    // ===================== gather by TMA: warp gw of GW owns RPW = 128 / GW rows of every tile; per stage its lane 0
-    // issues RPW / 4 row groups x 2 slabs (512 B each) against the stage's barrier, which needs no thread to hand it over
-    constexpr int RPW = 128 / GW;
-    const int gw = warp - 6;
-    auto load_id = [&](int tile) -> int {
-      if (lane >= RPW || tile >= p.num_tiles) return (int)p.src_rows;
-      const int r = gp_row_id(p.rows, p.src_rows, tile * 128 + gw * RPW + lane, p.T);
-      return r < 0 ? (int)p.src_rows : r;  // beyond the tensor map: zero row
-    };
-    int myid = load_id(blockIdx.x);
-    uint32_t g = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nid = load_id(tile + gridDim.x);
-      int rid[RPW];
-#pragma unroll
-      for (int i = 0; i < RPW; ++i) rid[i] = __shfl_sync(0xffffffffu, myid, i);
-      if (lane == 0) {
-        for (int st = 0; st < nstage; ++st, ++g) {
-          const uint32_t s = g % ARING;
-          mbar_wait(&sh->a_empty[s], ((g / ARING) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&sh->a_full[s], (uint32_t)(kGpFwdAStage / GW));
-          const uint32_t base = smem_u32(sA + s * kGpFwdAStage) + (uint32_t)(gw * RPW * 128);
-#pragma unroll
-          for (int q = 0; q < RPW / 4; ++q) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-              gp_tma_gather4(base + h * 16384 + q * 512, &tmap_tab, &sh->a_full[s], st * 128 + h * 64, rid[4 * q],
-                             rid[4 * q + 1], rid[4 * q + 2], rid[4 * q + 3]);
-          }
-        }
-      }
-      __syncwarp();
-      myid = nid;
-    }
-   } else {
-    // ===================== gather: 16 lanes x 16 B = 256 contiguous bytes of one table row =====================
-    const int t = threadIdx.x - 64;
-    const int c16 = t & 15, rb = t >> 4;
-    const uint32_t dst_off = (uint32_t)((c16 >> 3) * 16384 + rb * 128 + (((c16 & 7) ^ rb) << 4));
-    constexpr int LAG = ARING - 1;
-    uint32_t g = 0;
-    sh->ids[0][t] = gp_row_id(p.rows, p.src_rows, blockIdx.x * 128 + t, p.T);
-    named_bar_sync(1, 128);
-    uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
-      const int buf = tl & 3, nbuf = (tl + 1) & 3;
-      const int next = tile + gridDim.x;
-      // the next tile's node ids are requested now and parked in the next buffer after the first stage is on its way
-      const int nid = next < p.num_tiles ? gp_row_id(p.rows, p.src_rows, next * 128 + t, p.T) : -1;
-      int rid[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) rid[i] = sh->ids[buf][rb + 8 * i];
-      for (int st = 0; st < nstage; ++st, ++g) {
-        const uint32_t s = g % ARING;
-        // hand over the stage issued LAG iterations ago BEFORE waiting for a free slot: the MMA on it then overlaps the
-        // address arithmetic and issue of this stage (arriving after the issue chained consume -> issue -> arrive ->
-        // consume into one serial loop of ~1 us per stage, whatever the memory latency)
-        if (g >= (uint32_t)LAG) {
-          cp_async_wait<LAG - 1>();
-          fence_proxy_async_smem();
-          mbar_arrive(&sh->a_full[(g - LAG) % ARING]);
-        }
-        mbar_wait(&sh->a_empty[s], ((g / ARING) & 1u) ^ 1u);
-        const uint32_t base = smem_u32(sA + s * kGpFwdAStage) + dst_off;
-        const int col = st * 128 + c16 * 8;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const bool ok = rid[i] >= 0;
-          const uint16_t* src = ok ? p.table + (long long)rid[i] * p.ld + col : p.table;
-          cp_async_16(base + i * 1024, src, ok ? 16u : 0u);
-        }
-        cp_async_commit();
-        if (st == 0) {
-          sh->ids[nbuf][t] = nid;
-          named_bar_sync(1, 128);
-        }
-      }
-    }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (uint32_t i = (g > (uint32_t)LAG ? g - LAG : 0u); i < g; ++i) mbar_arrive(&sh->a_full[i % ARING]);  // the last LAG stages
-   }
+    // ===================== gather =====================
+    if constexpr (TMAG) gp_fwd_gather_tma<ARING, GW>(tmap_tab, p, sh, sA, warp - 6, lane, nstage);
+    else gp_fwd_gather_cp_async<ARING>(p, sh, sA, (int)threadIdx.x - 64, nstage);
   } else {
     // ===================== epilogue: + bias, bf16, one output row per thread =====================
     const int quarter = warp & 3;
@@ -341,12 +349,106 @@ struct GpDwShared {
 template <int NC>
 constexpr int gp_dw_smem() { return kGpRing * (kGpDwAStage + NC * 4096) + (int)sizeof(GpDwShared) + 1024; }
 
+// Gathered operand of the weight-gradient kernel by TMA: issuing warp gw = (warp - 2) % 8 owns tokens 4 gw .. 4 gw + 3 of every
+// 32-token stage (GW = 16: and one half of the slabs); its lane 0 issues one gather4 per 64-column slab.  Node ids: one
+// load per 8 stages (lane -> stage lane / 4, token lane % 4), the next block requested before the current one is issued.
+template <int NC, int GW>
+__device__ __forceinline__ void gp_dw_gather_tma(const CUtensorMap& tmap_tab, const GpDwParams& p, GpDwShared* sh, unsigned char* sB,
+                                                 int warp, int lane, int n0, int tok0, int tok1, int nstage) {
+  constexpr int kSlabs = NC / (GW / 8);  // slabs per issuing warp
+  const int gw = (warp - 2) & 7, c_first = ((warp - 2) >> 3) * kSlabs;
+  auto load_ids = [&](int blk) -> int {
+    const int st = blk * 8 + (lane >> 2);
+    const long long tok = (long long)tok0 + (long long)st * kGpDwTok + gw * 4 + (lane & 3);
+    if (st >= nstage || tok >= tok1) return (int)p.src_rows;
+    const long long r = p.rows[tok];
+    return (r < 0 || r >= p.src_rows) ? (int)p.src_rows : (int)r;  // beyond the tensor map: zero row
+  };
+  int cur = load_ids(0);
+  for (int blk = 0; blk * 8 < nstage; ++blk) {
+    const int nxt = load_ids(blk + 1);
+    const int jn = nstage - blk * 8 < 8 ? nstage - blk * 8 : 8;
+    for (int j = 0; j < jn; ++j) {
+      const int i = blk * 8 + j;
+      const int r0 = __shfl_sync(0xffffffffu, cur, 4 * j), r1 = __shfl_sync(0xffffffffu, cur, 4 * j + 1);
+      const int r2 = __shfl_sync(0xffffffffu, cur, 4 * j + 2), r3 = __shfl_sync(0xffffffffu, cur, 4 * j + 3);
+      if (lane == 0) {
+        const uint32_t s = (uint32_t)i % kGpRing;
+        mbar_wait(&sh->empty[s], (((uint32_t)i / kGpRing) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&sh->full[s], (uint32_t)(kSlabs * 512));
+        const uint32_t base = smem_u32(sB + s * (NC * 4096)) + (uint32_t)gw * 512u;
+#pragma unroll
+        for (int c = c_first; c < c_first + kSlabs; ++c)
+          gp_tma_gather4(base + c * 4096, &tmap_tab, &sh->full[s], n0 + c * 64, r0, r1, r2, r3);
+      }
+      __syncwarp();
+    }
+    cur = nxt;
+  }
+}
+
+// Gathered operand of the weight-gradient kernel by cp.async (PMGT_GATHER_TMA bit 1 clear): 128 threads, a warp's 32 lanes
+// cover 512 contiguous bytes of one table row.
+template <int NC>
+__device__ __forceinline__ void gp_dw_gather_cp_async(const GpDwParams& p, GpDwShared* sh, unsigned char* sB, int t, int n0, int tok0,
+                                                      int tok1, int nstage) {
+  constexpr int kPerThread = 2 * NC;  // 16-byte copies per gather thread and stage
+  constexpr int LAG = kGpRing - 1;
+  constexpr int kChunks = NC * 8;  // 16-byte chunks per row and stage
+  int row_of[kPerThread];
+  uint32_t dst_of[kPerThread];
+  int col_of[kPerThread];
+#pragma unroll
+  for (int j = 0; j < kPerThread; ++j) {
+    const int flat = j * 128 + t;
+    const int r = flat / kChunks, ch = flat % kChunks;
+    row_of[j] = r;
+    col_of[j] = n0 + ch * 8;
+    dst_of[j] = (uint32_t)((ch >> 3) * 4096 + r * 128 + (((ch & 7) ^ (r & 7)) << 4));
+  }
+  // node ids: thread t < 32 owns token t of every stage.  Stages [0, kGpDwIdAhead) are loaded here; inside the loop
+  // the ids of stage i + kGpDwIdAhead ride in stage i's cp.async group (no register ever waits on an id load), and
+  // become visible to the other threads through the full -> MMA -> empty barrier chain long before they are read.
+  auto id_src = [&](int stage) { return p.rows + tok0 + stage * kGpDwTok + t; };
+  auto id_ok = [&](int stage) { return tok0 + stage * kGpDwTok + t < tok1; };
+  if (t < kGpDwTok) {
+    for (int st = 0; st < kGpDwIdAhead && st < nstage; ++st) sh->ids[st % kGpDwIdRing][t] = id_ok(st) ? *id_src(st) : -1ll;
+  }
+  named_bar_sync(1, 128);
+  for (int i = 0; i < nstage; ++i) {
+    const uint32_t s = (uint32_t)i % kGpRing;
+    if (i >= LAG) {  // see the forward kernel: arrive first, then wait for the free slot
+      cp_async_wait<LAG - 1>();
+      fence_proxy_async_smem();
+      mbar_arrive(&sh->full[(i - LAG) % kGpRing]);
+    }
+    mbar_wait(&sh->empty[s], (((uint32_t)i / kGpRing) & 1u) ^ 1u);
+    const uint32_t base = smem_u32(sB + s * (NC * 4096));
+    const long long* ids = sh->ids[i % kGpDwIdRing];
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const long long r = ids[row_of[j]];
+      const bool ok = r >= 0 && r < p.src_rows;
+      const uint16_t* src = ok ? p.table + r * p.ld + col_of[j] : p.table;
+      cp_async_16(base + dst_of[j], src, ok ? 16u : 0u);
+    }
+    if (t < kGpDwTok && i + kGpDwIdAhead < nstage) {
+      long long* dst = &sh->ids[(i + kGpDwIdAhead) % kGpDwIdRing][t];
+      if (id_ok(i + kGpDwIdAhead)) gp_cp_async_8(smem_u32(dst), id_src(i + kGpDwIdAhead));
+      else *dst = -1ll;
+    }
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+  fence_proxy_async_smem();
+  for (int i = (nstage > LAG ? nstage - LAG : 0); i < nstage; ++i) mbar_arrive(&sh->full[i % kGpRing]);
+}
+
 template <int NC, bool TMAG, int GW>  // NC: 64-column slabs of the table row one CTA covers (8: 512 columns, 6: 384, 4: 256)
 __global__ void __launch_bounds__(gp_dw_threads(TMAG, GW), 1)
 gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_tab,
                       const GpDwParams p) {
   constexpr int kBStage = NC * 4096;
-  constexpr int kPerThread = 2 * NC;  // 16-byte copies per gather thread and stage
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = gp_align1024(smem_dyn);
   unsigned char* sB = smem;
@@ -411,93 +513,9 @@ gather_proj_dw_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
       umma_commit(&sh->acc_full);
     }
   } else {
-   if constexpr (TMAG) {
-    // ===================== gather by TMA: warp gw owns tokens 4 gw .. 4 gw + 3 of every 32-token stage (GW = 16: and one
-    // half of the slabs); its lane 0 issues one gather4 per 64-column slab.  Node ids: one load per 8 stages (lane ->
-    // stage lane / 4, token lane % 4), the next block requested before the current one is issued.
-    constexpr int kSlabs = NC / (GW / 8);  // slabs per issuing warp
-    const int gw = (warp - 2) & 7, c_first = ((warp - 2) >> 3) * kSlabs;
-    auto load_ids = [&](int blk) -> int {
-      const int st = blk * 8 + (lane >> 2);
-      const long long tok = (long long)tok0 + (long long)st * kGpDwTok + gw * 4 + (lane & 3);
-      if (st >= nstage || tok >= tok1) return (int)p.src_rows;
-      const long long r = p.rows[tok];
-      return (r < 0 || r >= p.src_rows) ? (int)p.src_rows : (int)r;  // beyond the tensor map: zero row
-    };
-    int cur = load_ids(0);
-    for (int blk = 0; blk * 8 < nstage; ++blk) {
-      const int nxt = load_ids(blk + 1);
-      const int jn = nstage - blk * 8 < 8 ? nstage - blk * 8 : 8;
-      for (int j = 0; j < jn; ++j) {
-        const int i = blk * 8 + j;
-        const int r0 = __shfl_sync(0xffffffffu, cur, 4 * j), r1 = __shfl_sync(0xffffffffu, cur, 4 * j + 1);
-        const int r2 = __shfl_sync(0xffffffffu, cur, 4 * j + 2), r3 = __shfl_sync(0xffffffffu, cur, 4 * j + 3);
-        if (lane == 0) {
-          const uint32_t s = (uint32_t)i % kGpRing;
-          mbar_wait(&sh->empty[s], (((uint32_t)i / kGpRing) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&sh->full[s], (uint32_t)(kSlabs * 512));
-          const uint32_t base = smem_u32(sB + s * kBStage) + (uint32_t)gw * 512u;
-#pragma unroll
-          for (int c = c_first; c < c_first + kSlabs; ++c)
-            gp_tma_gather4(base + c * 4096, &tmap_tab, &sh->full[s], n0 + c * 64, r0, r1, r2, r3);
-        }
-        __syncwarp();
-      }
-      cur = nxt;
-    }
-   } else {
-    // ===================== gather: a warp's 32 lanes cover 512 contiguous bytes of one table row =====================
-    const int t = threadIdx.x - 64;
-    constexpr int LAG = kGpRing - 1;
-    constexpr int kChunks = NC * 8;  // 16-byte chunks per row and stage
-    int row_of[kPerThread];
-    uint32_t dst_of[kPerThread];
-    int col_of[kPerThread];
-#pragma unroll
-    for (int j = 0; j < kPerThread; ++j) {
-      const int flat = j * 128 + t;
-      const int r = flat / kChunks, ch = flat % kChunks;
-      row_of[j] = r;
-      col_of[j] = n0 + ch * 8;
-      dst_of[j] = (uint32_t)((ch >> 3) * 4096 + r * 128 + (((ch & 7) ^ (r & 7)) << 4));
-    }
-    // node ids: thread t < 32 owns token t of every stage.  Stages [0, kGpDwIdAhead) are loaded here; inside the loop
-    // the ids of stage i + kGpDwIdAhead ride in stage i's cp.async group (no register ever waits on an id load), and
-    // become visible to the other threads through the full -> MMA -> empty barrier chain long before they are read.
-    auto id_src = [&](int stage) { return p.rows + tok0 + stage * kGpDwTok + t; };
-    auto id_ok = [&](int stage) { return tok0 + stage * kGpDwTok + t < tok1; };
-    if (t < kGpDwTok) {
-      for (int st = 0; st < kGpDwIdAhead && st < nstage; ++st) sh->ids[st % kGpDwIdRing][t] = id_ok(st) ? *id_src(st) : -1ll;
-    }
-    named_bar_sync(1, 128);
-    for (int i = 0; i < nstage; ++i) {
-      const uint32_t s = (uint32_t)i % kGpRing;
-      if (i >= LAG) {  // see the forward kernel: arrive first, then wait for the free slot
-        cp_async_wait<LAG - 1>();
-        fence_proxy_async_smem();
-        mbar_arrive(&sh->full[(i - LAG) % kGpRing]);
-      }
-      mbar_wait(&sh->empty[s], (((uint32_t)i / kGpRing) & 1u) ^ 1u);
-      const uint32_t base = smem_u32(sB + s * kBStage);
-      const long long* ids = sh->ids[i % kGpDwIdRing];
-#pragma unroll
-      for (int j = 0; j < kPerThread; ++j) {
-        const long long r = ids[row_of[j]];
-        const bool ok = r >= 0 && r < p.src_rows;
-        const uint16_t* src = ok ? p.table + r * p.ld + col_of[j] : p.table;
-        cp_async_16(base + dst_of[j], src, ok ? 16u : 0u);
-      }
-      if (t < kGpDwTok && i + kGpDwIdAhead < nstage) {
-        long long* dst = &sh->ids[(i + kGpDwIdAhead) % kGpDwIdRing][t];
-        if (id_ok(i + kGpDwIdAhead)) gp_cp_async_8(smem_u32(dst), id_src(i + kGpDwIdAhead));
-        else *dst = -1ll;
-      }
-      cp_async_commit();
-    }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int i = (nstage > LAG ? nstage - LAG : 0); i < nstage; ++i) mbar_arrive(&sh->full[i % kGpRing]);
-   }
+    // ===================== gather (warps 2..), then the flush (warps 2-5) =====================
+    if constexpr (TMAG) gp_dw_gather_tma<NC, GW>(tmap_tab, p, sh, sB, warp, lane, n0, tok0, tok1, nstage);
+    else gp_dw_gather_cp_async<NC>(p, sh, sB, (int)threadIdx.x - 64, n0, tok0, tok1, nstage);
 
     // ---- flush: dW[m][n0 ..] += accumulator row m, 32 columns at a time, the start column rotated per CTA so that
     //      the CTAs of one column group do not hit the same L2 lines in lock-step
