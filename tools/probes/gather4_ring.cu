@@ -3,6 +3,9 @@
 // gather_proj.cu?  The counterpart of ring_probe.cu (same table, ids, token count), which does it with 128 threads x
 // 16-byte cp.async.  A stage = ROWS rows x SLABS slabs of 64 bf16 columns (128 B); one gather4 instruction brings 4 rows
 // x 128 B, so a stage is ROWS/4 x SLABS instructions spread over the warp's lanes.
+// `./gather4_ring 3072` varies the stage geometry / ring depth / CTAs per SM with one issuing warp (k_g4); `./gather4_ring 3072
+// sweep` varies the number of issuing warps and lanes (k_g4w) -- the result that shaped gather_proj.cu: an instruction holds
+// its issuing thread for ~120 clocks and a warp serialises its lanes, so the gather needs 8-16 warps with one lane each.
 // build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o gather4_ring gather4_ring.cu
 #include <cstdio>
 #include <cstdlib>
