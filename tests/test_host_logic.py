@@ -184,3 +184,33 @@ def test_bench_batch_resolution_weak_and_strong():
         bench.resolve_batch(4096, 8190, 4)
     with pytest.raises(SystemExit):
         bench.resolve_batch(4096, 4, 8)
+
+
+@pytest.mark.parametrize("n,batch,ws", [(1000, 128, 1), (1000, 128, 4), (130, 64, 8), (64, 64, 2), (10, 64, 4)])
+def test_epoch_batches_cover_every_target_once_and_keep_ranks_in_step(n, batch, ws):
+    """trainer.epoch_batches: the reference's DataLoader keeps the partial last batch (shuffle=True, drop_last=False,
+    trainer.py:90-103).  Over the ranks an epoch visits every training target, full global batches exactly once; every
+    rank runs the same number of steps (the gradient exchange is collective); the shards of one step never overlap
+    except for the one target a rank with an empty tail share repeats."""
+    from pmgt_b200 import trainer
+    perm = trainer.epoch_permutation(n, 0, 3)
+    assert sorted(perm.tolist()) == list(range(n))
+    per_rank = [trainer.epoch_batches(n, batch, r, ws, perm) for r in range(ws)]
+    steps = {len(b) for b in per_rank}
+    assert len(steps) == 1
+    n_steps = steps.pop()
+    full = n // (batch * ws)
+    assert n_steps == full + (1 if n % (batch * ws) else 0)
+    seen = []
+    for step in range(n_steps):
+        shards = [per_rank[r][step] for r in range(ws)]
+        assert all(len(s) > 0 for s in shards)
+        if step < full:
+            assert all(len(s) == batch for s in shards)
+            cat = np.concatenate(shards)
+            assert len(set(cat.tolist())) == batch * ws
+            np.testing.assert_array_equal(cat, perm[step * batch * ws:(step + 1) * batch * ws])
+        seen.extend(np.concatenate(shards).tolist())
+    assert set(seen) == set(range(n))
+    # only the tail step may repeat a target (ranks without a share of a short tail)
+    assert len(seen) - n <= max(0, ws - 1)
