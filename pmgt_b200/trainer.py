@@ -102,7 +102,7 @@ def check_args(args: AttrDict) -> None:
         # computes in bf16 with fp32 accumulation / statistics, there is no fp16 path to switch on
         raise ValueError("mp_enabled (fp16 autocast) is not supported: pmgt_b200 always runs bf16 tensor-core math with "
                          "fp32 accumulation")
-    if int(args.accumulation_step or 1) < 1:
+    if args.accumulation_step is not None and int(args.accumulation_step) < 1:
         raise ValueError("accumulation_step must be >= 1")
 
 

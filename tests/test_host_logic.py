@@ -214,3 +214,21 @@ def test_epoch_batches_cover_every_target_once_and_keep_ranks_in_step(n, batch, 
     assert set(seen) == set(range(n))
     # only the tail step may repeat a target (ranks without a share of a short tail)
     assert len(seen) - n <= max(0, ws - 1)
+
+
+def test_trainer_check_args_error_behaviour_like_the_reference():
+    """trainer.check_args (reference trainer.py:213-218 + base_trainer.py check_args): same refusals, plus the two flags
+    this implementation cannot honour (fp16 autocast, LR schedulers) raise instead of being ignored; init_run refuses to
+    train without a CUDA device (no CPU fallback)."""
+    from pmgt_b200 import trainer
+    trainer.check_args(trainer.make_args(synthetic="TG"))
+    trainer.check_args(trainer.make_args(synthetic="TG", accumulation_step=4))
+    for bad in (dict(early_criterion="ndcg"), dict(model_name="NCF"), dict(optim="sgd"), dict(scheduler_type="linear"),
+                dict(mp_enabled=True), dict(accumulation_step=0)):
+        with pytest.raises(ValueError):
+            trainer.check_args(trainer.make_args(synthetic="TG", **bad))
+    with pytest.raises(ValueError):
+        trainer.check_args(trainer.make_args(dataset_name="Amazon"))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            trainer.init_run(trainer.make_args(synthetic="TG"))
